@@ -1,0 +1,624 @@
+// mf_api.cu -- extern "C" ABI of libmicroflow_cuda.so (include/microflow_cuda.h).
+//
+// The product path has NO CPU fallback: without a usable CUDA device every compute entry point fails with
+// MF_ERR_NO_DEVICE (only MF_FLAG_HOST_ONLY models -- parse + preprocess, i.e. the proc-macro's job -- work).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/microflow_cuda.h"
+#include "mf_engine.h"
+
+using namespace mf;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define MF_CUDA(expr)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess) return fail(MF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    uint8_t *act[2] = {nullptr, nullptr};
+    uint8_t *in_q = nullptr;
+    float *in_f32 = nullptr;
+    float *out_f32 = nullptr;
+    uint8_t *out_q = nullptr;
+    uint8_t *logits = nullptr;
+};
+
+}  // namespace
+
+struct mf_model {
+    ModelSpec spec;
+    std::vector<LayerExec> layers;
+    uint32_t flags = 0;
+    bool host_only = false;
+    int device = 0, num_sms = 148;
+    uint8_t *d_blob = nullptr;
+    size_t blob_bytes = 0;
+    size_t chunk = 0;
+    Slot slot[2];
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;   // (layers + 1) per profiled chunk
+    size_t prof_chunks = 0;
+    uint64_t launches = 0;
+    int softmax_tail = -1;                  // index of a trailing softmax layer (its input = "logits")
+    std::mutex mu;
+};
+
+namespace {
+
+int check_device(int *count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        if (count) *count = 0;
+        return fail(MF_ERR_NO_DEVICE, std::string("no usable CUDA device (") + cudaGetErrorString(e) +
+                                          "): libmicroflow_cuda has no CPU fallback; only MF_FLAG_HOST_ONLY models can be created");
+    }
+    if (count) *count = n;
+    return MF_OK;
+}
+
+void free_slot(Slot &s) {
+    if (s.stream) cudaStreamDestroy(s.stream);
+    for (auto *p : {(void *)s.act[0], (void *)s.act[1], (void *)s.in_q, (void *)s.in_f32, (void *)s.out_f32, (void *)s.out_q, (void *)s.logits})
+        if (p) cudaFree(p);
+    s = Slot{};
+}
+
+int alloc_slot(mf_model *m, Slot &s) {
+    const size_t c = m->chunk;
+    MF_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    MF_CUDA(cudaMalloc(&s.act[0], c * m->spec.max_elems));
+    MF_CUDA(cudaMalloc(&s.act[1], c * m->spec.max_elems));
+    MF_CUDA(cudaMalloc(&s.in_q, c * m->spec.in_elems));
+    MF_CUDA(cudaMalloc(&s.in_f32, c * m->spec.in_elems * sizeof(float)));
+    MF_CUDA(cudaMalloc(&s.out_f32, c * m->spec.out_elems * sizeof(float)));
+    MF_CUDA(cudaMalloc(&s.out_q, c * m->spec.out_elems));
+    MF_CUDA(cudaMalloc(&s.logits, c * m->spec.max_elems));
+    return MF_OK;
+}
+
+// Runs all layers for `n` <= chunk samples.  d_in: quantized input.  Outputs (each optional): dequantized f32, final
+// quantized bytes, and the input of the trailing softmax.  layer_outs (optional): device->host copies of every layer.
+int run_chunk(mf_model *m, Slot &s, const uint8_t *d_in, size_t n, float *d_out_f32, uint8_t *d_out_q, uint8_t *d_logits, cudaStream_t st,
+              cudaEvent_t *prof, void *const *layer_outs_host, size_t sample_offset) {
+    const uint8_t *cur = d_in;
+    int flip = 0;
+    if (prof) MF_CUDA(cudaEventRecord(prof[0], st));
+    for (size_t i = 0; i < m->layers.size(); ++i) {
+        const LayerExec &L = m->layers[i];
+        if (d_logits && (int)i == m->softmax_tail)
+            MF_CUDA(cudaMemcpyAsync(d_logits, cur, n * L.spec.in_elems, cudaMemcpyDeviceToDevice, st));
+        if (L.kernel != Kernel::None) {
+            uint8_t *dst = s.act[flip];
+            std::string err;
+            cudaError_t e = L.run(cur, dst, (long long)n, m->num_sms, st, &err);
+            if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string(kernel_name(L.kernel)) + " launch failed: " + cudaGetErrorString(e) + " " + err);
+            m->launches += 1;
+            cur = dst;
+            flip ^= 1;
+        }
+        if (layer_outs_host && layer_outs_host[i])
+            MF_CUDA(cudaMemcpyAsync((uint8_t *)layer_outs_host[i] + sample_offset * L.spec.out_elems, cur, n * L.spec.out_elems, cudaMemcpyDeviceToHost, st));
+        if (prof) MF_CUDA(cudaEventRecord(prof[i + 1], st));
+    }
+    const size_t total = n * m->spec.out_elems;
+    if (d_out_f32) {
+        cudaError_t e = launch_dequantize(cur, d_out_f32, total, m->spec.out_scale, (float)m->spec.out_zp, m->spec.is_u8_out, st);   // src/tensor.rs:89-92
+        if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("dequantize launch failed: ") + cudaGetErrorString(e));
+        m->launches += 1;
+    }
+    if (d_out_q) MF_CUDA(cudaMemcpyAsync(d_out_q, cur, total, cudaMemcpyDeviceToDevice, st));
+    return MF_OK;
+}
+
+int need_device(const mf_model *m) {
+    if (!m) return fail(MF_ERR_INVALID_ARG, "null model");
+    if (m->host_only) return fail(MF_ERR_NO_DEVICE, "model was created with MF_FLAG_HOST_ONLY: it has no device state and cannot predict");
+    return MF_OK;
+}
+
+// host-buffer batched path: chunks alternate between two streams so H2D(c+1) overlaps compute(c) and D2H(c-1)
+int predict_many_host(mf_model *m, const void *in_q, const float *in_f32, size_t n, float *out_f32, void *out_q, void *logits) {
+    int rc = need_device(m);
+    if (rc) return rc;
+    if ((!in_q && !in_f32) || (!out_f32 && !out_q)) return fail(MF_ERR_INVALID_ARG, "null input or output buffer");
+    if (logits && m->softmax_tail < 0) return fail(MF_ERR_INVALID_ARG, "model has no softmax layer: no logits to return");
+    std::lock_guard<std::mutex> lock(m->mu);
+    MF_CUDA(cudaSetDevice(m->device));
+    const size_t ie = m->spec.in_elems, oe = m->spec.out_elems;
+    const size_t le = m->softmax_tail >= 0 ? m->layers[(size_t)m->softmax_tail].spec.in_elems : 0;
+    size_t ci = 0;
+    for (size_t off = 0; off < n; off += m->chunk, ++ci) {
+        Slot &s = m->slot[ci & 1];
+        const size_t cn = std::min(m->chunk, n - off);
+        if (in_f32) {   // predict(): quantize the f32 input on the device (src/tensor.rs:80-86, :246-256)
+            MF_CUDA(cudaMemcpyAsync(s.in_f32, in_f32 + off * ie, cn * ie * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+            cudaError_t e = launch_quantize(s.in_f32, s.in_q, cn * ie, m->spec.in_scale, (float)m->spec.in_zp, m->spec.is_u8_in, s.stream);
+            if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("quantize launch failed: ") + cudaGetErrorString(e));
+            m->launches += 1;
+        } else {
+            MF_CUDA(cudaMemcpyAsync(s.in_q, (const uint8_t *)in_q + off * ie, cn * ie, cudaMemcpyHostToDevice, s.stream));
+        }
+        rc = run_chunk(m, s, s.in_q, cn, out_f32 ? s.out_f32 : nullptr, out_q ? s.out_q : nullptr, logits ? s.logits : nullptr, s.stream, nullptr, nullptr, 0);
+        if (rc) return rc;
+        if (out_f32) MF_CUDA(cudaMemcpyAsync(out_f32 + off * oe, s.out_f32, cn * oe * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        if (out_q) MF_CUDA(cudaMemcpyAsync((uint8_t *)out_q + off * oe, s.out_q, cn * oe, cudaMemcpyDeviceToHost, s.stream));
+        if (logits) MF_CUDA(cudaMemcpyAsync((uint8_t *)logits + off * le, s.logits, cn * le, cudaMemcpyDeviceToHost, s.stream));
+    }
+    MF_CUDA(cudaStreamSynchronize(m->slot[0].stream));
+    MF_CUDA(cudaStreamSynchronize(m->slot[1].stream));
+    return MF_OK;
+}
+
+int create_model(const uint8_t *buf, size_t len, const mf_options *opt, mf_model **out) {
+    if (!out) return fail(MF_ERR_INVALID_ARG, "null output pointer");
+    *out = nullptr;
+    mf_options o{};
+    o.struct_size = sizeof(mf_options);
+    o.device = -1;
+    if (opt) {
+        if (opt->struct_size < sizeof(mf_options)) return fail(MF_ERR_INVALID_ARG, "mf_options.struct_size too small");
+        o = *opt;
+    }
+    std::unique_ptr<mf_model, void (*)(mf_model *)> m(new mf_model(), mf_model_destroy);
+    std::string err;
+    int rc = parse_tflite(buf, len, m->spec, err);
+    if (rc != MF_OK) return fail(rc, err);
+    m->flags = o.flags;
+    m->host_only = (o.flags & MF_FLAG_HOST_ONLY) != 0;
+    bool have_device = false;
+    if (!m->host_only) {
+        int n = 0;
+        rc = check_device(&n);
+        if (rc) return rc;
+        if (o.device >= n) return fail(MF_ERR_INVALID_ARG, "device ordinal out of range");
+        if (o.device >= 0) MF_CUDA(cudaSetDevice(o.device));
+        MF_CUDA(cudaGetDevice(&m->device));
+        cudaDeviceProp prop{};
+        MF_CUDA(cudaGetDeviceProperties(&prop, m->device));
+        m->num_sms = prop.multiProcessorCount;
+        if (prop.major != 10) return fail(MF_ERR_NO_DEVICE, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                                              ": this library is built for sm_100a (B200) only");
+        have_device = true;
+    }
+    const int impl = (o.flags & MF_FLAG_FORCE_GENERIC) ? 1 : ((o.flags & MF_FLAG_NO_TENSOR_CORE) ? 2 : 0);
+    BlobBuilder bb;
+    m->layers.resize(m->spec.layers.size());
+    for (size_t i = 0; i < m->layers.size(); ++i) {
+        m->layers[i].spec = m->spec.layers[i];
+        m->layers[i].plan(bb, impl, have_device);
+        if (m->spec.layers[i].op == MF_OP_SOFTMAX && i + 1 == m->layers.size()) m->softmax_tail = (int)i;
+    }
+    if (m->softmax_tail < 0)
+        for (size_t i = m->layers.size(); i-- > 0;) {
+            if (m->spec.layers[i].op == MF_OP_RESHAPE) continue;
+            if (m->spec.layers[i].op == MF_OP_SOFTMAX) m->softmax_tail = (int)i;
+            break;
+        }
+    m->blob_bytes = bb.bytes().size();
+    if (have_device) {
+        m->chunk = o.chunk ? o.chunk : 2048;
+        if (m->blob_bytes) {
+            MF_CUDA(cudaMalloc(&m->d_blob, m->blob_bytes));
+            MF_CUDA(cudaMemcpy(m->d_blob, bb.bytes().data(), m->blob_bytes, cudaMemcpyHostToDevice));
+        }
+        for (auto &L : m->layers)
+            if (!L.resolve(m->d_blob, &err)) return fail(MF_ERR_CUDA, err);
+        for (int k = 0; k < 2; ++k) {
+            rc = alloc_slot(m.get(), m->slot[k]);
+            if (rc) return rc;
+        }
+    }
+    *out = m.release();
+    return MF_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int mf_abi_version(void) { return MF_ABI_VERSION; }
+const char *mf_last_error(void) { return g_err.c_str(); }
+const char *mf_status_string(int s) {
+    switch (s) {
+        case MF_OK: return "ok";
+        case MF_ERR_FILE: return "model file not found";
+        case MF_ERR_INVALID_MODEL: return "invalid TensorFlow Lite model";
+        case MF_ERR_UNSUPPORTED_TYPE: return "unsupported tensor type";
+        case MF_ERR_UNSUPPORTED_RANK: return "unsupported tensor rank";
+        case MF_ERR_UNSUPPORTED_OP: return "unsupported operator";
+        case MF_ERR_UNSUPPORTED_ACTIVATION: return "unsupported fused activation";
+        case MF_ERR_UNSUPPORTED_SHAPE: return "unsupported shape";
+        case MF_ERR_VIEW_OUT_OF_BOUNDS: return "VALID view out of bounds";
+        case MF_ERR_INVALID_ARG: return "invalid argument";
+        case MF_ERR_NO_DEVICE: return "no CUDA device (no CPU fallback)";
+        case MF_ERR_CUDA: return "CUDA error";
+        case MF_ERR_NONFINITE_CONSTANT: return "non-finite requantization constant";
+    }
+    return "unknown status";
+}
+int mf_device_count(int *count) { return check_device(count); }
+
+int mf_model_create_from_tflite(const void *buf, size_t len, const mf_options *opt, mf_model **out) {
+    if (!buf) return fail(MF_ERR_INVALID_ARG, "null model buffer");
+    return create_model((const uint8_t *)buf, len, opt, out);
+}
+int mf_model_create_from_file(const char *path, const mf_options *opt, mf_model **out) {
+    if (!path) return fail(MF_ERR_INVALID_ARG, "null path");
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return fail(MF_ERR_FILE, std::string("couldn't find '") + path + "', please provide a valid path");   // lib.rs:50-55
+    std::vector<char> data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    return create_model((const uint8_t *)data.data(), data.size(), opt, out);
+}
+void mf_model_destroy(mf_model *m) {
+    if (!m) return;
+    if (!m->host_only) {
+        cudaSetDevice(m->device);
+        cudaDeviceSynchronize();
+        for (auto e : m->prof_events) cudaEventDestroy(e);
+        free_slot(m->slot[0]);
+        free_slot(m->slot[1]);
+        if (m->d_blob) cudaFree(m->d_blob);
+    }
+    delete m;
+}
+
+int mf_model_io_info(const mf_model *m, mf_tensor_info *in, mf_tensor_info *out) {
+    if (!m) return fail(MF_ERR_INVALID_ARG, "null model");
+    if (in) {
+        *in = mf_tensor_info{};
+        in->rank = m->spec.in_rank;
+        for (int i = 0; i < 4; ++i) in->dims[i] = m->spec.in_dims[i];
+        in->dtype = m->spec.is_u8_in ? MF_DTYPE_U8 : MF_DTYPE_I8;
+        in->scale = m->spec.in_scale; in->zero_point = m->spec.in_zp; in->elems = m->spec.in_elems;
+    }
+    if (out) {
+        *out = mf_tensor_info{};
+        out->rank = m->spec.out_rank;
+        for (int i = 0; i < 4; ++i) out->dims[i] = m->spec.out_dims[i];
+        out->dtype = m->spec.is_u8_out ? MF_DTYPE_U8 : MF_DTYPE_I8;
+        out->scale = m->spec.out_scale; out->zero_point = m->spec.out_zp; out->elems = m->spec.out_elems;
+    }
+    return MF_OK;
+}
+int mf_model_num_layers(const mf_model *m) { return m ? (int)m->layers.size() : 0; }
+int mf_model_layer_info(const mf_model *m, int i, mf_layer_info *o) {
+    if (!m || !o || i < 0 || (size_t)i >= m->layers.size()) return fail(MF_ERR_INVALID_ARG, "bad layer index");
+    const LayerExec &E = m->layers[(size_t)i];
+    const LayerSpec &L = E.spec;
+    *o = mf_layer_info{};
+    o->op = L.op;
+    for (int k = 0; k < 4; ++k) { o->in_dims[k] = L.in_dims[k]; o->out_dims[k] = L.out_dims[k]; }
+    o->in_rank = L.in_rank; o->out_rank = L.out_rank;
+    o->kh = L.KH; o->kw = L.KW; o->stride_h = L.sh; o->stride_w = L.sw; o->padding = L.pad; o->activation = L.act;
+    o->in_zero_point = L.in_zp; o->out_zero_point = L.out_zp; o->in_scale = L.in_scale; o->out_scale = L.out_scale;
+    o->act_lo = L.act_lo; o->act_hi = L.act_hi;
+    o->n_c0 = (int)L.c0.size(); o->n_c1 = (int)L.c1.size();
+    o->macs = L.macs; o->bytes = E.alg_bytes; o->weight_bytes = E.weight_bytes;
+    std::snprintf(o->kernel, sizeof o->kernel, "%s", m->host_only ? "" : kernel_name(E.kernel));
+    return MF_OK;
+}
+int mf_model_layer_constants(const mf_model *m, int i, float *c0, float *c1, int32_t *c2, int32_t *c3, int cap) {
+    if (!m || i < 0 || (size_t)i >= m->layers.size() || cap < 0) return fail(MF_ERR_INVALID_ARG, "bad layer index");
+    const LayerSpec &L = m->layers[(size_t)i].spec;
+    for (size_t k = 0; c0 && k < L.c0.size() && k < (size_t)cap; ++k) c0[k] = L.c0[k];
+    for (size_t k = 0; c1 && k < L.c1.size() && k < (size_t)cap; ++k) c1[k] = L.c1[k];
+    for (size_t k = 0; c2 && k < L.c2.size() && k < (size_t)cap; ++k) c2[k] = L.c2[k];
+    if (c3) *c3 = L.c3;
+    return MF_OK;
+}
+int mf_model_dump(const mf_model *m, const char *path) {
+    if (!m || !path) return fail(MF_ERR_INVALID_ARG, "null argument");
+    FILE *f = std::fopen(path, "w");
+    if (!f) return fail(MF_ERR_FILE, std::string("cannot open '") + path + "' for writing");
+    std::fprintf(f, "# microflow_cuda model dump (equivalent of target/microflow-expansion.rs)\n");
+    std::fprintf(f, "input: rank %d dims [%d,%d,%d,%d] scale %.9g zp %d %s\n", m->spec.in_rank, m->spec.in_dims[0], m->spec.in_dims[1], m->spec.in_dims[2],
+                 m->spec.in_dims[3], m->spec.in_scale, m->spec.in_zp, m->spec.is_u8_in ? "u8" : "i8");
+    for (size_t i = 0; i < m->layers.size(); ++i) {
+        const LayerExec &E = m->layers[i];
+        const LayerSpec &L = E.spec;
+        std::fprintf(f, "layer %zu: op %d in [%d,%d,%d,%d] out [%d,%d,%d,%d] k %dx%d s %dx%d pad %d act %d izp %d ozp %d is %.9g os %.9g clamp [%d,%d] kernel %s%s%s\n", i,
+                     L.op, L.in_dims[0], L.in_dims[1], L.in_dims[2], L.in_dims[3], L.out_dims[0], L.out_dims[1], L.out_dims[2], L.out_dims[3], L.KH, L.KW, L.sh,
+                     L.sw, L.pad, L.act, L.in_zp, L.out_zp, L.in_scale, L.out_scale, L.act_lo, L.act_hi, m->host_only ? "-" : kernel_name(E.kernel),
+                     E.why_not_fast.empty() ? "" : "  # ", E.why_not_fast.c_str());
+        std::fprintf(f, "  c0:");
+        for (float v : L.c0) std::fprintf(f, " %.9g", v);
+        std::fprintf(f, "\n  c1:");
+        for (float v : L.c1) std::fprintf(f, " %.9g", v);
+        if (!L.c2.empty()) {
+            std::fprintf(f, "\n  c2:");
+            for (int32_t v : L.c2) std::fprintf(f, " %d", v);
+            std::fprintf(f, "\n  c3: %d", L.c3);
+        }
+        std::fprintf(f, "\n");
+    }
+    std::fprintf(f, "output: rank %d dims [%d,%d,%d,%d] scale %.9g zp %d\n", m->spec.out_rank, m->spec.out_dims[0], m->spec.out_dims[1], m->spec.out_dims[2],
+                 m->spec.out_dims[3], m->spec.out_scale, m->spec.out_zp);
+    std::fclose(f);
+    return MF_OK;
+}
+
+int mf_predict(mf_model *m, const float *in, float *out) { return predict_many_host(m, nullptr, in, 1, out, nullptr, nullptr); }
+int mf_predict_quantized(mf_model *m, const void *in_q, float *out) { return predict_many_host(m, in_q, nullptr, 1, out, nullptr, nullptr); }
+int mf_predict_many(mf_model *m, const float *in, size_t n, float *out) { return predict_many_host(m, nullptr, in, n, out, nullptr, nullptr); }
+int mf_predict_many_quantized(mf_model *m, const void *in_q, size_t n, float *out) { return predict_many_host(m, in_q, nullptr, n, out, nullptr, nullptr); }
+int mf_predict_many_logits(mf_model *m, const void *in_q, size_t n, void *out_q, void *logits_q) {
+    if (!out_q) return fail(MF_ERR_INVALID_ARG, "null out_q");
+    return predict_many_host(m, in_q, nullptr, n, nullptr, out_q, logits_q);
+}
+
+int mf_predict_many_device(mf_model *m, const void *d_in_q, size_t n, float *d_out_f32, void *d_out_q, void *stream) {
+    int rc = need_device(m);
+    if (rc) return rc;
+    if (!d_in_q) return fail(MF_ERR_INVALID_ARG, "null device input");
+    std::lock_guard<std::mutex> lock(m->mu);
+    MF_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : m->slot[0].stream;
+    const size_t ie = m->spec.in_elems, oe = m->spec.out_elems;
+    size_t nchunks = (n + m->chunk - 1) / m->chunk;
+    if (m->profiling) {
+        const size_t need = nchunks * (m->layers.size() + 1);
+        while (m->prof_events.size() < need) {
+            cudaEvent_t e;
+            MF_CUDA(cudaEventCreate(&e));
+            m->prof_events.push_back(e);
+        }
+        m->prof_chunks = nchunks;
+    }
+    size_t ci = 0;
+    for (size_t off = 0; off < n; off += m->chunk, ++ci) {
+        const size_t cn = std::min(m->chunk, n - off);
+        cudaEvent_t *prof = m->profiling ? &m->prof_events[ci * (m->layers.size() + 1)] : nullptr;
+        rc = run_chunk(m, m->slot[0], (const uint8_t *)d_in_q + off * ie, cn, d_out_f32 ? d_out_f32 + off * oe : nullptr,
+                       d_out_q ? (uint8_t *)d_out_q + off * oe : nullptr, nullptr, st, prof, nullptr, 0);
+        if (rc) return rc;
+    }
+    return MF_OK;
+}
+
+int mf_predict_trace(mf_model *m, const void *in_q, size_t n, void *const *layer_outs) {
+    int rc = need_device(m);
+    if (rc) return rc;
+    if (!in_q || !layer_outs) return fail(MF_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> lock(m->mu);
+    MF_CUDA(cudaSetDevice(m->device));
+    Slot &s = m->slot[0];
+    const size_t ie = m->spec.in_elems;
+    for (size_t off = 0; off < n; off += m->chunk) {
+        const size_t cn = std::min(m->chunk, n - off);
+        MF_CUDA(cudaMemcpyAsync(s.in_q, (const uint8_t *)in_q + off * ie, cn * ie, cudaMemcpyHostToDevice, s.stream));
+        rc = run_chunk(m, s, s.in_q, cn, nullptr, nullptr, nullptr, s.stream, nullptr, layer_outs, off);
+        if (rc) return rc;
+        MF_CUDA(cudaStreamSynchronize(s.stream));
+    }
+    return MF_OK;
+}
+
+int mf_model_synchronize(mf_model *m) {
+    int rc = need_device(m);
+    if (rc) return rc;
+    MF_CUDA(cudaSetDevice(m->device));
+    MF_CUDA(cudaDeviceSynchronize());
+    return MF_OK;
+}
+int mf_model_set_profiling(mf_model *m, int enabled) {
+    int rc = need_device(m);
+    if (rc) return rc;
+    m->profiling = enabled != 0;
+    m->prof_chunks = 0;
+    return MF_OK;
+}
+int mf_model_layer_times_ms(mf_model *m, float *ms, int cap) {
+    int rc = need_device(m);
+    if (rc) return rc;
+    if (!ms || cap < (int)m->layers.size()) return fail(MF_ERR_INVALID_ARG, "ms buffer too small");
+    MF_CUDA(cudaSetDevice(m->device));
+    MF_CUDA(cudaDeviceSynchronize());
+    const size_t L = m->layers.size();
+    for (size_t i = 0; i < L; ++i) ms[i] = 0.f;
+    for (size_t c = 0; c < m->prof_chunks; ++c)
+        for (size_t i = 0; i < L; ++i) {
+            float t = 0.f;
+            MF_CUDA(cudaEventElapsedTime(&t, m->prof_events[c * (L + 1) + i], m->prof_events[c * (L + 1) + i + 1]));
+            ms[i] += t;
+        }
+    return MF_OK;
+}
+int mf_model_launch_count(const mf_model *m, uint64_t *count) {
+    if (!m || !count) return fail(MF_ERR_INVALID_ARG, "null argument");
+    *count = m->launches;
+    return MF_OK;
+}
+int mf_model_blob(const mf_model *m, void **d_ptr, size_t *bytes) {
+    int rc = need_device(m);
+    if (rc) return rc;
+    if (d_ptr) *d_ptr = m->d_blob;
+    if (bytes) *bytes = m->blob_bytes;
+    return MF_OK;
+}
+
+int mf_host_alloc(void **p, size_t bytes) {
+    if (!p) return fail(MF_ERR_INVALID_ARG, "null pointer");
+    int rc = check_device(nullptr);
+    if (rc) return rc;
+    MF_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+    return MF_OK;
+}
+int mf_host_free(void *p) {
+    if (p) MF_CUDA(cudaFreeHost(p));
+    return MF_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// per-operator hooks: build a one-layer plan, run it on `batch` samples, copy back
+// -------------------------------------------------------------------------------------------------
+static int run_single_layer(LayerSpec &L, int impl, const void *in, void *out, size_t batch) {
+    int rc = check_device(nullptr);
+    if (rc) return rc;
+    if (!in || !out) return fail(MF_ERR_INVALID_ARG, "null buffer");
+    cudaDeviceProp prop{};
+    int dev = 0;
+    MF_CUDA(cudaGetDevice(&dev));
+    MF_CUDA(cudaGetDeviceProperties(&prop, dev));
+    activation_clamp(L.act, L.out_scale, L.out_zp, L.is_u8, L.act_lo, L.act_hi);
+    LayerExec E;
+    E.spec = L;
+    BlobBuilder bb;
+    E.plan(bb, impl == 1 ? 1 : 0, true);
+    uint8_t *d_blob = nullptr, *d_in = nullptr, *d_out = nullptr;
+    auto cleanup = [&] { cudaFree(d_blob); cudaFree(d_in); cudaFree(d_out); };
+    cudaError_t e = cudaSuccess;
+    std::string err;
+    do {
+        if ((e = cudaMalloc(&d_blob, bb.bytes().size() + 256)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(d_blob, bb.bytes().data(), bb.bytes().size(), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        E.resolve(d_blob, &err);
+        if (impl == 2 && (E.kernel == Kernel::ConvGeneric || E.kernel == Kernel::FcGeneric)) {
+            cleanup();
+            return fail(MF_ERR_UNSUPPORTED_SHAPE, "no fast kernel takes this operator: " + E.why_not_fast);
+        }
+        if ((e = cudaMalloc(&d_in, batch * L.in_elems + 256)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_out, batch * L.out_elems + 256)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(d_in, in, batch * L.in_elems, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = E.run(d_in, d_out, (long long)batch, prop.multiProcessorCount, nullptr, &err)) != cudaSuccess) break;
+        if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
+        e = cudaMemcpy(out, d_out, batch * L.out_elems, cudaMemcpyDeviceToHost);
+    } while (false);
+    cleanup();
+    if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string(kernel_name(E.kernel)) + ": " + cudaGetErrorString(e) + " " + err);
+    g_err = kernel_name(E.kernel);   // lets tests see which kernel ran
+    return MF_OK;
+}
+
+int mf_op_conv_2d(const mf_conv_desc *d, const void *in, void *out, size_t batch) {
+    if (!d || !d->filters || !d->filter_zero_points || !d->c0 || !d->c1 || d->n_filter_zero_points < 1 || d->n_c1 < 1)
+        return fail(MF_ERR_INVALID_ARG, "incomplete mf_conv_desc");
+    if (d->dtype != MF_DTYPE_I8 && d->dtype != MF_DTYPE_U8) return fail(MF_ERR_UNSUPPORTED_TYPE, "dtype must be INT8 or UINT8");
+    LayerSpec L;
+    L.op = d->depthwise ? MF_OP_DEPTHWISE_CONV_2D : MF_OP_CONV_2D;
+    L.is_u8 = d->dtype == MF_DTYPE_U8;
+    L.H = d->in_h; L.W = d->in_w; L.Cin = d->in_c; L.OH = d->out_h; L.OW = d->out_w; L.Cout = d->out_c;
+    L.KH = d->kh; L.KW = d->kw; L.sh = d->stride_h; L.sw = d->stride_w; L.pad = d->padding; L.act = d->activation;
+    L.in_zp = d->in_zero_point; L.out_scale = d->out_scale; L.out_zp = d->out_zero_point;
+    if (L.H <= 0 || L.W <= 0 || L.Cin <= 0 || L.OH <= 0 || L.OW <= 0 || L.Cout <= 0 || L.KH <= 0 || L.KW <= 0 || L.sh <= 0 || L.sw <= 0)
+        return fail(MF_ERR_UNSUPPORTED_SHAPE, "non-positive dimension");
+    if (L.pad == MF_PAD_VALID && (L.sh * (L.OH - 1) + L.KH > L.H || L.sw * (L.OW - 1) + L.KW > L.W))
+        return fail(MF_ERR_VIEW_OUT_OF_BOUNDS, "VALID view indexes outside the input (src/tensor.rs:222 would panic)");
+    const size_t wn = d->depthwise ? (size_t)L.KH * L.KW * L.Cout : (size_t)L.Cout * L.KH * L.KW * L.Cin;
+    L.w.assign((const uint8_t *)d->filters, (const uint8_t *)d->filters + wn);
+    L.w_zp.assign(d->filter_zero_points, d->filter_zero_points + d->n_filter_zero_points);
+    L.c0.assign(d->c0, d->c0 + L.Cout);
+    L.c1.assign(d->c1, d->c1 + d->n_c1);
+    L.in_elems = (size_t)L.H * L.W * L.Cin;
+    L.out_elems = (size_t)L.OH * L.OW * L.Cout;
+    return run_single_layer(L, d->impl, in, out, batch);
+}
+
+int mf_op_fully_connected(const mf_fc_desc *d, const void *in, void *out, size_t batch) {
+    if (!d || !d->weights_nk || !d->c0 || !d->c2) return fail(MF_ERR_INVALID_ARG, "incomplete mf_fc_desc");
+    if (d->dtype != MF_DTYPE_I8 && d->dtype != MF_DTYPE_U8) return fail(MF_ERR_UNSUPPORTED_TYPE, "dtype must be INT8 or UINT8");
+    if (d->in_features <= 0 || d->out_features <= 0) return fail(MF_ERR_UNSUPPORTED_SHAPE, "non-positive dimension");
+    LayerSpec L;
+    L.op = MF_OP_FULLY_CONNECTED;
+    L.is_u8 = d->dtype == MF_DTYPE_U8;
+    L.Cin = d->in_features; L.Cout = d->out_features;
+    L.w.assign((const uint8_t *)d->weights_nk, (const uint8_t *)d->weights_nk + (size_t)L.Cin * L.Cout);
+    L.w_zp.assign(1, d->weight_zero_point);
+    L.out_scale = d->out_scale; L.out_zp = d->out_zero_point; L.act = d->activation;
+    L.c0.assign(d->c0, d->c0 + L.Cout);
+    L.c1.assign(1, d->c1);
+    L.c2.assign(d->c2, d->c2 + L.Cout);
+    L.c3 = d->c3;
+    L.in_elems = (size_t)L.Cin; L.out_elems = (size_t)L.Cout;
+    return run_single_layer(L, d->impl, in, out, batch);
+}
+
+int mf_op_average_pool_2d(const mf_pool_desc *d, const void *in, void *out, size_t batch) {
+    if (!d) return fail(MF_ERR_INVALID_ARG, "null mf_pool_desc");
+    if (d->dtype != MF_DTYPE_I8 && d->dtype != MF_DTYPE_U8) return fail(MF_ERR_UNSUPPORTED_TYPE, "dtype must be INT8 or UINT8");
+    LayerSpec L;
+    L.op = MF_OP_AVERAGE_POOL_2D;
+    L.is_u8 = d->dtype == MF_DTYPE_U8;
+    L.H = d->in_h; L.W = d->in_w; L.Cin = L.Cout = d->chans; L.OH = d->out_h; L.OW = d->out_w;
+    L.KH = d->filter_h; L.KW = d->filter_w; L.sh = d->stride_h; L.sw = d->stride_w; L.pad = d->padding; L.act = d->activation;
+    L.out_scale = d->out_scale; L.out_zp = d->out_zero_point;
+    if (L.H <= 0 || L.W <= 0 || L.Cin <= 0 || L.OH <= 0 || L.OW <= 0 || L.KH <= 0 || L.KW <= 0 || L.sh <= 0 || L.sw <= 0)
+        return fail(MF_ERR_UNSUPPORTED_SHAPE, "non-positive dimension");
+    if (L.pad == MF_PAD_VALID && (L.sh * (L.OH - 1) + L.KH > L.H || L.sw * (L.OW - 1) + L.KW > L.W))
+        return fail(MF_ERR_VIEW_OUT_OF_BOUNDS, "VALID view indexes outside the input (src/tensor.rs:222 would panic)");
+    L.c0.assign(1, d->c0);
+    L.c1.assign(1, d->c1);
+    L.in_elems = (size_t)L.H * L.W * L.Cin;
+    L.out_elems = (size_t)L.OH * L.OW * L.Cin;
+    return run_single_layer(L, d->impl, in, out, batch);
+}
+
+int mf_op_softmax(int32_t dtype, int32_t rows, int32_t cols, float in_scale, float out_scale, int32_t out_zero_point, const void *in, void *out, size_t batch) {
+    if (dtype != MF_DTYPE_I8 && dtype != MF_DTYPE_U8) return fail(MF_ERR_UNSUPPORTED_TYPE, "dtype must be INT8 or UINT8");
+    if (rows <= 0 || cols <= 0) return fail(MF_ERR_UNSUPPORTED_SHAPE, "non-positive dimension");
+    LayerSpec L;
+    L.op = MF_OP_SOFTMAX;
+    L.is_u8 = dtype == MF_DTYPE_U8;
+    L.in_scale = in_scale; L.out_scale = out_scale; L.out_zp = out_zero_point;
+    L.out_rank = 2; L.out_dims[0] = rows; L.out_dims[1] = cols;
+    L.in_elems = L.out_elems = (size_t)rows * cols;
+    L.exp_lut.resize(256);
+    for (int b = 0; b < 256; ++b) L.exp_lut[(size_t)b] = libm_expf((float)(L.is_u8 ? b : (int)(int8_t)b) * in_scale);
+    return run_single_layer(L, 0, in, out, batch);
+}
+
+int mf_op_quantize(int32_t dtype, float scale, int32_t zero_point, const float *in, void *out, size_t n) {
+    int rc = check_device(nullptr);
+    if (rc) return rc;
+    if (!in || !out) return fail(MF_ERR_INVALID_ARG, "null buffer");
+    if (dtype != MF_DTYPE_I8 && dtype != MF_DTYPE_U8) return fail(MF_ERR_UNSUPPORTED_TYPE, "dtype must be INT8 or UINT8");
+    float *d_in = nullptr;
+    uint8_t *d_out = nullptr;
+    MF_CUDA(cudaMalloc(&d_in, n * 4 + 4));
+    MF_CUDA(cudaMalloc(&d_out, n + 4));
+    cudaError_t e = cudaMemcpy(d_in, in, n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_quantize(d_in, d_out, n, scale, (float)zero_point, dtype == MF_DTYPE_U8, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, n, cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(MF_ERR_CUDA, cudaGetErrorString(e));
+    return MF_OK;
+}
+int mf_op_dequantize(int32_t dtype, float scale, int32_t zero_point, const void *in, float *out, size_t n) {
+    int rc = check_device(nullptr);
+    if (rc) return rc;
+    if (!in || !out) return fail(MF_ERR_INVALID_ARG, "null buffer");
+    if (dtype != MF_DTYPE_I8 && dtype != MF_DTYPE_U8) return fail(MF_ERR_UNSUPPORTED_TYPE, "dtype must be INT8 or UINT8");
+    float *d_out = nullptr;
+    uint8_t *d_in = nullptr;
+    MF_CUDA(cudaMalloc(&d_in, n + 4));
+    MF_CUDA(cudaMalloc(&d_out, n * 4 + 4));
+    cudaError_t e = cudaMemcpy(d_in, in, n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_dequantize(d_in, d_out, n, scale, (float)zero_point, dtype == MF_DTYPE_U8, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(MF_ERR_CUDA, cudaGetErrorString(e));
+    return MF_OK;
+}
+
+}  // extern "C"

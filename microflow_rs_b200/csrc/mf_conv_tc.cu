@@ -1,0 +1,434 @@
+// mf_conv_tc.cu -- hand-written tcgen05 int8 implicit-GEMM Conv2D for sm_100a (B200).
+//
+// Replaces src/ops/conv_2d.rs:28-108 for the shapes that are worth a tensor core:
+//   * 3x3 stride-1 SAME convolutions with Cin a multiple of 128  (BASELINE config 5: 224x224x128 -> 128)
+//   * every 1x1 convolution of person_detect, as a "packed pixel" GEMM (see mf_conv_tc.h)
+//
+// Pipeline inside one persistent CTA (256 threads, 1 CTA / SM):
+//   warp 0 (one lane)  TMA producer : cp.async.bulk.tensor.4d  global -> smem ring (SWIZZLE_128B), mbarrier tx
+//   warp 1 (one lane)  MMA issuer   : tcgen05.mma.cta_group::1.kind::i8, D in TMEM (2 accumulator buffers)
+//   warp 2             TMEM alloc / dealloc
+//   warps 4..7         epilogue     : tcgen05.ld 32x32b -> registers -> exact f32 requantize (mf_device.cuh)
+//                                     -> int8 pack -> 16-byte global stores
+// The weights (B operand, <= 147 KB) are loaded once per CTA and stay in shared memory.
+//
+// Arithmetic: int32 accumulation is exact and order-independent, so any tiling is bit-identical to the
+// reference; zero-filled out-of-bounds taps (TMA OOB fill) reproduce the reference's zero-filled view
+// (src/tensor.rs:196-218) and the `in_zp * masked filter-sum` term (conv_2d.rs:83-89) becomes a per-border-class,
+// per-channel int32 table subtracted before the f32 epilogue.  Weight zero-points must be 0 on this path.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "mf_conv_tc.h"
+#include "mf_device.cuh"
+
+namespace mf {
+
+namespace {
+
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 256;
+constexpr uint32_t kSmemLimit = 232448;  // 227 KB usable per CTA on sm_100
+
+struct ConvTcParams {
+    uint8_t *out;
+    const float *c0z;
+    const float *c1;
+    const int32_t *corr;
+    int N, CB, KH, KW, TW, TH, tw_log2, off_r, off_c, ncls, stages;
+    int tiles_x, tiles_y;
+    long long num_tiles, OW, OH;
+    float lo, hi;
+    uint32_t idesc, stage_bytes, b_block_bytes, tmem_cols, nkb;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must trap (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > 8000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, int8 x int8 -> int32
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows * 128 B = 1024)
+//   [46,48) version = 1 | [49,52) base_offset = 0 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// 32 lanes x 32 columns of 32-bit accumulators: thread t <- TMEM lane (base_lane + t), columns [col, col + 32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sB = smem;
+    uint8_t *sA = sB + (size_t)p.nkb * p.b_block_bytes;
+    float *s_c0z = reinterpret_cast<float *>(sA + (size_t)p.stages * p.stage_bytes);
+    float *s_c1 = s_c0z + p.N;
+    int32_t *s_corr = reinterpret_cast<int32_t *>(s_c1 + p.N);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_corr + (size_t)p.ncls * p.N);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 5);
+
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](uint32_t s) { return bar0 + 8u * (kMaxStages + s); };
+    const uint32_t bfull_bar = bar0 + 8u * (2 * kMaxStages);
+    auto tfull_bar = [&](uint32_t a) { return bar0 + 8u * (2 * kMaxStages + 1 + a); };
+    auto tempty_bar = [&](uint32_t a) { return bar0 + 8u * (2 * kMaxStages + 3 + a); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(bfull_bar, 1);
+        mbar_init(tfull_bar(0), 1); mbar_init(tfull_bar(1), 1);
+        mbar_init(tempty_bar(0), 128); mbar_init(tempty_bar(1), 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 4) {  // per-channel epilogue tables -> smem
+        const int t = threadIdx.x - 128;
+        for (int k = t; k < p.N; k += 128) { s_c0z[k] = p.c0z[k]; s_c1[k] = p.c1[k]; }
+        for (int k = t; k < p.ncls * p.N; k += 128) s_corr[k] = p.corr[k];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const long long tiles_per_img = (long long)p.tiles_x * p.tiles_y;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            mbar_expect_tx(bfull_bar, p.nkb * p.b_block_bytes);
+            for (uint32_t kb = 0; kb < p.nkb; ++kb) tma_load_2d(smem_u32(sB + (size_t)kb * p.b_block_bytes), &tmap_b, bfull_bar, (int)(kb * 128), 0);
+            uint32_t s = 0, ph = 0;
+            for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int b = (int)(tile / tiles_per_img);
+                const int rem = (int)(tile - (long long)b * tiles_per_img);
+                const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+                for (int n = 0; n < p.KW; ++n)
+                    for (int cb = 0; cb < p.CB; ++cb) {
+                        mbar_wait(empty_bar(s), ph ^ 1);
+                        mbar_expect_tx(full_bar(s), p.stage_bytes);
+                        tma_load_4d(smem_u32(sA + (size_t)s * p.stage_bytes), &tmap_a, full_bar(s), cb * 128, tx * p.TW + n - p.off_c,
+                                    ty * p.TH - p.off_r, b);
+                        if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            mbar_wait(bfull_bar, 0);
+            tc_fence_after();
+            uint32_t s = 0, ph = 0, it = 0;
+            const uint32_t b_base = smem_u32(sB);
+            for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+                mbar_wait(tempty_bar(acc), aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.N;
+                uint32_t accumulate = 0;
+                for (int n = 0; n < p.KW; ++n)
+                    for (int cb = 0; cb < p.CB; ++cb) {
+                        mbar_wait(full_bar(s), ph);
+                        tc_fence_after();
+                        const uint32_t a_base = smem_u32(sA + (size_t)s * p.stage_bytes);
+                        for (int m = 0; m < p.KH; ++m) {
+                            const uint32_t kb = (uint32_t)((m * p.KW + n) * p.CB + cb);
+                            const uint32_t a_row = a_base + (uint32_t)(m * p.TW) * 128u;
+                            const uint32_t b_blk = b_base + kb * p.b_block_bytes;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                tc_mma_i8(d_tmem, make_desc(a_row + ks * 32), make_desc(b_blk + ks * 32), p.idesc, accumulate);
+                                accumulate = 1;
+                            }
+                        }
+                        tc_commit(empty_bar(s));  // smem slot is free once these MMAs retire
+                        if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+                    }
+                tc_commit(tfull_bar(acc));        // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue =====
+        const uint32_t q = (uint32_t)(warp & 3);
+        const int row = (int)(q * 32 + lane);
+        const int rr = row >> p.tw_log2, rc = row & (p.TW - 1);
+        uint32_t it = 0;
+        for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+            const int b = (int)(tile / tiles_per_img);
+            const int rem = (int)(tile - (long long)b * tiles_per_img);
+            const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+            const long long oy = (long long)ty * p.TH + rr, ox = (long long)tx * p.TW + rc;
+            const bool valid = oy < p.OH && ox < p.OW;
+            int cls = 0;
+            if (p.ncls == 9) cls = 3 * (oy == 0 ? 0 : (oy == p.OH - 1 ? 2 : 1)) + (ox == 0 ? 0 : (ox == p.OW - 1 ? 2 : 1));
+            const int32_t *corr = s_corr + (size_t)cls * p.N;
+            uint8_t *orow = p.out + (((long long)b * p.OH + oy) * p.OW + ox) * p.N;
+
+            mbar_wait(tfull_bar(acc), aph);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + acc * (uint32_t)p.N + ((q * 32u) << 16);
+            for (int c0 = 0; c0 < p.N; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(t_base + (uint32_t)c0, r);
+                uint32_t w[8];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const float4 z = *reinterpret_cast<const float4 *>(s_c0z + c0 + 4 * g);
+                    const float4 sc = *reinterpret_cast<const float4 *>(s_c1 + c0 + 4 * g);
+                    const int4 kc = *reinterpret_cast<const int4 *>(corr + c0 + 4 * g);
+                    const int y0 = requant((int)r[4 * g + 0] - kc.x, z.x, sc.x, p.lo, p.hi);
+                    const int y1 = requant((int)r[4 * g + 1] - kc.y, z.y, sc.y, p.lo, p.hi);
+                    const int y2 = requant((int)r[4 * g + 2] - kc.z, z.z, sc.z, p.lo, p.hi);
+                    const int y3 = requant((int)r[4 * g + 3] - kc.w, z.w, sc.w, p.lo, p.hi);
+                    w[g] = pack4(y0, y1, y2, y3);
+                }
+                if (valid) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
+                    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn(std::string *why) {
+    static std::once_flag once;
+    static EncodeTiledFn fn = nullptr;
+    static std::string err;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+            err = std::string("cuTensorMapEncodeTiled unavailable: ") + cudaGetErrorString(e);
+            (void)cudaGetLastError();
+        } else {
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        }
+    });
+    if (!fn && why) *why = err;
+    return fn;
+}
+
+bool encode_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box, std::string *why) {
+    EncodeTiledFn fn = get_encode_fn(why);
+    if (!fn) return false;
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (why) *why = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+        return false;
+    }
+    return true;
+}
+
+size_t plan_smem(const ConvTcPlan &p, int stages) {
+    const size_t b_bytes = (size_t)p.KH * p.KW * p.CB * p.N * 128;
+    const size_t stage = (size_t)(p.TH + p.KH - 1) * p.TW * 128;
+    const size_t tables = (size_t)p.N * 8 + (size_t)p.ncls * p.N * 4;
+    return 1024 + b_bytes + stage * stages + tables + (2 * kMaxStages + 5) * 8 + 16;
+}
+
+}  // namespace
+
+int conv_tc_pick_pack(int Cin, int Cout) {
+    if (Cin <= 0 || Cout <= 0) return 0;
+    if (Cin % 128 == 0) return (Cout % 32 == 0 && Cout <= 256) ? 1 : 0;
+    if (128 % Cin != 0) return 0;
+    const int P = 128 / Cin;
+    if ((long long)P * Cout > 256 || (P * Cout) % 32 != 0) return 0;
+    return P;
+}
+
+std::vector<uint8_t> conv_tc_pack_pointwise(const uint8_t *w, int Cout, int Cin, int P) {
+    const size_t K = (size_t)P * Cin, N = (size_t)P * Cout;
+    std::vector<uint8_t> m(N * K, 0);
+    for (int pp = 0; pp < P; ++pp)
+        for (int o = 0; o < Cout; ++o)
+            std::memcpy(&m[((size_t)pp * Cout + o) * K + (size_t)pp * Cin], w + (size_t)o * Cin, (size_t)Cin);
+    return m;
+}
+
+std::vector<int32_t> conv_tc_border_corr_3x3(const uint8_t *w, int Cout, int Cin, int in_zp, int H, int W) {
+    (void)H; (void)W;
+    std::vector<int32_t> t((size_t)9 * Cout, 0);
+    for (int rcls = 0; rcls < 3; ++rcls)
+        for (int ccls = 0; ccls < 3; ++ccls)
+            for (int o = 0; o < Cout; ++o) {
+                int32_t s = 0;
+                for (int m = 0; m < 3; ++m) {
+                    if ((rcls == 0 && m == 0) || (rcls == 2 && m == 2)) continue;  // tap row outside the image
+                    for (int n = 0; n < 3; ++n) {
+                        if ((ccls == 0 && n == 0) || (ccls == 2 && n == 2)) continue;
+                        const uint8_t *f = w + (((size_t)o * 3 + m) * 3 + n) * Cin;
+                        for (int c = 0; c < Cin; ++c) s += (int8_t)f[c];
+                    }
+                }
+                t[(size_t)(rcls * 3 + ccls) * Cout + o] = in_zp * s;
+            }
+    return t;
+}
+
+bool conv_tc_available(std::string *why) { return get_encode_fn(why) != nullptr; }
+
+bool conv_tc_finalize_plan(ConvTcPlan &p, std::string *why) {
+    auto no = [&](const char *m) { if (why) *why = m; return false; };
+    if (p.N % 32 != 0 || p.N < 32 || p.N > 256) return no("N must be a multiple of 32 in [32,256]");
+    if (p.TH * p.TW != 128 || (p.TW & (p.TW - 1)) != 0 || p.TW < 8) return no("tile must be TH x TW = 128 pixels with TW a power of two >= 8");
+    if (p.C != 128 * p.CB) return no("row bytes must be 128 * CB");
+    if (p.TH + p.KH - 1 > 256) return no("patch too tall for one TMA box");
+    int stages = 0;
+    for (int s = 4; s >= 2; --s)
+        if (plan_smem(p, s) <= kSmemLimit) { stages = s; break; }
+    if (!stages) return no("weights + pipeline stages do not fit in 227 KB of shared memory");
+    p.stages = stages;
+    p.smem_bytes = plan_smem(p, stages);
+    const cuuint64_t ktot = (cuuint64_t)p.KH * p.KW * p.C;
+    cuuint64_t dims[2] = {ktot, (cuuint64_t)p.N};
+    cuuint64_t strides[1] = {ktot};
+    cuuint32_t box[2] = {128, (cuuint32_t)p.N};
+    CUtensorMap m;
+    if (!encode_map(&m, p.d_wmat, 2, dims, strides, box, why)) return false;
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    std::memcpy(p.tmap_b, &m, sizeof m);
+    return true;
+}
+
+cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_sms, cudaStream_t s, std::string *why) {
+    CUtensorMap ta, tb;
+    std::memcpy(&tb, p.tmap_b, sizeof tb);
+    cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)l.W, (cuuint64_t)l.H, (cuuint64_t)l.B};
+    cuuint64_t strides[3] = {(cuuint64_t)p.C, (cuuint64_t)p.C * l.W, (cuuint64_t)p.C * l.W * l.H};
+    cuuint32_t box[4] = {128, (cuuint32_t)p.TW, (cuuint32_t)(p.TH + p.KH - 1), 1};
+    if (!encode_map(&ta, l.in, 4, dims, strides, box, why)) return cudaErrorInvalidValue;
+
+    ConvTcParams k{};
+    k.out = l.out; k.c0z = p.d_c0z; k.c1 = p.d_c1; k.corr = p.d_corr;
+    k.N = p.N; k.CB = p.CB; k.KH = p.KH; k.KW = p.KW; k.TW = p.TW; k.TH = p.TH;
+    k.tw_log2 = 0;
+    while ((1 << k.tw_log2) < p.TW) ++k.tw_log2;
+    k.off_r = p.off_r; k.off_c = p.off_c; k.ncls = p.ncls; k.stages = p.stages;
+    k.tiles_x = (int)((l.OW + p.TW - 1) / p.TW);
+    k.tiles_y = (int)((l.OH + p.TH - 1) / p.TH);
+    k.num_tiles = (long long)k.tiles_x * k.tiles_y * l.B;
+    k.OW = l.OW; k.OH = l.OH;
+    k.lo = p.lo; k.hi = p.hi;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 @4, a/b format INT8 = 1 @7/@10,
+    // K-major A and B (bits 15, 16 = 0), n_dim = N >> 3 @17, m_dim = 128 >> 4 @24
+    k.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
+    k.stage_bytes = (uint32_t)((p.TH + p.KH - 1) * p.TW * 128);
+    k.b_block_bytes = (uint32_t)(p.N * 128);
+    k.nkb = (uint32_t)(p.KH * p.KW * p.CB);
+    k.tmem_cols = 2 * p.N <= 32 ? 32 : (2 * p.N <= 64 ? 64 : (2 * p.N <= 128 ? 128 : (2 * p.N <= 256 ? 256 : 512)));
+    if (k.num_tiles <= 0) return cudaSuccess;
+
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] { attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit); });
+    if (attr_err != cudaSuccess) return attr_err;
+    const unsigned grid = (unsigned)(k.num_tiles < num_sms ? k.num_tiles : num_sms);
+    conv_tc_kernel<<<grid, kThreads, p.smem_bytes, s>>>(ta, tb, k);
+    return cudaGetLastError();
+}
+
+}  // namespace mf

@@ -1,0 +1,409 @@
+// mf_kernels.cu -- SIMT kernels (CUDA cores) of the MicroFlow B200 backend.
+//
+//  * generic direct kernels: one thread per output element, every term of the reference formula evaluated as
+//    written (dot, view-sum * w_zp, masked filter-sum * in_zp, len * Cin * in_zp * w_zp).  Any shape, stride,
+//    padding, zero point, int8 or uint8.  They are the cross-check path (MF_FLAG_FORCE_GENERIC) and the
+//    fallback for shapes no fast kernel takes.
+//  * fast kernels: int8 with weight zero-point 0 (every shipped model), NHWC-coalesced 32-bit / 128-bit
+//    accesses, dp4a.  Out-of-bounds taps read the input zero-point instead of 0, which turns the reference's
+//    per-pixel "masked filter-sum" correction into a per-channel constant (kcorr = in_zp * sum_all w):
+//       sum_valid (v - iz) * w  ==  sum_all v' * w - iz * sum_all w ,  v' = v inside, iz outside   (integer-exact)
+//
+// Reference semantics: src/ops/conv_2d.rs:50-107, depthwise_conv_2d.rs:50-104, fully_connected.rs:42-81,
+// average_pool_2d.rs:46-65, softmax.rs:20-26, src/tensor.rs:180-228 (view), src/quantize.rs:16-29.
+#include "mf_device.cuh"
+#include "mf_kernels.h"
+
+namespace mf {
+
+static inline unsigned grid_for(long long total, int block) { return (unsigned)((total + block - 1) / block); }
+
+// ================================================================================================
+// generic conv / depthwise conv
+// ================================================================================================
+template <bool U8>
+__global__ void __launch_bounds__(256) conv_generic_kernel(ConvArgs a, long long total) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int co = (int)(idx % a.Cout);
+    long long p = idx / a.Cout;
+    const int j = (int)(p % a.OW); p /= a.OW;
+    const int i = (int)(p % a.OH);
+    const long long b = p / a.OH;
+    const uint8_t *in = a.in + (size_t)b * a.H * a.W * a.Cin;
+    const int fz = a.w_zp[co];
+    int dot = 0, vsum = 0, fsum = 0, len = 0;
+    for (int m = 0; m < a.KH; ++m) {
+        const int r = a.sh * i + m - a.off_r;
+        for (int n = 0; n < a.KW; ++n) {
+            const int c = a.sw * j + n - a.off_c;
+            if (r < 0 || r >= a.H || c < 0 || c >= a.W) continue;       // tensor.rs:196-218: value 0, mask false, len -= 1
+            ++len;
+            const uint8_t *px = in + ((size_t)r * a.W + c) * a.Cin;
+            if (a.depthwise) {
+                const int ci = co < a.Cin ? co : 0;                       // depthwise_conv_2d.rs:67,:72
+                const int v = ld_elem<U8>(px + ci);
+                const int f = ld_elem<U8>(a.w + ((size_t)m * a.KW + n) * a.Cout + co);
+                dot += v * f; vsum += v; fsum += f;
+            } else {
+                const uint8_t *fw = a.w + (((size_t)co * a.KH + m) * a.KW + n) * a.Cin;
+                for (int ch = 0; ch < a.Cin; ++ch) {
+                    const int v = ld_elem<U8>(px + ch), f = ld_elem<U8>(fw + ch);
+                    dot += v * f; vsum += v; fsum += f;
+                }
+            }
+        }
+    }
+    const int cin_f = a.depthwise ? 1 : a.Cin;                            // conv_2d.rs:90 vs depthwise_conv_2d.rs:87
+    const int acc = dot - vsum * fz - a.in_zp * fsum + len * cin_f * a.in_zp * fz;
+    a.out[idx] = (uint8_t)requant(acc, a.c0z[co], a.c1[co], a.lo, a.hi);
+}
+
+cudaError_t launch_conv_generic(const ConvArgs &a, cudaStream_t s) {
+    const long long total = a.batch * a.OH * a.OW * a.Cout;
+    if (total <= 0) return cudaSuccess;
+    if (a.is_u8) conv_generic_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(a, total);
+    else conv_generic_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(a, total);
+    return cudaGetLastError();
+}
+
+// ================================================================================================
+// generic fully connected
+// ================================================================================================
+template <bool U8>
+__global__ void __launch_bounds__(256) fc_generic_kernel(FcArgs a, long long total) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int j = (int)(idx % a.N);
+    const long long b = idx / a.N;
+    const uint8_t *x = a.in + (size_t)b * a.K, *w = a.w + (size_t)j * a.K;
+    int dot = 0, rowsum = 0;
+    for (int k = 0; k < a.K; ++k) {
+        const int v = ld_elem<U8>(x + k);
+        dot += v * ld_elem<U8>(w + k);
+        rowsum += v;
+    }
+    const int acc = dot - rowsum * a.w_zp - a.c2[j] + a.c3;               // fully_connected.rs:71
+    a.out[idx] = (uint8_t)requant(acc, a.c0z[j], a.c1, a.lo, a.hi);
+}
+
+cudaError_t launch_fc_generic(const FcArgs &a, cudaStream_t s) {
+    const long long total = a.batch * a.N;
+    if (total <= 0) return cudaSuccess;
+    if (a.is_u8) fc_generic_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(a, total);
+    else fc_generic_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(a, total);
+    return cudaGetLastError();
+}
+
+// ================================================================================================
+// average pool (average_pool_2d.rs:52-56): x = (1/f32(len)) * f32(sum);  y = roundf(c0 * x + c1)
+// ================================================================================================
+template <bool U8>
+__global__ void __launch_bounds__(256) pool_generic_kernel(PoolArgs a, long long total) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ch = (int)(idx % a.C);
+    long long p = idx / a.C;
+    const int j = (int)(p % a.OW); p /= a.OW;
+    const int i = (int)(p % a.OH);
+    const long long b = p / a.OH;
+    const uint8_t *in = a.in + (size_t)b * a.H * a.W * a.C;
+    int sum = 0, len = 0;
+    for (int m = 0; m < a.KH; ++m) {
+        const int r = a.sh * i + m - a.off_r;
+        for (int n = 0; n < a.KW; ++n) {
+            const int c = a.sw * j + n - a.off_c;
+            if (r < 0 || r >= a.H || c < 0 || c >= a.W) continue;
+            ++len;
+            sum += ld_elem<U8>(in + ((size_t)r * a.W + c) * a.C + ch);
+        }
+    }
+    const float x = __fmul_rn(__fdiv_rn(1.0f, __int2float_rn(len)), __int2float_rn(sum));
+    const float t = __fadd_rn(__fmul_rn(a.c0, x), a.c1);
+    a.out[idx] = (uint8_t)round_clamp(t, a.lo, a.hi);
+}
+
+cudaError_t launch_pool_generic(const PoolArgs &a, cudaStream_t s) {
+    const long long total = a.batch * a.OH * a.OW * a.C;
+    if (total <= 0) return cudaSuccess;
+    if (a.is_u8) pool_generic_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(a, total);
+    else pool_generic_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(a, total);
+    return cudaGetLastError();
+}
+
+// ================================================================================================
+// softmax tail (softmax.rs:20-26; activation.rs:44-46): one thread per sample.
+// exp values come from the host-built 256-entry table (exact port of libm expf); the sum runs in nalgebra's
+// column-major order starting from 0.0; y = quantize(e / sum).
+// ================================================================================================
+__global__ void __launch_bounds__(128) softmax_kernel(SoftmaxArgs a) {
+    __shared__ float lut[256];
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) lut[t] = a.exp_lut[t];
+    __syncthreads();
+    long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.batch) return;
+    const int n = a.rows * a.cols;
+    const uint8_t *x = a.in + (size_t)b * n;
+    uint8_t *y = a.out + (size_t)b * n;
+    float sum = 0.0f;
+    for (int j = 0; j < a.cols; ++j)
+        for (int i = 0; i < a.rows; ++i) sum = __fadd_rn(sum, lut[x[(size_t)i * a.cols + j]]);
+    for (int k = 0; k < n; ++k) {
+        const float q = __fadd_rn(__fdiv_rn(__fdiv_rn(lut[x[k]], sum), a.out_scale), a.out_zp);   // quantize.rs:17
+        y[k] = (uint8_t)round_clamp(q, a.lo, a.hi);
+    }
+}
+
+cudaError_t launch_softmax(const SoftmaxArgs &a, cudaStream_t s) {
+    if (a.batch <= 0) return cudaSuccess;
+    softmax_kernel<<<grid_for(a.batch, 128), 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// ================================================================================================
+// quantize / dequantize (quantize.rs:16-29)
+// ================================================================================================
+__global__ void __launch_bounds__(256) quantize_kernel(const float *in, uint8_t *out, size_t n, float scale, float zp, float lo, float hi) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const float x = in[idx];
+    float t = __fadd_rn(__fdiv_rn(x, scale), zp);
+    if (t != t) t = 0.0f;                                                 // Rust `NaN as i8` == 0
+    out[idx] = (uint8_t)round_clamp(t, lo, hi);
+}
+template <bool U8>
+__global__ void __launch_bounds__(256) dequantize_kernel(const uint8_t *in, float *out, size_t n, float scale, float zp) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    out[idx] = __fmul_rn(scale, __fsub_rn(__int2float_rn(ld_elem<U8>(in + idx)), zp));
+}
+cudaError_t launch_quantize(const float *in, uint8_t *out, size_t n, float scale, float zp, int is_u8, cudaStream_t s) {
+    if (!n) return cudaSuccess;
+    quantize_kernel<<<grid_for((long long)n, 256), 256, 0, s>>>(in, out, n, scale, zp, is_u8 ? 0.f : -128.f, is_u8 ? 255.f : 127.f);
+    return cudaGetLastError();
+}
+cudaError_t launch_dequantize(const uint8_t *in, float *out, size_t n, float scale, float zp, int is_u8, cudaStream_t s) {
+    if (!n) return cudaSuccess;
+    if (is_u8) dequantize_kernel<true><<<grid_for((long long)n, 256), 256, 0, s>>>(in, out, n, scale, zp);
+    else dequantize_kernel<false><<<grid_for((long long)n, 256), 256, 0, s>>>(in, out, n, scale, zp);
+    return cudaGetLastError();
+}
+
+// ================================================================================================
+// FAST: depthwise conv, Cin == Cout = C, C % 4 == 0, int8, w_zp == 0.
+// One thread = 4 consecutive channels (one 32-bit word) of one output pixel; a warp covers 128 contiguous
+// output bytes and reads 128 contiguous input bytes per tap (stride 1).  4 MACs of different channels are
+// issued as 4 dp4a with a byte-masked weight word (no unpacking of the activations).
+// ================================================================================================
+template <int KH_T, int KW_T>
+__global__ void __launch_bounds__(256) dwconv_c4_kernel(ConvArgs a, long long total_words) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total_words) return;
+    const int KH = KH_T ? KH_T : a.KH, KW = KW_T ? KW_T : a.KW;
+    const int G = a.Cout >> 2;
+    const int g = (int)(idx % G);
+    long long p = idx / G;
+    const int j = (int)(p % a.OW); p /= a.OW;
+    const int i = (int)(p % a.OH);
+    const long long b = p / a.OH;
+    const uint32_t *inw = reinterpret_cast<const uint32_t *>(a.in) + (size_t)b * a.H * a.W * G;
+    const uint32_t *ww = reinterpret_cast<const uint32_t *>(a.w);
+    const uint32_t izw = (uint32_t)(a.in_zp & 0xff) * 0x01010101u;
+    int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+#pragma unroll
+    for (int m = 0; m < KH; ++m) {
+        const int r = a.sh * i + m - a.off_r;
+        const bool rok = (unsigned)r < (unsigned)a.H;
+#pragma unroll
+        for (int n = 0; n < KW; ++n) {
+            const int c = a.sw * j + n - a.off_c;
+            const bool ok = rok && (unsigned)c < (unsigned)a.W;
+            const uint32_t v = ok ? __ldg(inw + ((size_t)r * a.W + c) * G + g) : izw;
+            const uint32_t wv = __ldg(ww + (size_t)(m * KW + n) * G + g);
+            acc0 = __dp4a((int)v, (int)(wv & 0x000000ffu), acc0);
+            acc1 = __dp4a((int)v, (int)(wv & 0x0000ff00u), acc1);
+            acc2 = __dp4a((int)v, (int)(wv & 0x00ff0000u), acc2);
+            acc3 = __dp4a((int)v, (int)(wv & 0xff000000u), acc3);
+        }
+    }
+    const int4 kc = __ldg(reinterpret_cast<const int4 *>(a.kcorr) + g);
+    const float4 z = __ldg(reinterpret_cast<const float4 *>(a.c0z) + g);
+    const float4 s = __ldg(reinterpret_cast<const float4 *>(a.c1) + g);
+    const int y0 = requant(acc0 - kc.x, z.x, s.x, a.lo, a.hi);
+    const int y1 = requant(acc1 - kc.y, z.y, s.y, a.lo, a.hi);
+    const int y2 = requant(acc2 - kc.z, z.z, s.z, a.lo, a.hi);
+    const int y3 = requant(acc3 - kc.w, z.w, s.w, a.lo, a.hi);
+    reinterpret_cast<uint32_t *>(a.out)[idx] = pack4(y0, y1, y2, y3);
+}
+
+bool dwconv_c4_eligible(const ConvArgs &a) {
+    return a.depthwise && !a.is_u8 && a.Cin == a.Cout && (a.Cout % 4) == 0 && a.kcorr != nullptr;
+}
+cudaError_t launch_dwconv_c4(const ConvArgs &a, cudaStream_t s) {
+    const long long total = a.batch * a.OH * a.OW * (a.Cout / 4);
+    if (total <= 0) return cudaSuccess;
+    if (a.KH == 3 && a.KW == 3) dwconv_c4_kernel<3, 3><<<grid_for(total, 256), 256, 0, s>>>(a, total);
+    else dwconv_c4_kernel<0, 0><<<grid_for(total, 256), 256, 0, s>>>(a, total);
+    return cudaGetLastError();
+}
+
+// ================================================================================================
+// FAST: depthwise conv with a single input channel and a depth multiplier (person_detect layer 0: 3x3 s2 -> 8 ch,
+// speech layer 1: 10x8 s2 -> 8 ch).  Output channel c reads input channel 0 (depthwise_conv_2d.rs:67).
+// One thread = one output pixel, all COUT channels; the weights of 4 channels sit in one word and the activation
+// byte is moved to the matching byte lane, so each dp4a is one exact MAC without unpacking the weights.
+// ================================================================================================
+template <int COUT>
+__global__ void __launch_bounds__(128) dwconv_cin1_kernel(ConvArgs a, long long total_px) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total_px) return;
+    constexpr int Q = COUT / 4;
+    long long p = idx;
+    const int j = (int)(p % a.OW); p /= a.OW;
+    const int i = (int)(p % a.OH);
+    const long long b = p / a.OH;
+    const uint8_t *in = a.in + (size_t)b * a.H * a.W;
+    const uint32_t *ww = reinterpret_cast<const uint32_t *>(a.w);
+    int acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = 0;
+    for (int m = 0; m < a.KH; ++m) {
+        const int r = a.sh * i + m - a.off_r;
+        const bool rok = (unsigned)r < (unsigned)a.H;
+        for (int n = 0; n < a.KW; ++n) {
+            const int c = a.sw * j + n - a.off_c;
+            const bool ok = rok && (unsigned)c < (unsigned)a.W;
+            const uint32_t v = ok ? (uint32_t)__ldg(in + (size_t)r * a.W + c) : (uint32_t)(a.in_zp & 0xff);
+            const uint32_t v0 = v, v1 = v << 8, v2 = v << 16, v3 = v << 24;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int wv = (int)__ldg(ww + (size_t)(m * a.KW + n) * Q + q);
+                acc[4 * q + 0] = __dp4a(wv, (int)v0, acc[4 * q + 0]);
+                acc[4 * q + 1] = __dp4a(wv, (int)v1, acc[4 * q + 1]);
+                acc[4 * q + 2] = __dp4a(wv, (int)v2, acc[4 * q + 2]);
+                acc[4 * q + 3] = __dp4a(wv, (int)v3, acc[4 * q + 3]);
+            }
+        }
+    }
+    uint32_t *out = reinterpret_cast<uint32_t *>(a.out) + (size_t)idx * Q;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int4 kc = __ldg(reinterpret_cast<const int4 *>(a.kcorr) + q);
+        const float4 z = __ldg(reinterpret_cast<const float4 *>(a.c0z) + q);
+        const float4 s = __ldg(reinterpret_cast<const float4 *>(a.c1) + q);
+        out[q] = pack4(requant(acc[4 * q + 0] - kc.x, z.x, s.x, a.lo, a.hi), requant(acc[4 * q + 1] - kc.y, z.y, s.y, a.lo, a.hi),
+                       requant(acc[4 * q + 2] - kc.z, z.z, s.z, a.lo, a.hi), requant(acc[4 * q + 3] - kc.w, z.w, s.w, a.lo, a.hi));
+    }
+}
+
+bool dwconv_cin1_eligible(const ConvArgs &a) {
+    return a.depthwise && !a.is_u8 && a.Cin == 1 && (a.Cout % 4) == 0 && a.Cout >= 4 && a.Cout <= 16 && a.kcorr != nullptr;
+}
+cudaError_t launch_dwconv_cin1(const ConvArgs &a, cudaStream_t s) {
+    const long long total = a.batch * a.OH * a.OW;
+    if (total <= 0) return cudaSuccess;
+    const unsigned grid = grid_for(total, 128);
+    switch (a.Cout) {
+        case 4: dwconv_cin1_kernel<4><<<grid, 128, 0, s>>>(a, total); break;
+        case 8: dwconv_cin1_kernel<8><<<grid, 128, 0, s>>>(a, total); break;
+        case 12: dwconv_cin1_kernel<12><<<grid, 128, 0, s>>>(a, total); break;
+        case 16: dwconv_cin1_kernel<16><<<grid, 128, 0, s>>>(a, total); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// ================================================================================================
+// FAST (fallback for shapes the tcgen05 GEMM does not take): 1x1 conv, int8, w_zp == 0, Cin % 4 == 0, Cout % 4 == 0.
+// One thread = 4 output channels of one pixel; dp4a over the input channels.
+// ================================================================================================
+__global__ void __launch_bounds__(256) pwconv_dp4a_kernel(ConvArgs a, long long total_words) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total_words) return;
+    const int G = a.Cout >> 2, K4 = a.Cin >> 2;
+    const int g = (int)(idx % G);
+    long long p = idx / G;
+    const int j = (int)(p % a.OW); p /= a.OW;
+    const int i = (int)(p % a.OH);
+    const long long b = p / a.OH;
+    const uint32_t *x = reinterpret_cast<const uint32_t *>(a.in) + (((size_t)b * a.H + (size_t)a.sh * i) * a.W + (size_t)a.sw * j) * K4;
+    const uint32_t *w0 = reinterpret_cast<const uint32_t *>(a.w) + (size_t)(4 * g) * K4;
+    int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+    for (int k = 0; k < K4; ++k) {
+        const int v = (int)__ldg(x + k);
+        acc0 = __dp4a(v, (int)__ldg(w0 + k), acc0);
+        acc1 = __dp4a(v, (int)__ldg(w0 + K4 + k), acc1);
+        acc2 = __dp4a(v, (int)__ldg(w0 + 2 * K4 + k), acc2);
+        acc3 = __dp4a(v, (int)__ldg(w0 + 3 * K4 + k), acc3);
+    }
+    const int4 kc = __ldg(reinterpret_cast<const int4 *>(a.kcorr) + g);
+    const float4 z = __ldg(reinterpret_cast<const float4 *>(a.c0z) + g);
+    const float4 s = __ldg(reinterpret_cast<const float4 *>(a.c1) + g);
+    reinterpret_cast<uint32_t *>(a.out)[idx] =
+        pack4(requant(acc0 - kc.x, z.x, s.x, a.lo, a.hi), requant(acc1 - kc.y, z.y, s.y, a.lo, a.hi),
+              requant(acc2 - kc.z, z.z, s.z, a.lo, a.hi), requant(acc3 - kc.w, z.w, s.w, a.lo, a.hi));
+}
+
+bool pwconv_dp4a_eligible(const ConvArgs &a) {
+    return !a.depthwise && !a.is_u8 && a.KH == 1 && a.KW == 1 && (a.Cin % 4) == 0 && (a.Cout % 4) == 0 && a.kcorr != nullptr;
+}
+cudaError_t launch_pwconv_dp4a(const ConvArgs &a, cudaStream_t s) {
+    const long long total = a.batch * a.OH * a.OW * (a.Cout / 4);
+    if (total <= 0) return cudaSuccess;
+    pwconv_dp4a_kernel<<<grid_for(total, 256), 256, 0, s>>>(a, total);
+    return cudaGetLastError();
+}
+
+// ================================================================================================
+// FAST: fully connected with few outputs (speech: 4000 -> 4): one warp per sample, 128-bit loads, dp4a,
+// shuffle reduction.  Pure bandwidth: K bytes per sample.
+// ================================================================================================
+template <int N_T>
+__global__ void __launch_bounds__(256) fc_warp_kernel(FcArgs a) {
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= a.batch) return;
+    const int4 *x = reinterpret_cast<const int4 *>(a.in + (size_t)warp * a.K);
+    const int chunks = a.K >> 4;
+    int acc[N_T];
+#pragma unroll
+    for (int j = 0; j < N_T; ++j) acc[j] = 0;
+    int rowsum = 0;
+    for (int t = lane; t < chunks; t += 32) {
+        const int4 v = __ldg(x + t);
+        rowsum = __dp4a(v.x, 0x01010101, rowsum); rowsum = __dp4a(v.y, 0x01010101, rowsum);
+        rowsum = __dp4a(v.z, 0x01010101, rowsum); rowsum = __dp4a(v.w, 0x01010101, rowsum);
+#pragma unroll
+        for (int j = 0; j < N_T; ++j) {
+            if (j < a.N) {
+                const int4 w = __ldg(reinterpret_cast<const int4 *>(a.w + (size_t)j * a.K) + t);
+                acc[j] = __dp4a(v.x, w.x, acc[j]); acc[j] = __dp4a(v.y, w.y, acc[j]);
+                acc[j] = __dp4a(v.z, w.z, acc[j]); acc[j] = __dp4a(v.w, w.w, acc[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        rowsum += __shfl_xor_sync(0xffffffffu, rowsum, off);
+#pragma unroll
+        for (int j = 0; j < N_T; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+    }
+#pragma unroll
+    for (int j = 0; j < N_T; ++j) {
+        if (lane == j && j < a.N) {
+            const int t = acc[j] - rowsum * a.w_zp - a.c2[j] + a.c3;
+            a.out[(size_t)warp * a.N + j] = (uint8_t)requant(t, a.c0z[j], a.c1, a.lo, a.hi);
+        }
+    }
+}
+
+bool fc_warp_eligible(const FcArgs &a) { return !a.is_u8 && (a.K % 16) == 0 && a.N >= 1 && a.N <= 8; }
+cudaError_t launch_fc_warp(const FcArgs &a, cudaStream_t s) {
+    if (a.batch <= 0) return cudaSuccess;
+    const unsigned grid = grid_for(a.batch * 32, 256);
+    if (a.N <= 4) fc_warp_kernel<4><<<grid, 256, 0, s>>>(a);
+    else fc_warp_kernel<8><<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace mf

@@ -1,0 +1,75 @@
+// mf_kernels.h -- launch interface of the hand-written CUDA kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mf {
+
+// One quantized conv / depthwise-conv layer on `batch` independent NHWC samples.
+struct ConvArgs {
+    const uint8_t *in = nullptr;
+    uint8_t *out = nullptr;
+    const uint8_t *w = nullptr;     // conv: OHWI [Cout][KH][KW][Cin]; depthwise: [KH][KW][Cout]
+    const int32_t *w_zp = nullptr;  // [Cout] (per-tensor values are replicated)
+    const float *c0z = nullptr;     // [Cout]  f32(out_zp) + c0[ch]
+    const float *c1 = nullptr;      // [Cout]
+    const int32_t *kcorr = nullptr; // [Cout]  in_zp * sum over ALL taps (and input channels) of w -- fast kernels only
+    int H = 1, W = 1, Cin = 1, OH = 1, OW = 1, Cout = 1, KH = 1, KW = 1, sh = 1, sw = 1;
+    int off_r = 0, off_c = 0;       // SAME: (K-1)/2 (src/tensor.rs:193), VALID: 0
+    int in_zp = 0;
+    float lo = -128.f, hi = 127.f;
+    int is_u8 = 0, depthwise = 0;
+    long long batch = 0;
+};
+
+struct FcArgs {
+    const uint8_t *in = nullptr;   // [batch][K]
+    uint8_t *out = nullptr;        // [batch][N]
+    const uint8_t *w = nullptr;    // [N][K]
+    const float *c0z = nullptr;    // [N]
+    const int32_t *c2 = nullptr;   // [N]
+    float c1 = 0.f;
+    int32_t c3 = 0, w_zp = 0;
+    int K = 1, N = 1;
+    float lo = -128.f, hi = 127.f;
+    int is_u8 = 0;
+    long long batch = 0;
+};
+
+struct PoolArgs {
+    const uint8_t *in = nullptr;
+    uint8_t *out = nullptr;
+    int H = 1, W = 1, C = 1, OH = 1, OW = 1, KH = 1, KW = 1, sh = 1, sw = 1, off_r = 0, off_c = 0;
+    float c0 = 0.f, c1 = 0.f, lo = -128.f, hi = 127.f;
+    int is_u8 = 0;
+    long long batch = 0;
+};
+
+struct SoftmaxArgs {
+    const uint8_t *in = nullptr;
+    uint8_t *out = nullptr;
+    const float *exp_lut = nullptr;  // [256] expf(f32(q) * in_scale), indexed by the raw byte
+    int rows = 1, cols = 1;
+    float out_scale = 1.f, out_zp = 0.f, lo = -128.f, hi = 127.f;
+    long long batch = 0;
+};
+
+// ---- generic direct kernels: any shape / zero point / dtype; the cross-check path --------------------
+cudaError_t launch_conv_generic(const ConvArgs &a, cudaStream_t s);
+cudaError_t launch_fc_generic(const FcArgs &a, cudaStream_t s);
+cudaError_t launch_pool_generic(const PoolArgs &a, cudaStream_t s);
+cudaError_t launch_softmax(const SoftmaxArgs &a, cudaStream_t s);
+cudaError_t launch_quantize(const float *in, uint8_t *out, size_t n, float scale, float zp, int is_u8, cudaStream_t s);
+cudaError_t launch_dequantize(const uint8_t *in, float *out, size_t n, float scale, float zp, int is_u8, cudaStream_t s);
+
+// ---- SIMT fast kernels (int8, weight zero-point 0): coalesced NHWC, dp4a -------------------------------
+bool dwconv_c4_eligible(const ConvArgs &a);      // depthwise, Cin == Cout, C % 4 == 0
+cudaError_t launch_dwconv_c4(const ConvArgs &a, cudaStream_t s);
+bool dwconv_cin1_eligible(const ConvArgs &a);    // depthwise with Cin == 1 (depth multiplier), Cout % 4 == 0, Cout <= 16
+cudaError_t launch_dwconv_cin1(const ConvArgs &a, cudaStream_t s);
+bool pwconv_dp4a_eligible(const ConvArgs &a);    // 1x1 stride-1 conv, Cin % 4 == 0, Cout % 4 == 0
+cudaError_t launch_pwconv_dp4a(const ConvArgs &a, cudaStream_t s);
+bool fc_warp_eligible(const FcArgs &a);          // K % 16 == 0, N <= 8
+cudaError_t launch_fc_warp(const FcArgs &a, cudaStream_t s);
+
+}  // namespace mf

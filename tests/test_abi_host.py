@@ -1,0 +1,99 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol include/microflow_cuda.h declares,
+fails loudly without a GPU (no CPU fallback), and its run-time loader (the proc-macro's job) reproduces the oracle's --
+i.e. the reference's -- pre-processing constants bit for bit.  No compute calls here."""
+import ctypes as C
+import re
+
+import numpy as np
+import pytest
+
+import microflow_rs_b200 as mf
+import oracle
+from conftest import MODELS, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "microflow_cuda.h").read_text()
+    declared = sorted(set(re.findall(r"\b(mf_[a-z0-9_]+)\s*\(", header)))
+    assert declared == sorted(mf.ABI_SYMBOLS)
+    L = mf.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.mf_abi_version() == 1
+
+
+def _has_gpu():
+    try:
+        return mf.device_count() > 0
+    except mf.MicroflowError:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback_without_gpu():
+    with pytest.raises(mf.MicroflowError) as e:
+        mf.device_count()
+    assert e.value.status == 10  # MF_ERR_NO_DEVICE
+    with pytest.raises(mf.MicroflowError) as e:
+        mf.Model(MODELS / "sine.tflite")
+    assert e.value.status == 10
+    m = mf.Model(MODELS / "sine.tflite", flags=mf.FLAG_HOST_ONLY)
+    with pytest.raises(mf.MicroflowError) as e:
+        m.predict(np.zeros((1, 1), np.float32))
+    assert e.value.status == 10
+    with pytest.raises(mf.MicroflowError):
+        mf.ops.quantize(np.zeros(4, np.float32), 0.1, 0)
+
+
+@pytest.mark.parametrize("name", ["sine", "speech", "person_detect"])
+def test_loader_matches_oracle(name):
+    m = mf.Model(MODELS / f"{name}.tflite", flags=mf.FLAG_HOST_ONLY)
+    o = oracle.Model(MODELS / f"{name}.tflite")
+    assert m.in_shape == o.in_shape and m.out_shape == o.out_shape
+    assert m.in_scale == o.in_scale and m.in_zp == o.in_zp and m.out_scale == o.out_scale and m.out_zp == o.out_zp
+    assert len(m.layers) == len(o.layers)
+    for i, (a, b) in enumerate(zip(m.layers, o.layers)):
+        assert a["op"] == b["op"], i
+        assert tuple(a["out_shape"]) == tuple(b["out_shape"]), i
+        if a["op"] in ("reshape", "softmax"):
+            continue
+        c0, c1, c2, c3 = m.layer_constants(i)
+        oc0, oc1, oc2, oc3 = o.layer_consts(i)
+        if a["op"] == "average_pool_2d":
+            assert c0[0] == oc0[0] and c1[0] == oc1[0]
+            continue
+        np.testing.assert_array_equal(c0, oc0[: len(c0)])
+        np.testing.assert_array_equal(c1, oc1[: len(c1)])
+        if a["op"] == "fully_connected":
+            np.testing.assert_array_equal(c2[: len(c0)], oc2[: len(c0)])
+            assert c3 == oc3
+
+
+def test_person_detect_graph_facts():
+    """MAC counts and the ReLU6 clamp evaluating to the full int8 range."""
+    m = mf.Model(MODELS / "person_detect.tflite", flags=mf.FLAG_HOST_ONLY)
+    assert sum(L["macs"] for L in m.layers) == 7157888
+    assert sum(L["macs"] for L in m.layers if L["op"] == "conv_2d") == 6193664
+    assert all(L["clamp"] == (-128, 127) for L in m.layers if L["op"] in ("conv_2d", "depthwise_conv_2d"))
+    s = mf.Model(MODELS / "speech.tflite", flags=mf.FLAG_HOST_ONLY)
+    assert sum(L["macs"] for L in s.layers) == 336000
+
+
+def test_loader_errors_map_to_reference_diagnostics(tmp_path):
+    with pytest.raises(mf.MicroflowError) as e:
+        mf.Model(tmp_path / "missing.tflite", flags=mf.FLAG_HOST_ONLY)
+    assert e.value.status == 1 and "couldn't find" in e.value.text          # lib.rs:50-55
+    with pytest.raises(mf.MicroflowError) as e:
+        mf.Model(b"\x00" * 64, flags=mf.FLAG_HOST_ONLY)
+    assert e.value.status == 2                                               # lib.rs:56-58
+    data = bytearray((MODELS / "sine.tflite").read_bytes())
+    with pytest.raises(mf.MicroflowError):
+        mf.Model(bytes(data[:200]), flags=mf.FLAG_HOST_ONLY)                 # truncated flatbuffer
+
+
+def test_model_dump(tmp_path):
+    m = mf.Model(MODELS / "speech.tflite", flags=mf.FLAG_HOST_ONLY)
+    p = tmp_path / "dump.txt"
+    m.dump(p)
+    text = p.read_text()
+    assert "layer 1: op 4" in text and "c0:" in text
