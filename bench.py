@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of MicroFlow's quantized hot path on B200 (driver contract: see the task brief).
+
+    python bench.py --gpus N --steps K --warmup W                 our CUDA arm (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W  the reference algorithm on the host CPU cores
+
+A "step" = one pass of the whole quantized graph over one batch of synthetic int8 inputs of the model's shape
+(default workload: person_detect.tflite, batch 8192 per GPU = BASELINE.json configs[2]; weak scaling: batch 8192 on
+every GPU, samples are independent, no collective on the inference path, one NCCL broadcast of the weight blob at init).
+
+Printed JSON (one line, rank 0):
+  value      inferences/s, inputs resident in HBM, CUDA-event timed on the launching stream, max over ranks
+  e2e        same metric through the public C-ABI call mf_predict_many_quantized with pinned HOST buffers (H2D + D2H inside)
+  roofline   dominant kernel of the step: algorithmic bytes / its summed launch time vs the measured HBM copy peak
+  conv2d     BASELINE config 5 (synthetic 224x224x128->128 3x3 Conv2D) on the tcgen05 kernel vs the int8 tensor peak (N=1 only)
+  cpu_baseline  the oracle (faithful CPU port of the reference algorithm; the Rust reference cannot be built here) timed on one
+                host core over a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+MODELS = ROOT / "tests" / "golden" / "models"
+SEEDS = {"person_detect": 0x5EED0003, "speech": 0x5EED0002, "sine": 0x5EED0001}
+DEFAULT_BATCH = {"person_detect": 8192, "speech": 4096, "sine": 65536}
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+
+
+def splitmix_bytes(seed, n, offset=0):
+    k = (np.arange(offset, offset + n, dtype=np.uint64) + np.uint64(seed)) * np.uint64(0x9E3779B97F4A7C15)
+    with np.errstate(over="ignore"):
+        z = k
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z & np.uint64(0xFF)).astype(np.uint8).view(np.int8)
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                    "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"]))}, "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS, bf16_tflops_sustained=1400.0), "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(workload, seconds=12.0, threads=1, max_samples=4096):
+    """Times the oracle (-O3 -march=native build) on a bounded sample of the same synthetic workload."""
+    import oracle
+    o = oracle.Model(MODELS / f"{workload}.tflite", fast=True)
+    block = {"person_detect": 64, "speech": 512, "sine": 8192}[workload] * max(1, threads)
+    done, t_used, off = 0, 0.0, 0
+    o.predict_many_quantized(splitmix_bytes(SEEDS[workload], 2 * o.in_elems).reshape(2, -1), threads=1)  # warm-up
+    while t_used < seconds and done < max_samples * max(1, threads):
+        xs = splitmix_bytes(SEEDS[workload], block * o.in_elems, offset=off).reshape(block, -1)
+        t0 = time.perf_counter()
+        o.predict_many_quantized(xs, threads=threads)
+        t_used += time.perf_counter() - t0
+        done += block
+        off += block * o.in_elems
+    return {"value": done / t_used, "unit": "inferences/s", "cores": threads, "kind": "port",
+            "sample": f"{done} synthetic {workload} samples (splitmix64 seed {SEEDS[workload]:#x}), {t_used:.1f} s, "
+                      f"oracle/microflow_oracle.c -O3 -march=native -ffp-contract=off, {threads} thread(s)"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own algorithm on the box's host cores (oracle port; Rust cannot be built here)."""
+    if rank != 0:
+        return
+    import oracle
+    wl = args.workload
+    threads = oracle.max_threads()
+    o = oracle.Model(MODELS / f"{wl}.tflite", fast=True)
+    per_step = {"person_detect": 48, "speech": 384, "sine": 16384}[wl] * threads   # bounded sample per step (~0.5-1 s)
+    xs = splitmix_bytes(SEEDS[wl], per_step * o.in_elems).reshape(per_step, -1)
+    for _ in range(args.warmup):
+        o.predict_many_quantized(xs, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.predict_many_quantized(xs, threads=threads)
+    dt = time.perf_counter() - t0
+    val = per_step * args.steps / dt
+    sample = f"{per_step} synthetic {wl} samples per step on {threads} host threads (oracle port of the reference algorithm)"
+    line = {"impl": "reference", "metric": f"inferences/s {wl} int8", "value": val, "unit": "inferences/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8", "data": "synthetic", "config": {"workload": f"{wl}.tflite int8, bounded CPU sample of {per_step} samples/step"},
+            "cpu_baseline": {"value": val, "unit": "inferences/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "inferences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+class _DevMem:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def conv2d_roofline(torch, mf, peaks, steps, warmup, batch=16):
+    """BASELINE config 5: synthetic Conv2D 224x224x128 -> 128, k3 s1 SAME, int8, ReLU6 on the tcgen05 kernel."""
+    import ctypes as C
+    H = W = 224
+    Cin = Cout = 128
+    seed = 0x5EED0005
+    w = splitmix_bytes(seed, Cout * 9 * Cin).reshape(Cout, 3, 3, Cin)
+    r = np.random.default_rng(seed)
+    c1 = (r.uniform(1e-3, 1e-2, Cout) * 0.0235294 / 0.0235294 / 64.0).astype(np.float32)
+    c0 = r.uniform(-4, 4, Cout).astype(np.float32)
+    # drive the op through a one-layer engine object (private helper of the package keeps device buffers resident)
+    from microflow_rs_b200 import _convbench
+    return _convbench.run(torch, w, c0, c1, in_zp=-128, out_zp=-128, out_scale=0.0235294, H=H, W=W, batch=batch, steps=steps, warmup=warmup,
+                          peaks=peaks, seed=seed)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="person_detect", choices=["person_detect", "speech", "sine"])
+    ap.add_argument("--batch", type=int, default=0, help="samples per GPU per step (default: BASELINE config)")
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-conv2d", action="store_true")
+    ap.add_argument("--flags", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import microflow_rs_b200 as mf
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = args.workload
+    batch = args.batch or DEFAULT_BATCH[wl]
+    peaks, peak_src = load_peaks()
+
+    m = mf.Model(MODELS / f"{wl}.tflite", device=local_rank, chunk=args.chunk, flags=args.flags)
+    # ---- init: ONE NCCL broadcast of the static weights/constants blob from rank 0 (ranks != 0 clear theirs first)
+    ptr, nbytes = m.blob()
+    if world > 1 and nbytes:
+        blob = torch.as_tensor(_DevMem(ptr, nbytes), device=f"cuda:{local_rank}")
+        if rank != 0:
+            blob.zero_()
+        dist.broadcast(blob, src=0)
+        torch.cuda.synchronize()
+
+    ie, oe = m.in_elems, m.out_elems
+    # inputs: contiguous shard of the global sample range [rank*batch, (rank+1)*batch), R rotating batches so that
+    # every step reads inputs that have left the 126 MB L2 (R * batch * in_elems > L2)
+    R = max(2, int(np.ceil(160e6 / (batch * ie))) + 1)
+    R = min(R, 64)
+    host_in = [mf.PinnedBuffer((batch, ie), np.int8) for _ in range(min(R, 4))]
+    for r_i, hb in enumerate(host_in):
+        hb.array[:] = splitmix_bytes(SEEDS[wl] + r_i, batch * ie, offset=rank * batch * ie).reshape(batch, ie)
+    d_in = [torch.from_numpy(host_in[i % len(host_in)].array).cuda() for i in range(R)]
+    d_out = torch.empty((batch, oe), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step(i):
+        m.predict_many_device(d_in[i % R].data_ptr(), batch, d_out.data_ptr(), None, stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    # ---- timed region: exactly K steps, CUDA events on the launching stream, per-layer events inside the engine
+    m.set_profiling(True)
+    launches0 = m.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = m.launch_count() - launches0
+    layer_ms = m.layer_times_ms()
+    m.set_profiling(False)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * batch * args.steps / (ms * 1e-3)
+
+    # ---- e2e through the public C-ABI with HOST buffers (H2D of the inputs and D2H of the result inside the timed region)
+    host_out = mf.PinnedBuffer((batch, oe), np.float32)
+    for i in range(3):
+        m.predict_many_quantized(host_in[i % len(host_in)].array, out=host_out.array)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        m.predict_many_quantized(host_in[i % len(host_in)].array, out=host_out.array)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * batch * args.steps / float(t.item())
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel: group layers by kernel, take the largest share of the step
+        groups = {}
+        for L, tms in zip(m.layers, layer_ms):
+            if not L["kernel"] or L["kernel"].startswith("none"):
+                continue
+            g = groups.setdefault(L["kernel"], {"ms": 0.0, "bytes": 0, "macs": 0, "launches": 0})
+            g["ms"] += float(tms)
+            g["bytes"] += (L["bytes"] - L["weight_bytes"]) * batch * args.steps + L["weight_bytes"] * args.steps
+            g["macs"] += L["macs"] * batch * args.steps
+            g["launches"] += 1
+        total_layer_ms = sum(g["ms"] for g in groups.values()) or 1.0
+        dom_name, dom = max(groups.items(), key=lambda kv: kv[1]["ms"])
+        achieved = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
+        traffic = None
+        tp = ROOT / "profiles" / "traffic_latest.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get(dom_name)
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                    "traffic": traffic, "peak_source": peak_src, "share_of_step": dom["ms"] / total_layer_ms,
+                    "note": "achieved = algorithmic bytes (layer input+output per sample x batch + weights once per launch) of this kernel's layers / its summed "
+                            "CUDA-event time inside the timed region"}
+        kernels = {k: {"ms_per_step": g["ms"] / args.steps, "share": g["ms"] / total_layer_ms, "GBps": g["bytes"] / (g["ms"] * 1e-3) / 1e9 if g["ms"] > 0 else None,
+                       "TOPS": 2 * g["macs"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else None} for k, g in groups.items()}
+        line = {
+            "metric": f"inferences/s {wl} int8", "value": value, "unit": "inferences/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": {"workload": f"{wl}.tflite int8, batch {batch} per GPU (BASELINE configs[2])" if wl == "person_detect" else f"{wl}.tflite int8, batch {batch} per GPU",
+                       "global_batch": batch * world, "parallelism": f"dp{world} (independent samples, contiguous shards, one NCCL weight broadcast at init)",
+                       "l2": f"inputs rotate over {R} device batches ({R * batch * ie / 1e6:.0f} MB > 126 MB L2)", "chunk": args.chunk or 2048},
+            "e2e": {"value": e2e_val, "unit": "inferences/s", "h2d_bytes_per_step": batch * ie, "d2h_bytes_per_step": batch * oe * 4,
+                    "api": "mf_predict_many_quantized (pinned host buffers)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "model_level": {"int8_TOPS": value * 2 * sum(L["macs"] for L in m.layers) / 1e12,
+                            "layerwise_GBps": value * sum(L["bytes"] - L["weight_bytes"] for L in m.layers) / 1e9,
+                            "compulsory_GBps": value * (ie + oe * 4) / 1e9},
+        }
+        if world == 1 and not args.no_conv2d:
+            try:
+                line["conv2d"] = conv2d_roofline(torch, mf, peaks, steps=max(5, args.steps // 2), warmup=3)
+            except Exception as e:  # the headline line must still print
+                line["conv2d"] = {"error": repr(e)[:300]}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    m.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

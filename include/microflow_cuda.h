@@ -143,7 +143,8 @@ int mf_predict_many_device(mf_model *m, const void *d_in_q, size_t n, float *d_o
 int mf_predict_trace(mf_model *m, const void *in_q, size_t n, void *const *layer_outs);
 int mf_model_synchronize(mf_model *m);
 
-/* per-layer device timing (CUDA events on the launching stream) of the last mf_predict_many_device call */
+/* per-layer device timing (CUDA events on the launching stream), summed over every mf_predict_many_device call since
+ * profiling was enabled or mf_model_layer_times_ms() was last read (reading synchronizes and resets) */
 int mf_model_set_profiling(mf_model *m, int enabled);
 int mf_model_layer_times_ms(mf_model *m, float *ms, int cap);
 /* number of kernels launched by this model since creation (for bench.py's gpu_launches) */
@@ -175,6 +176,15 @@ typedef struct mf_conv_desc {          /* microflow::ops::conv_2d / depthwise_co
     int32_t impl;
 } mf_conv_desc;
 int mf_op_conv_2d(const mf_conv_desc *d, const void *in, void *out, size_t batch);
+
+/* persistent form of the same operator: plan once (weights/constants uploaded, kernel selected), then run on
+ * DEVICE-resident NHWC buffers, asynchronously on `stream` (cudaStream_t).  Used by pipelines and by bench.py's
+ * BASELINE config 5 (synthetic 224x224x128->128 Conv2D roofline). */
+typedef struct mf_op mf_op;
+int mf_op_conv_2d_create(const mf_conv_desc *d, mf_op **out);
+int mf_op_run_device(mf_op *op, const void *d_in, void *d_out, size_t batch, void *stream);
+const char *mf_op_kernel_name(const mf_op *op);
+void mf_op_destroy(mf_op *op);
 
 typedef struct mf_fc_desc {            /* microflow::ops::fully_connected (src/ops/fully_connected.rs:24-41) */
     int32_t dtype;

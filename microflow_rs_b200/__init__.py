@@ -23,7 +23,7 @@ import numpy as np
 
 from . import _build
 
-__all__ = ["model", "Model", "ops", "MicroflowError", "lib", "build", "device_count", "PinnedBuffer"]
+__all__ = ["model", "Model", "ConvOp", "ops", "MicroflowError", "lib", "build", "device_count", "PinnedBuffer"]
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libmicroflow_cuda.so"
@@ -87,7 +87,7 @@ ABI_SYMBOLS = [
     "mf_model_destroy", "mf_model_io_info", "mf_model_num_layers", "mf_model_layer_info", "mf_model_layer_constants", "mf_model_dump",
     "mf_predict", "mf_predict_quantized", "mf_predict_many", "mf_predict_many_quantized", "mf_predict_many_logits", "mf_predict_many_device",
     "mf_predict_trace", "mf_model_synchronize", "mf_model_set_profiling", "mf_model_layer_times_ms", "mf_model_launch_count", "mf_model_blob",
-    "mf_host_alloc", "mf_host_free", "mf_op_conv_2d", "mf_op_fully_connected", "mf_op_average_pool_2d", "mf_op_softmax", "mf_op_quantize",
+    "mf_host_alloc", "mf_host_free", "mf_op_conv_2d", "mf_op_conv_2d_create", "mf_op_run_device", "mf_op_kernel_name", "mf_op_destroy", "mf_op_fully_connected", "mf_op_average_pool_2d", "mf_op_softmax", "mf_op_quantize",
     "mf_op_dequantize",
 ]
 
@@ -136,6 +136,12 @@ def lib():
         L.mf_host_free.argtypes = [C.c_void_p]
         L.mf_device_count.argtypes = [C.POINTER(C.c_int)]
         L.mf_op_conv_2d.argtypes = [C.POINTER(_ConvDesc), C.c_void_p, C.c_void_p, C.c_size_t]
+        L.mf_op_conv_2d_create.argtypes = [C.POINTER(_ConvDesc), C.POINTER(C.c_void_p)]
+        L.mf_op_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.mf_op_kernel_name.argtypes = [C.c_void_p]
+        L.mf_op_kernel_name.restype = C.c_char_p
+        L.mf_op_destroy.argtypes = [C.c_void_p]
+        L.mf_op_destroy.restype = None
         L.mf_op_fully_connected.argtypes = [C.POINTER(_FcDesc), C.c_void_p, C.c_void_p, C.c_size_t]
         L.mf_op_average_pool_2d.argtypes = [C.POINTER(_PoolDesc), C.c_void_p, C.c_void_p, C.c_size_t]
         L.mf_op_softmax.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]
@@ -332,6 +338,45 @@ class Model:
         p, n = C.c_void_p(), C.c_size_t()
         _check(lib().mf_model_blob(self._h, C.byref(p), C.byref(n)))
         return p.value or 0, n.value
+
+
+class ConvOp:
+    """Persistent Conv2D / DepthwiseConv2D operator (mf_op_conv_2d_create): plan once, run on device-resident buffers."""
+
+    def __init__(self, in_hwc, in_zp, filters, filter_zp, out_scale, out_zp, act, pad, strides, c0, c1, out_hw, depthwise=False, impl=0, dtype=np.int8):
+        filters = np.ascontiguousarray(filters)
+        H, W, Cin = in_hwc
+        if depthwise:
+            _, KH, KW, Cout = filters.shape
+        else:
+            Cout, KH, KW, _ = filters.shape
+        fz = np.ascontiguousarray(np.atleast_1d(filter_zp), np.int32)
+        c0 = np.ascontiguousarray(c0, np.float32)
+        c1 = np.ascontiguousarray(np.atleast_1d(c1), np.float32)
+        d = _ConvDesc(DTYPE_U8 if np.dtype(dtype) == np.uint8 else DTYPE_I8, int(depthwise), H, W, Cin, out_hw[0], out_hw[1], Cout, KH, KW, strides[0],
+                      strides[1], PAD[pad], ACT[act], int(in_zp), np.float32(out_scale), int(out_zp), filters.ctypes.data, fz.ctypes.data, len(fz),
+                      c0.ctypes.data, c1.ctypes.data, len(c1), impl)
+        self._h = C.c_void_p()
+        _check(lib().mf_op_conv_2d_create(C.byref(d), C.byref(self._h)))
+        self.kernel = lib().mf_op_kernel_name(self._h).decode()
+        self.in_elems = H * W * Cin
+        self.out_elems = out_hw[0] * out_hw[1] * Cout
+        self.macs = out_hw[0] * out_hw[1] * Cout * KH * KW * (1 if depthwise else Cin)
+        self.weight_bytes = filters.size + 8 * Cout
+
+    def run_device(self, d_in_ptr, d_out_ptr, batch, stream=None):
+        _check(lib().mf_op_run_device(self._h, C.c_void_p(d_in_ptr), C.c_void_p(d_out_ptr), batch, C.c_void_p(stream or 0)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mf_op_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def model(path, **kw):

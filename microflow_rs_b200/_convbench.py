@@ -1,0 +1,46 @@
+"""BASELINE config 5: synthetic Conv2D 224x224x128 -> 128, k3 s1 SAME, int8, ReLU6, on device-resident buffers.
+Returns the `conv2d` roofline object of bench.py (tensor-pipe bound)."""
+import numpy as np
+
+from . import ConvOp
+
+
+def run(torch, w, c0, c1, in_zp, out_zp, out_scale, H, W, batch, steps, warmup, peaks, seed):
+    Cout, _, _, Cin = w.shape
+    fast = ConvOp((H, W, Cin), in_zp, w, [0], out_scale, out_zp, "relu6", "same", (1, 1), c0, c1, (H, W), impl=0)
+    res = {"workload": f"synthetic Conv2D {H}x{W}x{Cin}->{Cout} k3 s1 SAME int8 ReLU6, batch {batch} (BASELINE configs[4])", "kernel": fast.kernel}
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    x = [torch.randint(-128, 128, (batch, H, W, Cin), dtype=torch.int8, device="cuda", generator=g) for _ in range(2)]
+    y = torch.empty((batch, H, W, Cout), dtype=torch.int8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    # correctness guard inside the bench: one image against the generic direct kernel (bit-exact)
+    gen = ConvOp((H, W, Cin), in_zp, w, [0], out_scale, out_zp, "relu6", "same", (1, 1), c0, c1, (H, W), impl=1)
+    y1 = torch.empty((1, H, W, Cout), dtype=torch.int8, device="cuda")
+    y2 = torch.empty((1, H, W, Cout), dtype=torch.int8, device="cuda")
+    fast.run_device(x[0].data_ptr(), y1.data_ptr(), 1, st)
+    gen.run_device(x[0].data_ptr(), y2.data_ptr(), 1, st)
+    torch.cuda.synchronize()
+    res["verified_vs_generic_kernel"] = bool(torch.equal(y1, y2))
+    gen.close()
+    for i in range(warmup):
+        fast.run_device(x[i & 1].data_ptr(), y.data_ptr(), batch, st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fast.run_device(x[i & 1].data_ptr(), y.data_ptr(), batch, st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ops = 2.0 * fast.macs * batch
+    tops = ops / (ms * 1e-3) / 1e12
+    peak = 2.0 * peaks["bf16_tflops"]
+    res.update({"ms_per_launch": ms, "images_per_s": batch / (ms * 1e-3),
+                "roofline": {"bound": "tensor", "achieved": tops, "peak": peak, "unit": "TOP/s", "frac": tops / peak, "traffic": None,
+                             "peak_source": "2 x measured cuBLAS bf16 burst TFLOP/s (tcgen05 kind::i8 issues 2x the bf16 MAC rate); nominal dense int8 is 4500",
+                             "frac_of_nominal_4500": tops / 4500.0},
+                "l2": f"input+output per launch {(x[0].numel() + y.numel()) / 1e6:.0f} MB > 126 MB L2; inputs alternate between 2 buffers",
+                "algorithmic_bytes_per_launch": int(x[0].numel() + y.numel() + fast.weight_bytes)})
+    fast.close()
+    return res

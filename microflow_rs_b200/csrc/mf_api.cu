@@ -377,16 +377,17 @@ int mf_predict_many_device(mf_model *m, const void *d_in_q, size_t n, float *d_o
     cudaStream_t st = stream ? (cudaStream_t)stream : m->slot[0].stream;
     const size_t ie = m->spec.in_elems, oe = m->spec.out_elems;
     size_t nchunks = (n + m->chunk - 1) / m->chunk;
-    if (m->profiling) {
-        const size_t need = nchunks * (m->layers.size() + 1);
+    size_t ci = 0;
+    if (m->profiling) {   // event groups accumulate over calls until mf_model_layer_times_ms() reads and resets them
+        ci = m->prof_chunks;
+        const size_t need = (m->prof_chunks + nchunks) * (m->layers.size() + 1);
         while (m->prof_events.size() < need) {
             cudaEvent_t e;
             MF_CUDA(cudaEventCreate(&e));
             m->prof_events.push_back(e);
         }
-        m->prof_chunks = nchunks;
+        m->prof_chunks += nchunks;
     }
-    size_t ci = 0;
     for (size_t off = 0; off < n; off += m->chunk, ++ci) {
         const size_t cn = std::min(m->chunk, n - off);
         cudaEvent_t *prof = m->profiling ? &m->prof_events[ci * (m->layers.size() + 1)] : nullptr;
@@ -443,6 +444,7 @@ int mf_model_layer_times_ms(mf_model *m, float *ms, int cap) {
             MF_CUDA(cudaEventElapsedTime(&t, m->prof_events[c * (L + 1) + i], m->prof_events[c * (L + 1) + i + 1]));
             ms[i] += t;
         }
+    m->prof_chunks = 0;
     return MF_OK;
 }
 int mf_model_launch_count(const mf_model *m, uint64_t *count) {
@@ -511,11 +513,10 @@ static int run_single_layer(LayerSpec &L, int impl, const void *in, void *out, s
     return MF_OK;
 }
 
-int mf_op_conv_2d(const mf_conv_desc *d, const void *in, void *out, size_t batch) {
+static int conv_spec_from_desc(const mf_conv_desc *d, LayerSpec &L) {
     if (!d || !d->filters || !d->filter_zero_points || !d->c0 || !d->c1 || d->n_filter_zero_points < 1 || d->n_c1 < 1)
         return fail(MF_ERR_INVALID_ARG, "incomplete mf_conv_desc");
     if (d->dtype != MF_DTYPE_I8 && d->dtype != MF_DTYPE_U8) return fail(MF_ERR_UNSUPPORTED_TYPE, "dtype must be INT8 or UINT8");
-    LayerSpec L;
     L.op = d->depthwise ? MF_OP_DEPTHWISE_CONV_2D : MF_OP_CONV_2D;
     L.is_u8 = d->dtype == MF_DTYPE_U8;
     L.H = d->in_h; L.W = d->in_w; L.Cin = d->in_c; L.OH = d->out_h; L.OW = d->out_w; L.Cout = d->out_c;
@@ -523,6 +524,8 @@ int mf_op_conv_2d(const mf_conv_desc *d, const void *in, void *out, size_t batch
     L.in_zp = d->in_zero_point; L.out_scale = d->out_scale; L.out_zp = d->out_zero_point;
     if (L.H <= 0 || L.W <= 0 || L.Cin <= 0 || L.OH <= 0 || L.OW <= 0 || L.Cout <= 0 || L.KH <= 0 || L.KW <= 0 || L.sh <= 0 || L.sw <= 0)
         return fail(MF_ERR_UNSUPPORTED_SHAPE, "non-positive dimension");
+    if (L.act != MF_ACT_NONE && L.act != MF_ACT_RELU && L.act != MF_ACT_RELU6) return fail(MF_ERR_UNSUPPORTED_ACTIVATION, "unsupported fused activation");
+    if (L.pad != MF_PAD_SAME && L.pad != MF_PAD_VALID) return fail(MF_ERR_INVALID_ARG, "unknown padding");
     if (L.pad == MF_PAD_VALID && (L.sh * (L.OH - 1) + L.KH > L.H || L.sw * (L.OW - 1) + L.KW > L.W))
         return fail(MF_ERR_VIEW_OUT_OF_BOUNDS, "VALID view indexes outside the input (src/tensor.rs:222 would panic)");
     const size_t wn = d->depthwise ? (size_t)L.KH * L.KW * L.Cout : (size_t)L.Cout * L.KH * L.KW * L.Cin;
@@ -532,7 +535,62 @@ int mf_op_conv_2d(const mf_conv_desc *d, const void *in, void *out, size_t batch
     L.c1.assign(d->c1, d->c1 + d->n_c1);
     L.in_elems = (size_t)L.H * L.W * L.Cin;
     L.out_elems = (size_t)L.OH * L.OW * L.Cout;
+    L.macs = (uint64_t)L.OH * L.OW * L.Cout * L.KH * L.KW * (d->depthwise ? 1 : L.Cin);
+    activation_clamp(L.act, L.out_scale, L.out_zp, L.is_u8, L.act_lo, L.act_hi);
+    return MF_OK;
+}
+
+int mf_op_conv_2d(const mf_conv_desc *d, const void *in, void *out, size_t batch) {
+    LayerSpec L;
+    int rc = conv_spec_from_desc(d, L);
+    if (rc) return rc;
     return run_single_layer(L, d->impl, in, out, batch);
+}
+
+// ---- persistent operator object: plan once, run on device-resident buffers (benchmarks, pipelines) ----------------
+struct mf_op {
+    LayerExec exec;
+    uint8_t *d_blob = nullptr;
+    int num_sms = 148;
+};
+
+int mf_op_conv_2d_create(const mf_conv_desc *d, mf_op **out) {
+    if (!out) return fail(MF_ERR_INVALID_ARG, "null output pointer");
+    *out = nullptr;
+    int rc = check_device(nullptr);
+    if (rc) return rc;
+    LayerSpec L;
+    rc = conv_spec_from_desc(d, L);
+    if (rc) return rc;
+    std::unique_ptr<mf_op, void (*)(mf_op *)> op(new mf_op(), mf_op_destroy);
+    cudaDeviceProp prop{};
+    int dev = 0;
+    MF_CUDA(cudaGetDevice(&dev));
+    MF_CUDA(cudaGetDeviceProperties(&prop, dev));
+    op->num_sms = prop.multiProcessorCount;
+    op->exec.spec = L;
+    BlobBuilder bb;
+    op->exec.plan(bb, d->impl == 1 ? 1 : 0, true);
+    MF_CUDA(cudaMalloc(&op->d_blob, bb.bytes().size() + 256));
+    MF_CUDA(cudaMemcpy(op->d_blob, bb.bytes().data(), bb.bytes().size(), cudaMemcpyHostToDevice));
+    std::string err;
+    op->exec.resolve(op->d_blob, &err);
+    if (d->impl == 2 && op->exec.kernel == Kernel::ConvGeneric) return fail(MF_ERR_UNSUPPORTED_SHAPE, "no fast kernel takes this operator: " + op->exec.why_not_fast);
+    *out = op.release();
+    return MF_OK;
+}
+int mf_op_run_device(mf_op *op, const void *d_in, void *d_out, size_t batch, void *stream) {
+    if (!op || !d_in || !d_out) return fail(MF_ERR_INVALID_ARG, "null argument");
+    std::string err;
+    cudaError_t e = op->exec.run((const uint8_t *)d_in, (uint8_t *)d_out, (long long)batch, op->num_sms, (cudaStream_t)stream, &err);
+    if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string(kernel_name(op->exec.kernel)) + ": " + cudaGetErrorString(e) + " " + err);
+    return MF_OK;
+}
+const char *mf_op_kernel_name(const mf_op *op) { return op ? kernel_name(op->exec.kernel) : ""; }
+void mf_op_destroy(mf_op *op) {
+    if (!op) return;
+    if (op->d_blob) cudaFree(op->d_blob);
+    delete op;
 }
 
 int mf_op_fully_connected(const mf_fc_desc *d, const void *in, void *out, size_t batch) {

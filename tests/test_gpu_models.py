@@ -1,0 +1,126 @@
+"""GPU parity, model level, through the reference-shaped API (predict / predict_quantized / predict_many) of the C-ABI:
+the reference's end-to-end goldens, the 500-row sine CSV, the sample inputs, and seeded random batches checked against
+the oracle layer by layer (trace), at the final quantized output and at the pre-softmax logits."""
+import numpy as np
+import pytest
+
+import microflow_rs_b200 as mf
+import oracle
+from conftest import GOLDEN, MODELS, f32, splitmix_bytes
+
+pytestmark = pytest.mark.gpu
+NAMES = ["sine", "speech", "person_detect"]
+SEEDS = {"sine": 0x5EED0001, "speech": 0x5EED0002, "person_detect": 0x5EED0003}
+
+
+@pytest.fixture(scope="module")
+def gpu_models():
+    ms = {n: mf.Model(MODELS / f"{n}.tflite") for n in NAMES}
+    yield ms
+    for m in ms.values():
+        m.close()
+
+
+@pytest.fixture(scope="module")
+def ora():
+    return {n: oracle.Model(MODELS / f"{n}.tflite", fast=True) for n in NAMES}
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_e2e_goldens(gpu_models, kats, name):
+    k = kats["e2e"][name]
+    m = gpu_models[name]
+    out = m.predict(np.full(m.in_shape, k["input_fill"], np.float32))
+    np.testing.assert_array_equal(out.reshape(-1), f32(k["output"]))
+
+
+def test_sine_accuracy_csv_500_rows(gpu_models):
+    rows = np.loadtxt(GOLDEN / "sine_microflow.csv", delimiter=",", skiprows=1, dtype=np.float32)
+    m = gpu_models["sine"]
+    one_by_one = np.array([m.predict(f32([[x]]))[0, 0] for x in rows[:50, 0]], np.float32)
+    np.testing.assert_array_equal(one_by_one, rows[:50, 1])
+    batched = m.predict_many(np.ascontiguousarray(rows[:, 0]))
+    np.testing.assert_array_equal(batched.reshape(-1), rows[:, 1])
+
+
+def test_samples(gpu_models, samples):
+    sp, pd_ = gpu_models["speech"], gpu_models["person_detect"]
+    np.testing.assert_array_equal(sp.predict_quantized(samples["YES"]).reshape(-1), f32([0, 0, 0.99609375, 0]))
+    np.testing.assert_array_equal(sp.predict_quantized(samples["NO"]).reshape(-1), f32([0, 0.0546875, 0, 0.9453125]))
+    np.testing.assert_array_equal(pd_.predict_quantized(samples["PERSON"]).reshape(-1), f32([0.26953125, 0.73046875]))
+    np.testing.assert_array_equal(pd_.predict_quantized(samples["NO_PERSON"]).reshape(-1), f32([0.6171875, 0.3828125]))
+
+
+@pytest.mark.parametrize("name,n", [("sine", 64), ("speech", 24), ("person_detect", 6)])
+@pytest.mark.parametrize("flags", [0, mf.FLAG_NO_TENSOR_CORE, mf.FLAG_FORCE_GENERIC])
+def test_trace_every_layer_vs_oracle(ora, name, n, flags):
+    o = ora[name]
+    m = mf.Model(MODELS / f"{name}.tflite", flags=flags)
+    try:
+        xs = splitmix_bytes(SEEDS[name], n * o.in_elems).reshape(n, -1)
+        tr = m.predict_trace(xs)
+        for s in range(n):
+            _, q, ot = o.predict_quantized(xs[s], return_q=True, trace=True)
+            for i, (a, b) in enumerate(zip(tr, ot)):
+                assert np.array_equal(a[s], b.reshape(-1)), f"{name} sample {s}: layer {i} ({m.layers[i]['op']}, {m.layers[i]['kernel']}) differs"
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("name,n", [("sine", 3000), ("speech", 600), ("person_detect", 300)])
+def test_predict_many_vs_oracle(gpu_models, ora, name, n):
+    m, o = gpu_models[name], ora[name]
+    xs = splitmix_bytes(SEEDS[name], n * o.in_elems).reshape(n, -1)
+    want_f, want_q = o.predict_many_quantized(xs, threads=oracle.max_threads())
+    got_f = m.predict_many_quantized(xs)
+    np.testing.assert_array_equal(got_f, want_f)
+    got_q, logits = m.predict_many_logits(xs)
+    np.testing.assert_array_equal(got_q, want_q)
+    if logits is not None:   # pre-softmax logits: the part of the output that is pinned independently of libm expf
+        idx = max(i for i, L in enumerate(o.layers) if L["op"] == "softmax")
+        for s in range(0, n, max(1, n // 16)):
+            _, _, tr = o.predict_quantized(xs[s], return_q=True, trace=True)
+            np.testing.assert_array_equal(logits[s], tr[idx - 1].reshape(-1))
+
+
+def test_f32_predict_many_equals_quantize_then_predict(gpu_models, ora):
+    m, o = gpu_models["speech"], ora["speech"]
+    r = np.random.default_rng(5)
+    xf = r.uniform(-14, 14, (40, o.in_elems)).astype(np.float32)
+    got = m.predict_many(xf)
+    want = np.stack([o.predict(xf[s]).reshape(-1) for s in range(40)])
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("name,n", [("speech", 4096), ("person_detect", 4099)])
+def test_full_size_fast_equals_generic_and_chunking_is_invisible(name, n):
+    """At (near) BASELINE batch sizes the oracle is too slow; use size-independent properties instead: the fast path equals the
+    generic cross-check path bit for bit, results do not depend on the chunk size, and duplicated rows give duplicated outputs."""
+    base = splitmix_bytes(SEEDS[name] + 7, 1024 * oracle.Model(MODELS / f"{name}.tflite").in_elems).reshape(1024, -1)
+    xs = np.concatenate([base] * (n // 1024) + [base[: n % 1024]])
+    a = mf.Model(MODELS / f"{name}.tflite", chunk=2048)
+    b = mf.Model(MODELS / f"{name}.tflite", chunk=333, flags=mf.FLAG_FORCE_GENERIC)
+    try:
+        qa, la = a.predict_many_logits(xs)
+        qb, lb = b.predict_many_logits(xs)
+        np.testing.assert_array_equal(qa, qb)
+        np.testing.assert_array_equal(la, lb)
+        np.testing.assert_array_equal(qa[:1024], qa[1024:2048])
+        assert a.launch_count() > 0 and any("conv_tc" in L["kernel"] for L in a.layers) == (name == "person_detect")
+    finally:
+        a.close(); b.close()
+
+
+def test_device_resident_api(gpu_models, ora):
+    torch = pytest.importorskip("torch")
+    m, o = gpu_models["person_detect"], ora["person_detect"]
+    n = 64
+    xs = splitmix_bytes(0x5EED0004, n * o.in_elems).reshape(n, -1)
+    d_in = torch.from_numpy(xs.copy()).cuda()
+    d_out = torch.empty((n, o.out_elems), dtype=torch.float32, device="cuda")
+    d_q = torch.empty((n, o.out_elems), dtype=torch.int8, device="cuda")
+    m.predict_many_device(d_in.data_ptr(), n, d_out.data_ptr(), d_q.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    want_f, want_q = o.predict_many_quantized(xs, threads=oracle.max_threads())
+    np.testing.assert_array_equal(d_out.cpu().numpy(), want_f)
+    np.testing.assert_array_equal(d_q.cpu().numpy(), want_q)

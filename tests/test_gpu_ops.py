@@ -1,0 +1,226 @@
+"""GPU parity, op level: every reference op KAT driven through the C-ABI per-op hooks, then seeded differential tests
+CUDA-vs-oracle (bit-exact) over shapes of the three models, odd shapes, strides, paddings, non-zero weight
+zero-points and uint8.  `impl=1` = generic kernels, `impl=0` = whatever the engine would pick (fast / tensor core)."""
+import zlib
+
+import numpy as np
+import pytest
+
+import microflow_rs_b200 as mf
+import oracle
+from conftest import f32
+
+pytestmark = pytest.mark.gpu
+
+
+def _arr(d, dtype=np.int8):
+    return np.array(d["data"], dtype=dtype).reshape(d["shape"])
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+# ---------------------------------------------------------------- reference KATs on the GPU ------------------
+@pytest.mark.parametrize("impl", [0, 1])
+def test_conv_2d_kat(kats, impl):
+    k = kats["conv_2d"]
+    x, f = _arr(k["input"]), _arr(k["filters"])
+    out = mf.ops.conv_2d(x[None], k["input"]["zero_point"], f, k["filters"]["zero_point"], k["output_scale"], k["output_zero_point"], k["act"],
+                         k["pad"], k["strides"], f32(k["constants"][0]), f32(k["constants"][1]), k["output"]["shape"][:2], impl=impl)
+    np.testing.assert_array_equal(out[0], _arr(k["output"]))
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_depthwise_conv_2d_kat(kats, impl):
+    k = kats["depthwise_conv_2d"]
+    x, w = _arr(k["input"]), _arr(k["weights"])
+    out = mf.ops.depthwise_conv_2d(x[None], k["input"]["zero_point"], w, k["weights"]["zero_point"], k["output_scale"], k["output_zero_point"],
+                                   k["act"], k["pad"], k["strides"], f32(k["constants"][0]), f32(k["constants"][1]), k["output"]["shape"][:2],
+                                   impl=impl)
+    np.testing.assert_array_equal(out[0], _arr(k["output"]))
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_fully_connected_kat(kats, impl):
+    k = kats["fully_connected"]
+    x = _arr(k["input"])
+    w_nk = np.ascontiguousarray(_arr(k["weights_kn"]).T)
+    c0, c1, c2, c3 = k["constants"]
+    out = mf.ops.fully_connected(x, w_nk, k["weights_kn"]["zero_point"], k["output_scale"], k["output_zero_point"], k["act"], f32(c0), c1, c2, c3,
+                                 impl=impl)
+    np.testing.assert_array_equal(out, _arr(k["output"]))
+
+
+def test_average_pool_2d_kat(kats):
+    k = kats["average_pool_2d"]
+    out = mf.ops.average_pool_2d(_arr(k["input"])[None], k["filter_shape"], k["output_scale"], k["output_zero_point"], k["act"], k["pad"],
+                                 k["strides"], k["constants"][0], k["constants"][1], k["output"]["shape"][:2])
+    np.testing.assert_array_equal(out[0], _arr(k["output"]))
+
+
+def test_softmax_kat(kats):
+    k = kats["softmax"]
+    out = mf.ops.softmax(_arr(k["input"])[None], k["input"]["scale"], k["output_scale"], k["output_zero_point"])
+    np.testing.assert_array_equal(out[0], _arr(k["output"]))
+
+
+def test_quantize_dequantize_kats(kats):
+    t = kats["tensor"]["t2d"]
+    np.testing.assert_array_equal(mf.ops.quantize(f32(t["buffer"]), t["scale"], t["zero_point"]), np.array(t["quantized"], np.int8))
+    np.testing.assert_array_equal(mf.ops.dequantize(np.array(t["quantized"], np.int8), t["scale"], t["zero_point"]), f32(t["dequantized"]))
+    t = kats["tensor"]["t4d"]
+    np.testing.assert_array_equal(mf.ops.quantize(f32(t["buffer"]), t["scale"], t["zero_point"]), np.array(t["quantized"], np.int8))
+    np.testing.assert_array_equal(mf.ops.dequantize(np.array(t["quantized"], np.int8), t["scale"], t["zero_point"]), f32(t["buffer"]))
+    k = kats["quantize"]
+    assert mf.ops.quantize(f32([k["value"]]), k["scale"], k["zero_point"])[0] == k["quantized"]
+
+
+def test_quantize_matches_oracle_on_ties_and_extremes():
+    xs = f32(np.concatenate([np.arange(-70, 70) * 0.05, [0.5, -0.5, 1.5, 2.5, -2.5, 1e9, -1e9, 0.49999997, 12.7, 12.75, -12.85, np.nan]]))
+    for scale, zp in [(0.1, 2), (0.05, -3), (1.0, 0), (0.0078431, -1)]:
+        got = mf.ops.quantize(xs, scale, zp)
+        want = np.array([oracle.quantize(v, scale, zp) for v in xs], np.int8)
+        np.testing.assert_array_equal(got, want)
+
+
+# ---------------------------------------------------------------- differential helpers -----------------------
+def _conv_case(r, B, H, W, Cin, Cout, KH, KW, sh, sw, pad, act, dw, dtype, wzp0, per_channel=True):
+    lo, hi = (0, 256) if dtype == np.uint8 else (-128, 128)
+    x = r.integers(lo, hi, (B, H, W, Cin)).astype(dtype)
+    wshape = (1, KH, KW, Cout) if dw else (Cout, KH, KW, Cin)
+    w = r.integers(lo, hi, wshape).astype(dtype)
+    nq = Cout if per_channel else 1
+    wzp = np.zeros(nq, np.int32) if wzp0 else r.integers(lo, hi, nq).astype(np.int32)
+    in_zp = int(r.integers(lo, hi))
+    out_zp = int(r.integers(lo, hi))
+    kdim = KH * KW * (1 if dw else Cin)
+    c1 = (r.uniform(0.2, 2.0, nq) / (kdim * 40.0)).astype(np.float32)
+    c0 = r.uniform(-20, 20, Cout).astype(np.float32)
+    if pad == "same":
+        OH, OW = -(-H // sh), -(-W // sw)
+    else:
+        OH, OW = (H - KH) // sh + 1, (W - KW) // sw + 1
+    out_scale = np.float32(r.uniform(0.02, 0.2))
+    return dict(x=x, in_zp=in_zp, w=w, wzp=wzp, out_scale=out_scale, out_zp=out_zp, act=act, pad=pad, strides=(sh, sw), c0=c0, c1=c1,
+                out_hw=(OH, OW), dw=dw)
+
+
+def _run_conv(c, impl):
+    got = mf.ops.conv_2d(c["x"], c["in_zp"], c["w"], c["wzp"], c["out_scale"], c["out_zp"], c["act"], c["pad"], c["strides"], c["c0"], c["c1"],
+                         c["out_hw"], depthwise=c["dw"], impl=impl)
+    kern = mf.ops.last_kernel
+    want = np.stack([oracle.conv_2d(c["x"][b], c["in_zp"], c["w"], c["wzp"], c["out_scale"], c["out_zp"], c["act"], c["pad"], c["strides"], c["c0"],
+                                    c["c1"], c["out_hw"], depthwise=c["dw"]) for b in range(c["x"].shape[0])])
+    return got, want, kern
+
+
+GENERIC_CASES = [
+    # B, H, W, Cin, Cout, KH, KW, sh, sw, pad, act, dw, dtype, wzp0
+    (2, 5, 7, 3, 4, 3, 3, 1, 1, "same", "none", False, np.int8, False),
+    (2, 6, 6, 2, 5, 3, 3, 2, 2, "same", "relu", False, np.int8, False),     # stride 2, even input: MicroFlow pads top/left
+    (1, 9, 8, 4, 3, 2, 3, 1, 2, "same", "relu6", False, np.int8, False),    # even kernel height
+    (2, 8, 9, 3, 2, 3, 2, 2, 1, "valid", "none", False, np.int8, False),
+    (2, 7, 5, 3, 3, 3, 3, 1, 1, "same", "relu6", True, np.int8, False),     # depthwise, general zero points
+    (2, 6, 6, 1, 4, 3, 3, 2, 2, "same", "none", True, np.int8, False),      # depth multiplier (channel fallback to 0)
+    (1, 5, 5, 2, 5, 2, 2, 1, 1, "valid", "relu", True, np.int8, False),     # Cout > Cin > 1: channels >= Cin read channel 0
+    (2, 5, 6, 3, 4, 3, 3, 1, 1, "same", "relu", False, np.uint8, False),    # uint8
+    (2, 5, 6, 4, 4, 3, 3, 2, 1, "same", "none", True, np.uint8, False),
+    (1, 1, 1, 8, 4, 1, 1, 1, 1, "same", "none", False, np.int8, True),
+    (1, 3, 3, 4, 4, 5, 5, 1, 1, "same", "none", False, np.int8, True),      # kernel larger than the image
+]
+
+
+@pytest.mark.parametrize("case", GENERIC_CASES)
+def test_conv_generic_vs_oracle(case):
+    B, H, W, Cin, Cout, KH, KW, sh, sw, pad, act, dw, dtype, wzp0 = case
+    c = _conv_case(rng(zlib.crc32(repr(case).encode())), B, H, W, Cin, Cout, KH, KW, sh, sw, pad, act, dw, dtype, wzp0)
+    got, want, kern = _run_conv(c, impl=1)
+    assert "generic" in kern
+    np.testing.assert_array_equal(got, want)
+
+
+FAST_SIMT_CASES = [
+    # shapes of person_detect / speech depthwise layers (scaled-down spatial extents keep the oracle fast) + odd ones
+    (3, 12, 12, 8, 8, 3, 3, 1, 1, "same", "relu6", True, "dwconv_c4"),
+    (3, 12, 12, 16, 16, 3, 3, 2, 2, "same", "relu6", True, "dwconv_c4"),
+    (2, 6, 6, 128, 128, 3, 3, 1, 1, "same", "relu6", True, "dwconv_c4"),
+    (2, 3, 3, 256, 256, 3, 3, 1, 1, "same", "relu6", True, "dwconv_c4"),
+    (2, 7, 9, 12, 12, 5, 3, 2, 1, "same", "relu", True, "dwconv_c4"),
+    (2, 9, 7, 4, 4, 3, 3, 1, 1, "valid", "none", True, "dwconv_c4"),
+    (3, 96, 96, 1, 8, 3, 3, 2, 2, "same", "relu6", True, "dwconv_cin1"),     # person_detect layer 0
+    (3, 49, 40, 1, 8, 10, 8, 2, 2, "same", "relu", True, "dwconv_cin1"),     # speech layer 1
+    (2, 11, 13, 1, 16, 3, 5, 1, 2, "valid", "none", True, "dwconv_cin1"),
+    (3, 12, 12, 8, 16, 1, 1, 1, 1, "same", "relu6", False, "pwconv_dp4a|conv_tc"),   # person_detect layer 2 shape
+    (2, 5, 5, 12, 20, 1, 1, 1, 1, "same", "none", False, "pwconv_dp4a"),
+    (2, 6, 6, 8, 4, 1, 1, 2, 2, "same", "relu", False, "pwconv_dp4a"),
+    (5, 1, 1, 256, 4, 1, 1, 1, 1, "same", "none", False, "pwconv_dp4a"),
+]
+
+
+@pytest.mark.parametrize("case", FAST_SIMT_CASES)
+def test_conv_fast_simt_vs_oracle(case):
+    import re
+    B, H, W, Cin, Cout, KH, KW, sh, sw, pad, act, dw, kname = case
+    c = _conv_case(rng(zlib.crc32(repr(case).encode())), B, H, W, Cin, Cout, KH, KW, sh, sw, pad, act, dw, np.int8, True)
+    got, want, kern = _run_conv(c, impl=0)
+    assert re.search(kname, kern), kern
+    np.testing.assert_array_equal(got, want)
+    got_g, _, _ = _run_conv(c, impl=1)
+    np.testing.assert_array_equal(got_g, want)
+
+
+def test_requant_saturation_and_large_accumulators():
+    """Accumulators beyond 2^24 (i32->f32 rounding), saturation at both ends, ties."""
+    r = rng(7)
+    B, H, W, Cin, Cout = 2, 4, 4, 1152, 8
+    x = r.integers(100, 128, (B, H, W, Cin)).astype(np.int8)
+    w = r.integers(100, 128, (Cout, 1, 1, Cin)).astype(np.int8)
+    w[1] = -w[1]
+    c1 = f32([1e-5, 1e-5, 3e-6, 1.0, 0.5, 0.25, 7.62939453125e-06, 2.0])
+    c0 = f32([0, 0, 0.5, 0, -0.5, 1e9, -30.5, -1e9])
+    for impl in (0, 1):
+        got = mf.ops.conv_2d(x, -128, w, [0], 0.05, -3, "none", "same", (1, 1), c0, c1, (H, W), impl=impl)
+        want = np.stack([oracle.conv_2d(x[b], -128, w, [0], 0.05, -3, "none", "same", (1, 1), c0, c1, (H, W)) for b in range(B)])
+        np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("K,N,B,wzp,dtype", [(1, 16, 5, 0, np.int8), (16, 16, 7, 0, np.int8), (16, 1, 3, 0, np.int8), (4000, 4, 9, 0, np.int8),
+                                              (37, 5, 4, 22, np.int8), (64, 8, 6, -7, np.int8), (48, 3, 4, 9, np.uint8)])
+def test_fully_connected_vs_oracle(K, N, B, wzp, dtype):
+    r = rng(K * 131 + N)
+    lo, hi = (0, 256) if dtype == np.uint8 else (-128, 128)
+    x = r.integers(lo, hi, (B, K)).astype(dtype)
+    w = r.integers(lo, hi, (N, K)).astype(dtype)
+    in_zp = int(r.integers(lo, hi))
+    c0 = r.uniform(-10, 10, N).astype(np.float32)
+    c1 = np.float32(1.0 / (K * 30.0))
+    c2 = (w.astype(np.int32).sum(1) * in_zp).astype(np.int32)
+    c3 = K * in_zp * wzp
+    for impl in (0, 1):
+        got = mf.ops.fully_connected(x, w, wzp, 0.1, 3, "relu", c0, c1, c2, c3, impl=impl)
+        want = oracle.fully_connected(x, w, wzp, 0.1, 3, "relu", c0, c1, c2, c3)
+        np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("H,W,C,FH,FW,sh,sw,pad,dtype", [(3, 3, 256, 3, 3, 2, 2, "valid", np.int8), (7, 9, 5, 2, 3, 1, 2, "same", np.int8),
+                                                           (8, 8, 4, 3, 3, 2, 2, "same", np.uint8)])
+def test_average_pool_vs_oracle(H, W, C, FH, FW, sh, sw, pad, dtype):
+    r = rng(H * 100 + C)
+    lo, hi = (0, 256) if dtype == np.uint8 else (-128, 128)
+    x = r.integers(lo, hi, (3, H, W, C)).astype(dtype)
+    OH, OW = (-(-H // sh), -(-W // sw)) if pad == "same" else ((H - FH) // sh + 1, (W - FW) // sw + 1)
+    c0, c1 = oracle.pool_preprocess(0.0235294, -128 if dtype == np.int8 else 3, 0.0186093, -128 if dtype == np.int8 else 7)
+    got = mf.ops.average_pool_2d(x, (FH, FW), 0.0186093, -128 if dtype == np.int8 else 7, "none", pad, (sh, sw), c0, c1, (OH, OW))
+    want = np.stack([oracle.average_pool_2d(x[b], (FH, FW), 0.0186093, -128 if dtype == np.int8 else 7, "none", pad, (sh, sw), c0, c1, (OH, OW))
+                     for b in range(3)])
+    np.testing.assert_array_equal(got, want)
+
+
+def test_softmax_all_256_inputs_vs_oracle():
+    """Every int8 value through the exp table, for the two scales the shipped models use."""
+    for in_scale in (0.0917319, 0.0125188):
+        x = np.arange(-128, 128, dtype=np.int8).reshape(64, 1, 4)
+        got = mf.ops.softmax(x, in_scale, 1.0 / 256.0, -128)
+        want = np.stack([oracle.softmax(x[b], in_scale, 1.0 / 256.0, -128) for b in range(64)])
+        np.testing.assert_array_equal(got, want)
