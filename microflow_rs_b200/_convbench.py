@@ -14,6 +14,7 @@ def run(torch, w, c0, c1, in_zp, out_zp, out_scale, H, W, batch, steps, warmup, 
     x = [torch.randint(-128, 128, (batch, H, W, Cin), dtype=torch.int8, device="cuda", generator=g) for _ in range(2)]
     y = torch.empty((batch, H, W, Cout), dtype=torch.int8, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
+    assert st != 0, "run under a non-default torch stream so that the CUDA events bracket the kernel launches"
     # correctness guard inside the bench: one image against the generic direct kernel (bit-exact)
     gen = ConvOp((H, W, Cin), in_zp, w, [0], out_scale, out_zp, "relu6", "same", (1, 1), c0, c1, (H, W), impl=1)
     y1 = torch.empty((1, H, W, Cout), dtype=torch.int8, device="cuda")
@@ -44,3 +45,32 @@ def run(torch, w, c0, c1, in_zp, out_zp, out_scale, H, W, batch, steps, warmup, 
                 "algorithmic_bytes_per_launch": int(x[0].numel() + y.numel() + fast.weight_bytes)})
     fast.close()
     return res
+
+
+def main():
+    """python -m microflow_rs_b200._convbench [batch] [steps] -- stand-alone BASELINE config 5 run (used under ncu)."""
+    import json
+    import sys
+    from pathlib import Path
+
+    import torch
+    root = Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root))
+    import bench
+    batch = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    peaks, _ = bench.load_peaks()
+    torch.cuda.set_stream(torch.cuda.Stream())
+    H = W = 224
+    Cin = Cout = 128
+    seed = 0x5EED0005
+    w = bench.splitmix_bytes(seed, Cout * 9 * Cin).reshape(Cout, 3, 3, Cin)
+    r = np.random.default_rng(seed)
+    c1 = r.uniform(1e-3, 1e-2, Cout).astype(np.float32)
+    c0 = r.uniform(-4, 4, Cout).astype(np.float32)
+    print(json.dumps(run(torch, w, c0, c1, in_zp=-128, out_zp=-128, out_scale=0.0235294, H=H, W=W, batch=batch, steps=steps, warmup=3, peaks=peaks,
+                         seed=seed)))
+
+
+if __name__ == "__main__":
+    main()

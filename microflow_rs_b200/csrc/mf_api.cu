@@ -217,7 +217,7 @@ int create_model(const uint8_t *buf, size_t len, const mf_options *opt, mf_model
         }
     m->blob_bytes = bb.bytes().size();
     if (have_device) {
-        m->chunk = o.chunk ? o.chunk : 2048;
+        m->chunk = o.chunk ? o.chunk : 4096;
         if (m->blob_bytes) {
             MF_CUDA(cudaMalloc(&m->d_blob, m->blob_bytes));
             MF_CUDA(cudaMemcpy(m->d_blob, bb.bytes().data(), m->blob_bytes, cudaMemcpyHostToDevice));

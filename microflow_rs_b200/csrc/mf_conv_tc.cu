@@ -2,14 +2,16 @@
 //
 // Replaces src/ops/conv_2d.rs:28-108 for the shapes that are worth a tensor core:
 //   * 3x3 stride-1 SAME convolutions with Cin a multiple of 128  (BASELINE config 5: 224x224x128 -> 128)
-//   * every 1x1 convolution of person_detect, as a "packed pixel" GEMM (see mf_conv_tc.h)
+//   * every 1x1 convolution of person_detect but the last (256 -> 2), as a "packed pixel" GEMM (see mf_conv_tc.h)
 //
 // Pipeline inside one persistent CTA (256 threads, 1 CTA / SM):
 //   warp 0 (one lane)  TMA producer : cp.async.bulk.tensor.4d  global -> smem ring (SWIZZLE_128B), mbarrier tx
 //   warp 1 (one lane)  MMA issuer   : tcgen05.mma.cta_group::1.kind::i8, D in TMEM (2 accumulator buffers)
 //   warp 2             TMEM alloc / dealloc
-//   warps 4..7         epilogue     : tcgen05.ld 32x32b -> registers -> exact f32 requantize (mf_device.cuh)
-//                                     -> int8 pack -> 16-byte global stores
+//   warps 4..19        epilogue     : 16 warps = 4 TMEM lane quarters x 4 column groups; tcgen05.ld 32x32b -> registers
+//                                     -> exact f32 requantize (mf_device.cuh) -> int8 pack -> 16-byte global stores.
+//                                     (The epilogue is ~8 ALU instructions per output value; one warp per scheduler cannot
+//                                     hide its own latencies, four can, and the MMA of the next tile runs underneath.)
 // The weights (B operand, <= 147 KB) are loaded once per CTA and stay in shared memory.
 //
 // Arithmetic: int32 accumulation is exact and order-independent, so any tiling is bit-identical to the
@@ -21,6 +23,8 @@
 
 #include <cstring>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include "mf_conv_tc.h"
 #include "mf_device.cuh"
@@ -30,7 +34,8 @@ namespace mf {
 namespace {
 
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr uint32_t kSmemLimit = 232448;  // 227 KB usable per CTA on sm_100
 
 struct ConvTcParams {
@@ -127,6 +132,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+template <bool FULL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -156,7 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(bfull_bar, 1);
         mbar_init(tfull_bar(0), 1); mbar_init(tfull_bar(1), 1);
-        mbar_init(tempty_bar(0), 128); mbar_init(tempty_bar(1), 128);
+        mbar_init(tempty_bar(0), kEpiWarps); mbar_init(tempty_bar(1), kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -165,8 +171,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     if (warp >= 4) {  // per-channel epilogue tables -> smem
         const int t = threadIdx.x - 128;
-        for (int k = t; k < p.N; k += 128) { s_c0z[k] = p.c0z[k]; s_c1[k] = p.c1[k]; }
-        for (int k = t; k < p.ncls * p.N; k += 128) s_corr[k] = p.corr[k];
+        for (int k = t; k < p.N; k += 32 * kEpiWarps) { s_c0z[k] = p.c0z[k]; s_c1[k] = p.c1[k]; }
+        for (int k = t; k < p.ncls * p.N; k += 32 * kEpiWarps) s_corr[k] = p.corr[k];
     }
     tc_fence_before();
     __syncthreads();
@@ -230,8 +236,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue =====
-        const uint32_t q = (uint32_t)(warp & 3);
+        // ===== epilogue: warp e = (lane quarter q, column group cg); chunk c of 32 columns belongs to group c % 4 =====
+        const uint32_t q = (uint32_t)(warp & 3);               // == warp % 4: the TMEM lane quarter this warp may read
+        const int cg = (warp - 4) >> 2;
         const int row = (int)(q * 32 + lane);
         const int rr = row >> p.tw_log2, rc = row & (p.TW - 1);
         uint32_t it = 0;
@@ -250,7 +257,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_wait(tfull_bar(acc), aph);
             tc_fence_after();
             const uint32_t t_base = tmem_base + acc * (uint32_t)p.N + ((q * 32u) << 16);
-            for (int c0 = 0; c0 < p.N; c0 += 32) {
+            for (int c0 = 32 * cg; c0 < p.N; c0 += 128) {
                 uint32_t r[32];
                 tmem_ld32(t_base + (uint32_t)c0, r);
                 uint32_t w[8];
@@ -259,10 +266,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const float4 z = *reinterpret_cast<const float4 *>(s_c0z + c0 + 4 * g);
                     const float4 sc = *reinterpret_cast<const float4 *>(s_c1 + c0 + 4 * g);
                     const int4 kc = *reinterpret_cast<const int4 *>(corr + c0 + 4 * g);
-                    const int y0 = requant((int)r[4 * g + 0] - kc.x, z.x, sc.x, p.lo, p.hi);
-                    const int y1 = requant((int)r[4 * g + 1] - kc.y, z.y, sc.y, p.lo, p.hi);
-                    const int y2 = requant((int)r[4 * g + 2] - kc.z, z.z, sc.z, p.lo, p.hi);
-                    const int y3 = requant((int)r[4 * g + 3] - kc.w, z.w, sc.w, p.lo, p.hi);
+                    const int y0 = requant_t<FULL>((int)r[4 * g + 0] - kc.x, z.x, sc.x, p.lo, p.hi);
+                    const int y1 = requant_t<FULL>((int)r[4 * g + 1] - kc.y, z.y, sc.y, p.lo, p.hi);
+                    const int y2 = requant_t<FULL>((int)r[4 * g + 2] - kc.z, z.z, sc.z, p.lo, p.hi);
+                    const int y3 = requant_t<FULL>((int)r[4 * g + 3] - kc.w, z.w, sc.w, p.lo, p.hi);
                     w[g] = pack4(y0, y1, y2, y3);
                 }
                 if (valid) {
@@ -272,7 +279,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
             }
             tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
     }
 
@@ -394,13 +402,37 @@ bool conv_tc_finalize_plan(ConvTcPlan &p, std::string *why) {
     return true;
 }
 
+namespace {
+struct MapKey {
+    const void *p; long long W, H, B; int C, TW, BH;
+    bool operator==(const MapKey &o) const { return p == o.p && W == o.W && H == o.H && B == o.B && C == o.C && TW == o.TW && BH == o.BH; }
+};
+struct MapCache {   // activation tensor maps are re-used launch after launch (ping-pong buffers): encode each once
+    std::mutex mu;
+    std::vector<std::pair<MapKey, CUtensorMap>> v;
+};
+MapCache g_maps;
+}  // namespace
+
 cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_sms, cudaStream_t s, std::string *why) {
     CUtensorMap ta, tb;
     std::memcpy(&tb, p.tmap_b, sizeof tb);
-    cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)l.W, (cuuint64_t)l.H, (cuuint64_t)l.B};
-    cuuint64_t strides[3] = {(cuuint64_t)p.C, (cuuint64_t)p.C * l.W, (cuuint64_t)p.C * l.W * l.H};
-    cuuint32_t box[4] = {128, (cuuint32_t)p.TW, (cuuint32_t)(p.TH + p.KH - 1), 1};
-    if (!encode_map(&ta, l.in, 4, dims, strides, box, why)) return cudaErrorInvalidValue;
+    const MapKey key{l.in, l.W, l.H, l.B, p.C, p.TW, p.TH + p.KH - 1};
+    bool found = false;
+    {
+        std::lock_guard<std::mutex> lock(g_maps.mu);
+        for (auto &e : g_maps.v)
+            if (e.first == key) { ta = e.second; found = true; break; }
+    }
+    if (!found) {
+        cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)l.W, (cuuint64_t)l.H, (cuuint64_t)l.B};
+        cuuint64_t strides[3] = {(cuuint64_t)p.C, (cuuint64_t)p.C * l.W, (cuuint64_t)p.C * l.W * l.H};
+        cuuint32_t box[4] = {128, (cuuint32_t)p.TW, (cuuint32_t)(p.TH + p.KH - 1), 1};
+        if (!encode_map(&ta, l.in, 4, dims, strides, box, why)) return cudaErrorInvalidValue;
+        std::lock_guard<std::mutex> lock(g_maps.mu);
+        if (g_maps.v.size() >= 256) g_maps.v.clear();
+        g_maps.v.emplace_back(key, ta);
+    }
 
     ConvTcParams k{};
     k.out = l.out; k.c0z = p.d_c0z; k.c1 = p.d_c1; k.corr = p.d_corr;
@@ -424,10 +456,14 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
 
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, [] { attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit); });
+    std::call_once(attr_once, [] {
+        attr_err = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
+    });
     if (attr_err != cudaSuccess) return attr_err;
     const unsigned grid = (unsigned)(k.num_tiles < num_sms ? k.num_tiles : num_sms);
-    conv_tc_kernel<<<grid, kThreads, p.smem_bytes, s>>>(ta, tb, k);
+    if (p.lo == -128.f && p.hi == 127.f) conv_tc_kernel<true><<<grid, kThreads, p.smem_bytes, s>>>(ta, tb, k);
+    else conv_tc_kernel<false><<<grid, kThreads, p.smem_bytes, s>>>(ta, tb, k);
     return cudaGetLastError();
 }
 

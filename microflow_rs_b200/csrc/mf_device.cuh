@@ -40,9 +40,24 @@ template <bool U8> __device__ __forceinline__ int ld_elem(const uint8_t *p) {
     return U8 ? (int)(*p) : (int)(*(const int8_t *)p);
 }
 
-// pack four values already clamped to the int8 (or uint8) range into one word
+// pack four values already clamped to the int8 (or uint8) range into one word: 3 PRMT
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
-    return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
+    const uint32_t lo = __byte_perm((uint32_t)a, (uint32_t)b, 0x0040), hi = __byte_perm((uint32_t)c, (uint32_t)d, 0x0040);
+    return __byte_perm(lo, hi, 0x5410);
+}
+
+// requant for layers whose clamp is the whole int8 range (every conv of person_detect: ReLU6's upper bound quantizes
+// to 127 and the lower bound is the zero point -128): the saturating F2I.S8 conversion replaces both FMNMX.
+// cvt.rzi.sat.s8.f32 == trunc then saturate to [-128,127], NaN -> 0 (exactly Rust's `as i8`).
+__device__ __forceinline__ int requant_full_i8(int acc, float c0z, float c1) {
+    float t = __fadd_rn(c0z, __fmul_rn(c1, __int2float_rn(acc)));
+    float s = __fadd_rn(t, round_bias(t));
+    int y;
+    asm("cvt.rzi.sat.s8.f32 %0, %1;" : "=r"(y) : "f"(s));
+    return y;
+}
+template <bool FULL> __device__ __forceinline__ int requant_t(int acc, float c0z, float c1, float lo, float hi) {
+    return FULL ? requant_full_i8(acc, c0z, c1) : requant(acc, c0z, c1, lo, hi);
 }
 
 }  // namespace mf

@@ -14,6 +14,7 @@ const char *kernel_name(Kernel k) {
         case Kernel::ConvTc3x3: return "conv_tc_kernel(3x3)";
         case Kernel::PwConvDp4a: return "pwconv_dp4a_kernel";
         case Kernel::DwConvC4: return "dwconv_c4_kernel";
+        case Kernel::DwConv3x3Rows: return "dwconv3x3_rows_kernel";
         case Kernel::DwConvCin1: return "dwconv_cin1_kernel";
         case Kernel::FcGeneric: return "fc_generic_kernel";
         case Kernel::FcWarp: return "fc_warp_kernel";
@@ -76,7 +77,8 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
         if (impl == 1) { why_not_fast = "generic kernels forced"; return; }
         if (L.is_u8 || !wz0) { why_not_fast = "uint8 or non-zero weight zero-point: generic kernel"; return; }
         if (dw) {
-            if (L.Cin == L.Cout && L.Cout % 4 == 0) kernel = Kernel::DwConvC4;
+            if (L.Cin == L.Cout && L.Cout % 4 == 0)
+                kernel = (L.KH == 3 && L.KW == 3 && L.sh == L.sw && (L.sh == 1 || L.sh == 2)) ? Kernel::DwConv3x3Rows : Kernel::DwConvC4;
             else if (L.Cin == 1 && L.Cout % 4 == 0 && L.Cout >= 4 && L.Cout <= 16) kernel = Kernel::DwConvCin1;
             else why_not_fast = "depthwise shape not covered by a fast kernel";
             return;
@@ -128,7 +130,7 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
             }
             why_not_fast = "tensor core: " + why;
         }
-        if (L.KH == 1 && L.KW == 1 && L.Cin % 4 == 0 && L.Cout % 4 == 0) kernel = Kernel::PwConvDp4a;
+        if (L.KH == 1 && L.KW == 1 && L.Cin % 4 == 0) kernel = Kernel::PwConvDp4a;
         return;
     }
     if (L.op == MF_OP_FULLY_CONNECTED) {
@@ -174,7 +176,7 @@ bool LayerExec::resolve(const uint8_t *d, std::string *err) {
             std::string why;
             if (!conv_tc_finalize_plan(tc, &why)) {  // fall back to the SIMT path, never to the CPU
                 why_not_fast = "tensor core plan rejected: " + why;
-                kernel = (L.KH == 1 && L.KW == 1 && L.Cin % 4 == 0 && L.Cout % 4 == 0) ? Kernel::PwConvDp4a : Kernel::ConvGeneric;
+                kernel = (L.KH == 1 && L.KW == 1 && L.Cin % 4 == 0) ? Kernel::PwConvDp4a : Kernel::ConvGeneric;
             }
         }
     } else if (L.op == MF_OP_FULLY_CONNECTED) {
@@ -208,12 +210,13 @@ bool LayerExec::resolve(const uint8_t *d, std::string *err) {
 cudaError_t LayerExec::run(const uint8_t *in, uint8_t *out, long long batch, int num_sms, cudaStream_t s, std::string *err) const {
     switch (kernel) {
         case Kernel::None: return cudaSuccess;
-        case Kernel::ConvGeneric: case Kernel::PwConvDp4a: case Kernel::DwConvC4: case Kernel::DwConvCin1: {
+        case Kernel::ConvGeneric: case Kernel::PwConvDp4a: case Kernel::DwConvC4: case Kernel::DwConv3x3Rows: case Kernel::DwConvCin1: {
             ConvArgs a = conv;
             a.in = in; a.out = out; a.batch = batch;
             if (kernel == Kernel::ConvGeneric) return launch_conv_generic(a, s);
             if (kernel == Kernel::PwConvDp4a) return launch_pwconv_dp4a(a, s);
             if (kernel == Kernel::DwConvC4) return launch_dwconv_c4(a, s);
+            if (kernel == Kernel::DwConv3x3Rows) return launch_dwconv3x3_rows(a, s);
             return launch_dwconv_cin1(a, s);
         }
         case Kernel::ConvTcPointwise: {

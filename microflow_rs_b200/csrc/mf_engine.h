@@ -18,6 +18,7 @@ enum class Kernel {
     ConvTc3x3,        // tcgen05 implicit GEMM
     PwConvDp4a,
     DwConvC4,
+    DwConv3x3Rows,
     DwConvCin1,
     FcGeneric,
     FcWarp,

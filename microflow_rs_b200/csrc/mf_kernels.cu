@@ -190,109 +190,218 @@ cudaError_t launch_dequantize(const uint8_t *in, float *out, size_t n, float sca
 }
 
 // ================================================================================================
-// FAST: depthwise conv, Cin == Cout = C, C % 4 == 0, int8, w_zp == 0.
-// One thread = 4 consecutive channels (one 32-bit word) of one output pixel; a warp covers 128 contiguous
-// output bytes and reads 128 contiguous input bytes per tap (stride 1).  4 MACs of different channels are
-// issued as 4 dp4a with a byte-masked weight word (no unpacking of the activations).
+// FAST kernels.  Grid: blockIdx.y = sample (grid-stride), blockIdx.x * blockDim.x + threadIdx.x = 32-bit index inside
+// the sample, decoded with FastDiv (no 64-bit div/mod on the device).
 // ================================================================================================
+static inline dim3 grid2(long long per_sample, int block, long long batch) {
+    return dim3((unsigned)((per_sample + block - 1) / block), (unsigned)(batch < 65535 ? batch : 65535), 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise conv, Cin == Cout = C, C % 4 == 0, int8, w_zp == 0, any kernel / stride / padding.
+// One thread = 4 consecutive channels (one 32-bit word) of one output pixel; a warp covers 128 contiguous
+// output bytes and reads 128 contiguous input bytes per tap (stride 1).  The 4 MACs of different channels are
+// 4 dp4a against a byte-masked weight word (no unpacking of the activations).
+// ------------------------------------------------------------------------------------------------
 template <int KH_T, int KW_T>
-__global__ void __launch_bounds__(256) dwconv_c4_kernel(ConvArgs a, long long total_words) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total_words) return;
+__global__ void __launch_bounds__(256) dwconv_c4_kernel(ConvArgs a, uint32_t words_per_sample, FastDiv fd_g, FastDiv fd_ow) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= words_per_sample) return;
     const int KH = KH_T ? KH_T : a.KH, KW = KW_T ? KW_T : a.KW;
     const int G = a.Cout >> 2;
-    const int g = (int)(idx % G);
-    long long p = idx / G;
-    const int j = (int)(p % a.OW); p /= a.OW;
-    const int i = (int)(p % a.OH);
-    const long long b = p / a.OH;
-    const uint32_t *inw = reinterpret_cast<const uint32_t *>(a.in) + (size_t)b * a.H * a.W * G;
+    uint32_t p, g, i, j;
+    fd_g.divmod(idx, p, g);
+    fd_ow.divmod(p, i, j);
     const uint32_t *ww = reinterpret_cast<const uint32_t *>(a.w);
     const uint32_t izw = (uint32_t)(a.in_zp & 0xff) * 0x01010101u;
-    int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
-#pragma unroll
-    for (int m = 0; m < KH; ++m) {
-        const int r = a.sh * i + m - a.off_r;
-        const bool rok = (unsigned)r < (unsigned)a.H;
-#pragma unroll
-        for (int n = 0; n < KW; ++n) {
-            const int c = a.sw * j + n - a.off_c;
-            const bool ok = rok && (unsigned)c < (unsigned)a.W;
-            const uint32_t v = ok ? __ldg(inw + ((size_t)r * a.W + c) * G + g) : izw;
-            const uint32_t wv = __ldg(ww + (size_t)(m * KW + n) * G + g);
-            acc0 = __dp4a((int)v, (int)(wv & 0x000000ffu), acc0);
-            acc1 = __dp4a((int)v, (int)(wv & 0x0000ff00u), acc1);
-            acc2 = __dp4a((int)v, (int)(wv & 0x00ff0000u), acc2);
-            acc3 = __dp4a((int)v, (int)(wv & 0xff000000u), acc3);
-        }
-    }
     const int4 kc = __ldg(reinterpret_cast<const int4 *>(a.kcorr) + g);
     const float4 z = __ldg(reinterpret_cast<const float4 *>(a.c0z) + g);
     const float4 s = __ldg(reinterpret_cast<const float4 *>(a.c1) + g);
-    const int y0 = requant(acc0 - kc.x, z.x, s.x, a.lo, a.hi);
-    const int y1 = requant(acc1 - kc.y, z.y, s.y, a.lo, a.hi);
-    const int y2 = requant(acc2 - kc.z, z.z, s.z, a.lo, a.hi);
-    const int y3 = requant(acc3 - kc.w, z.w, s.w, a.lo, a.hi);
-    reinterpret_cast<uint32_t *>(a.out)[idx] = pack4(y0, y1, y2, y3);
+    for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
+        const uint32_t *inw = reinterpret_cast<const uint32_t *>(a.in) + (size_t)b * a.H * a.W * G;
+        int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+#pragma unroll
+        for (int m = 0; m < KH; ++m) {
+            const int r = a.sh * (int)i + m - a.off_r;
+            const bool rok = (unsigned)r < (unsigned)a.H;
+#pragma unroll
+            for (int n = 0; n < KW; ++n) {
+                const int c = a.sw * (int)j + n - a.off_c;
+                const bool ok = rok && (unsigned)c < (unsigned)a.W;
+                const uint32_t v = ok ? __ldg(inw + ((size_t)r * a.W + c) * G + g) : izw;
+                const uint32_t wv = __ldg(ww + (size_t)(m * KW + n) * G + g);
+                acc0 = __dp4a((int)v, (int)(wv & 0x000000ffu), acc0);
+                acc1 = __dp4a((int)v, (int)(wv & 0x0000ff00u), acc1);
+                acc2 = __dp4a((int)v, (int)(wv & 0x00ff0000u), acc2);
+                acc3 = __dp4a((int)v, (int)(wv & 0xff000000u), acc3);
+            }
+        }
+        reinterpret_cast<uint32_t *>(a.out)[(size_t)b * words_per_sample + idx] =
+            pack4(requant(acc0 - kc.x, z.x, s.x, a.lo, a.hi), requant(acc1 - kc.y, z.y, s.y, a.lo, a.hi),
+                  requant(acc2 - kc.z, z.z, s.z, a.lo, a.hi), requant(acc3 - kc.w, z.w, s.w, a.lo, a.hi));
+    }
 }
 
 bool dwconv_c4_eligible(const ConvArgs &a) {
     return a.depthwise && !a.is_u8 && a.Cin == a.Cout && (a.Cout % 4) == 0 && a.kcorr != nullptr;
 }
 cudaError_t launch_dwconv_c4(const ConvArgs &a, cudaStream_t s) {
-    const long long total = a.batch * a.OH * a.OW * (a.Cout / 4);
-    if (total <= 0) return cudaSuccess;
-    if (a.KH == 3 && a.KW == 3) dwconv_c4_kernel<3, 3><<<grid_for(total, 256), 256, 0, s>>>(a, total);
-    else dwconv_c4_kernel<0, 0><<<grid_for(total, 256), 256, 0, s>>>(a, total);
+    const long long per = (long long)a.OH * a.OW * (a.Cout / 4);
+    if (per <= 0 || a.batch <= 0) return cudaSuccess;
+    const FastDiv fg((uint32_t)(a.Cout / 4)), fow((uint32_t)a.OW);
+    if (a.KH == 3 && a.KW == 3) dwconv_c4_kernel<3, 3><<<grid2(per, 256, a.batch), 256, 0, s>>>(a, (uint32_t)per, fg, fow);
+    else dwconv_c4_kernel<0, 0><<<grid2(per, 256, a.batch), 256, 0, s>>>(a, (uint32_t)per, fg, fow);
     return cudaGetLastError();
 }
 
-// ================================================================================================
-// FAST: depthwise conv with a single input channel and a depth multiplier (person_detect layer 0: 3x3 s2 -> 8 ch,
-// speech layer 1: 10x8 s2 -> 8 ch).  Output channel c reads input channel 0 (depthwise_conv_2d.rs:67).
-// One thread = one output pixel, all COUT channels; the weights of 4 channels sit in one word and the activation
-// byte is moved to the matching byte lane, so each dp4a is one exact MAC without unpacking the weights.
-// ================================================================================================
-template <int COUT>
-__global__ void __launch_bounds__(128) dwconv_cin1_kernel(ConvArgs a, long long total_px) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total_px) return;
-    constexpr int Q = COUT / 4;
-    long long p = idx;
-    const int j = (int)(p % a.OW); p /= a.OW;
-    const int i = (int)(p % a.OH);
-    const long long b = p / a.OH;
-    const uint8_t *in = a.in + (size_t)b * a.H * a.W;
+// ------------------------------------------------------------------------------------------------
+// depthwise 3x3 (every person_detect depthwise layer but the first), stride 1x1 or 2x2.
+// One thread = one 4-channel word of one output column, walking DOWN a strip of output rows with the 3x3 input
+// window held in 9 registers: each new output row loads 3 (stride 1) or 6 (stride 2) words instead of 9, and the
+// 36 byte-masked weight words, the epilogue constants and all index math are hoisted out of the row loop.
+// Lanes run along (column, channel-word), i.e. along contiguous NHWC memory: every load and store is coalesced.
+// ------------------------------------------------------------------------------------------------
+template <int S, bool FULL>
+__global__ void __launch_bounds__(128) dwconv3x3_rows_kernel(ConvArgs a, uint32_t threads_per_sample, uint32_t rows_per_strip, FastDiv fd_xw, FastDiv fd_g) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= threads_per_sample) return;
+    const int G = a.Cout >> 2;
+    uint32_t strip, x, j, g;
+    fd_xw.divmod(t, strip, x);
+    fd_g.divmod(x, j, g);
     const uint32_t *ww = reinterpret_cast<const uint32_t *>(a.w);
-    int acc[COUT];
+    uint32_t wm[9][4];
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[c] = 0;
-    for (int m = 0; m < a.KH; ++m) {
-        const int r = a.sh * i + m - a.off_r;
-        const bool rok = (unsigned)r < (unsigned)a.H;
-        for (int n = 0; n < a.KW; ++n) {
-            const int c = a.sw * j + n - a.off_c;
-            const bool ok = rok && (unsigned)c < (unsigned)a.W;
-            const uint32_t v = ok ? (uint32_t)__ldg(in + (size_t)r * a.W + c) : (uint32_t)(a.in_zp & 0xff);
-            const uint32_t v0 = v, v1 = v << 8, v2 = v << 16, v3 = v << 24;
+    for (int k = 0; k < 9; ++k) {
+        const uint32_t wv = __ldg(ww + (size_t)k * G + g);
+        wm[k][0] = wv & 0x000000ffu; wm[k][1] = wv & 0x0000ff00u; wm[k][2] = wv & 0x00ff0000u; wm[k][3] = wv & 0xff000000u;
+    }
+    const int4 kc = __ldg(reinterpret_cast<const int4 *>(a.kcorr) + g);
+    const float4 z = __ldg(reinterpret_cast<const float4 *>(a.c0z) + g);
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(a.c1) + g);
+    const uint32_t izw = (uint32_t)(a.in_zp & 0xff) * 0x01010101u;
+    const int c0 = S * (int)j - a.off_c;
+    const bool cok0 = (unsigned)c0 < (unsigned)a.W, cok1 = (unsigned)(c0 + 1) < (unsigned)a.W, cok2 = (unsigned)(c0 + 2) < (unsigned)a.W;
+    const int i0 = (int)(strip * rows_per_strip);
+    const int i1 = min(a.OH, i0 + (int)rows_per_strip);
+    const size_t row_words = (size_t)a.W * G;
+
+    for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
+        const uint32_t *inw = reinterpret_cast<const uint32_t *>(a.in) + (size_t)b * a.H * row_words + (ptrdiff_t)c0 * G + g;
+        uint32_t *outw = reinterpret_cast<uint32_t *>(a.out) + ((size_t)b * a.OH * a.OW + j) * G + g;
+        auto load_row = [&](int r, uint32_t &v0, uint32_t &v1, uint32_t &v2) {
+            const bool rok = (unsigned)r < (unsigned)a.H;
+            const uint32_t *p = inw + (ptrdiff_t)r * (ptrdiff_t)row_words;
+            v0 = (rok && cok0) ? __ldg(p) : izw;
+            v1 = (rok && cok1) ? __ldg(p + G) : izw;
+            v2 = (rok && cok2) ? __ldg(p + 2 * G) : izw;
+        };
+        uint32_t w00, w01, w02, w10, w11, w12, w20, w21, w22;
+        int r = S * i0 - a.off_r;
+        load_row(r, w00, w01, w02);
+        load_row(r + 1, w10, w11, w12);
+        for (int i = i0; i < i1; ++i) {
+            load_row(r + 2, w20, w21, w22);
+            int acc[4];
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const int wv = (int)__ldg(ww + (size_t)(m * a.KW + n) * Q + q);
-                acc[4 * q + 0] = __dp4a(wv, (int)v0, acc[4 * q + 0]);
-                acc[4 * q + 1] = __dp4a(wv, (int)v1, acc[4 * q + 1]);
-                acc[4 * q + 2] = __dp4a(wv, (int)v2, acc[4 * q + 2]);
-                acc[4 * q + 3] = __dp4a(wv, (int)v3, acc[4 * q + 3]);
+            for (int k = 0; k < 4; ++k) {
+                int s = 0;
+                s = __dp4a((int)w00, (int)wm[0][k], s); s = __dp4a((int)w01, (int)wm[1][k], s); s = __dp4a((int)w02, (int)wm[2][k], s);
+                s = __dp4a((int)w10, (int)wm[3][k], s); s = __dp4a((int)w11, (int)wm[4][k], s); s = __dp4a((int)w12, (int)wm[5][k], s);
+                s = __dp4a((int)w20, (int)wm[6][k], s); s = __dp4a((int)w21, (int)wm[7][k], s); s = __dp4a((int)w22, (int)wm[8][k], s);
+                acc[k] = s;
+            }
+            outw[(size_t)i * a.OW * G] =
+                pack4(requant_t<FULL>(acc[0] - kc.x, z.x, sc.x, a.lo, a.hi), requant_t<FULL>(acc[1] - kc.y, z.y, sc.y, a.lo, a.hi),
+                      requant_t<FULL>(acc[2] - kc.z, z.z, sc.z, a.lo, a.hi), requant_t<FULL>(acc[3] - kc.w, z.w, sc.w, a.lo, a.hi));
+            if (S == 1) {
+                w00 = w10; w01 = w11; w02 = w12;
+                w10 = w20; w11 = w21; w12 = w22;
+                r += 1;
+            } else {
+                w00 = w20; w01 = w21; w02 = w22;
+                r += 2;
+                if (i + 1 < i1) load_row(r + 1, w10, w11, w12);
             }
         }
     }
-    uint32_t *out = reinterpret_cast<uint32_t *>(a.out) + (size_t)idx * Q;
+}
+
+bool dwconv3x3_rows_eligible(const ConvArgs &a) {
+    return dwconv_c4_eligible(a) && a.KH == 3 && a.KW == 3 && a.sh == a.sw && (a.sh == 1 || a.sh == 2);
+}
+cudaError_t launch_dwconv3x3_rows(const ConvArgs &a, cudaStream_t s) {
+    if (a.batch <= 0) return cudaSuccess;
+    const int G = a.Cout / 4;
+    const uint32_t xw = (uint32_t)(a.OW * G);
+    // strips of output rows: long enough to amortise the 2 extra window rows, short enough to fill the machine
+    uint32_t rows = a.OH <= 12 ? (uint32_t)a.OH : 8u;
+    if ((long long)xw * a.batch < 148 * 4 * 128) rows = a.OH >= 4 ? (uint32_t)((a.OH + 1) / 2) : (uint32_t)a.OH;
+    const uint32_t strips = (uint32_t)((a.OH + rows - 1) / rows);
+    const long long per = (long long)strips * xw;
+    const FastDiv fxw(xw), fg((uint32_t)G);
+    const bool full = a.lo == -128.f && a.hi == 127.f;
+    const dim3 grid = grid2(per, 128, a.batch);
+    if (a.sh == 1) {
+        if (full) dwconv3x3_rows_kernel<1, true><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
+        else dwconv3x3_rows_kernel<1, false><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
+    } else {
+        if (full) dwconv3x3_rows_kernel<2, true><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
+        else dwconv3x3_rows_kernel<2, false><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise conv with a single input channel and a depth multiplier (person_detect layer 0: 3x3 s2 -> 8 ch,
+// speech layer 1: 10x8 s2 -> 8 ch).  Output channel c reads input channel 0 (depthwise_conv_2d.rs:67).
+// One thread = one output pixel, all COUT channels; the weights of 4 channels sit in one word and the activation
+// byte is moved to the matching byte lane, so each dp4a is one exact MAC without unpacking the weights.
+// ------------------------------------------------------------------------------------------------
+template <int COUT, int KH_T, int KW_T>
+__global__ void __launch_bounds__(128) dwconv_cin1_kernel(ConvArgs a, uint32_t px_per_sample, FastDiv fd_ow) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= px_per_sample) return;
+    constexpr int Q = COUT / 4;
+    const int KH = KH_T ? KH_T : a.KH, KW = KW_T ? KW_T : a.KW;
+    uint32_t i, j;
+    fd_ow.divmod(idx, i, j);
+    const uint32_t *ww = reinterpret_cast<const uint32_t *>(a.w);
+    const int r0 = a.sh * (int)i - a.off_r, c0 = a.sw * (int)j - a.off_c;
+    for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
+        const uint8_t *in = a.in + (size_t)b * a.H * a.W;
+        int acc[COUT];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
-        const int4 kc = __ldg(reinterpret_cast<const int4 *>(a.kcorr) + q);
-        const float4 z = __ldg(reinterpret_cast<const float4 *>(a.c0z) + q);
-        const float4 s = __ldg(reinterpret_cast<const float4 *>(a.c1) + q);
-        out[q] = pack4(requant(acc[4 * q + 0] - kc.x, z.x, s.x, a.lo, a.hi), requant(acc[4 * q + 1] - kc.y, z.y, s.y, a.lo, a.hi),
-                       requant(acc[4 * q + 2] - kc.z, z.z, s.z, a.lo, a.hi), requant(acc[4 * q + 3] - kc.w, z.w, s.w, a.lo, a.hi));
+        for (int c = 0; c < COUT; ++c) acc[c] = 0;
+#pragma unroll
+        for (int m = 0; m < KH; ++m) {
+            const int r = r0 + m;
+            const bool rok = (unsigned)r < (unsigned)a.H;
+#pragma unroll
+            for (int n = 0; n < KW; ++n) {
+                const int c = c0 + n;
+                const bool ok = rok && (unsigned)c < (unsigned)a.W;
+                const uint32_t v = ok ? (uint32_t)__ldg(in + (size_t)r * a.W + c) : (uint32_t)(a.in_zp & 0xff);
+                const uint32_t v1 = v << 8, v2 = v << 16, v3 = v << 24;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const int wv = (int)__ldg(ww + (size_t)(m * KW + n) * Q + q);
+                    acc[4 * q + 0] = __dp4a(wv, (int)v, acc[4 * q + 0]);
+                    acc[4 * q + 1] = __dp4a(wv, (int)v1, acc[4 * q + 1]);
+                    acc[4 * q + 2] = __dp4a(wv, (int)v2, acc[4 * q + 2]);
+                    acc[4 * q + 3] = __dp4a(wv, (int)v3, acc[4 * q + 3]);
+                }
+            }
+        }
+        uint32_t *out = reinterpret_cast<uint32_t *>(a.out) + ((size_t)b * px_per_sample + idx) * Q;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int4 kc = __ldg(reinterpret_cast<const int4 *>(a.kcorr) + q);
+            const float4 z = __ldg(reinterpret_cast<const float4 *>(a.c0z) + q);
+            const float4 s = __ldg(reinterpret_cast<const float4 *>(a.c1) + q);
+            out[q] = pack4(requant(acc[4 * q + 0] - kc.x, z.x, s.x, a.lo, a.hi), requant(acc[4 * q + 1] - kc.y, z.y, s.y, a.lo, a.hi),
+                           requant(acc[4 * q + 2] - kc.z, z.z, s.z, a.lo, a.hi), requant(acc[4 * q + 3] - kc.w, z.w, s.w, a.lo, a.hi));
+        }
     }
 }
 
@@ -300,57 +409,65 @@ bool dwconv_cin1_eligible(const ConvArgs &a) {
     return a.depthwise && !a.is_u8 && a.Cin == 1 && (a.Cout % 4) == 0 && a.Cout >= 4 && a.Cout <= 16 && a.kcorr != nullptr;
 }
 cudaError_t launch_dwconv_cin1(const ConvArgs &a, cudaStream_t s) {
-    const long long total = a.batch * a.OH * a.OW;
-    if (total <= 0) return cudaSuccess;
-    const unsigned grid = grid_for(total, 128);
+    const long long per = (long long)a.OH * a.OW;
+    if (per <= 0 || a.batch <= 0) return cudaSuccess;
+    const dim3 grid = grid2(per, 128, a.batch);
+    const FastDiv fow((uint32_t)a.OW);
+    const uint32_t n = (uint32_t)per;
+    const bool k33 = a.KH == 3 && a.KW == 3;
     switch (a.Cout) {
-        case 4: dwconv_cin1_kernel<4><<<grid, 128, 0, s>>>(a, total); break;
-        case 8: dwconv_cin1_kernel<8><<<grid, 128, 0, s>>>(a, total); break;
-        case 12: dwconv_cin1_kernel<12><<<grid, 128, 0, s>>>(a, total); break;
-        case 16: dwconv_cin1_kernel<16><<<grid, 128, 0, s>>>(a, total); break;
+        case 4: dwconv_cin1_kernel<4, 0, 0><<<grid, 128, 0, s>>>(a, n, fow); break;
+        case 8:
+            if (k33) dwconv_cin1_kernel<8, 3, 3><<<grid, 128, 0, s>>>(a, n, fow);
+            else dwconv_cin1_kernel<8, 0, 0><<<grid, 128, 0, s>>>(a, n, fow);
+            break;
+        case 12: dwconv_cin1_kernel<12, 0, 0><<<grid, 128, 0, s>>>(a, n, fow); break;
+        case 16: dwconv_cin1_kernel<16, 0, 0><<<grid, 128, 0, s>>>(a, n, fow); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
-// ================================================================================================
-// FAST (fallback for shapes the tcgen05 GEMM does not take): 1x1 conv, int8, w_zp == 0, Cin % 4 == 0, Cout % 4 == 0.
-// One thread = 4 output channels of one pixel; dp4a over the input channels.
-// ================================================================================================
-__global__ void __launch_bounds__(256) pwconv_dp4a_kernel(ConvArgs a, long long total_words) {
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total_words) return;
-    const int G = a.Cout >> 2, K4 = a.Cin >> 2;
-    const int g = (int)(idx % G);
-    long long p = idx / G;
-    const int j = (int)(p % a.OW); p /= a.OW;
-    const int i = (int)(p % a.OH);
-    const long long b = p / a.OH;
-    const uint32_t *x = reinterpret_cast<const uint32_t *>(a.in) + (((size_t)b * a.H + (size_t)a.sh * i) * a.W + (size_t)a.sw * j) * K4;
-    const uint32_t *w0 = reinterpret_cast<const uint32_t *>(a.w) + (size_t)(4 * g) * K4;
-    int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
-    for (int k = 0; k < K4; ++k) {
-        const int v = (int)__ldg(x + k);
-        acc0 = __dp4a(v, (int)__ldg(w0 + k), acc0);
-        acc1 = __dp4a(v, (int)__ldg(w0 + K4 + k), acc1);
-        acc2 = __dp4a(v, (int)__ldg(w0 + 2 * K4 + k), acc2);
-        acc3 = __dp4a(v, (int)__ldg(w0 + 3 * K4 + k), acc3);
+// ------------------------------------------------------------------------------------------------
+// 1x1 conv on CUDA cores (shapes the tcgen05 GEMM does not take, e.g. person_detect's final 256 -> 2 layer):
+// int8, w_zp == 0, Cin % 4 == 0.  One thread = up to 4 output channels of one pixel; dp4a over the input channels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pwconv_dp4a_kernel(ConvArgs a, uint32_t items_per_sample, FastDiv fd_g, FastDiv fd_ow) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= items_per_sample) return;
+    const int K4 = a.Cin >> 2;
+    uint32_t p, g, i, j;
+    fd_g.divmod(idx, p, g);
+    fd_ow.divmod(p, i, j);
+    const int co = 4 * (int)g;
+    const int nco = min(4, a.Cout - co);
+    const uint32_t *w0 = reinterpret_cast<const uint32_t *>(a.w) + (size_t)co * K4;
+    const uint32_t *w1 = w0 + (nco > 1 ? K4 : 0), *w2 = w0 + (nco > 2 ? 2 * K4 : 0), *w3 = w0 + (nco > 3 ? 3 * K4 : 0);
+    for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
+        const uint32_t *x = reinterpret_cast<const uint32_t *>(a.in) + (((size_t)b * a.H + (size_t)a.sh * i) * a.W + (size_t)a.sw * j) * K4;
+        int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+#pragma unroll 4
+        for (int k = 0; k < K4; ++k) {
+            const int v = (int)__ldg(x + k);
+            acc0 = __dp4a(v, (int)__ldg(w0 + k), acc0);
+            acc1 = __dp4a(v, (int)__ldg(w1 + k), acc1);
+            acc2 = __dp4a(v, (int)__ldg(w2 + k), acc2);
+            acc3 = __dp4a(v, (int)__ldg(w3 + k), acc3);
+        }
+        const int accs[4] = {acc0, acc1, acc2, acc3};
+        uint8_t *o = a.out + ((size_t)b * a.OH * a.OW + p) * a.Cout + co;
+        for (int u = 0; u < nco; ++u) o[u] = (uint8_t)requant(accs[u] - a.kcorr[co + u], a.c0z[co + u], a.c1[co + u], a.lo, a.hi);
     }
-    const int4 kc = __ldg(reinterpret_cast<const int4 *>(a.kcorr) + g);
-    const float4 z = __ldg(reinterpret_cast<const float4 *>(a.c0z) + g);
-    const float4 s = __ldg(reinterpret_cast<const float4 *>(a.c1) + g);
-    reinterpret_cast<uint32_t *>(a.out)[idx] =
-        pack4(requant(acc0 - kc.x, z.x, s.x, a.lo, a.hi), requant(acc1 - kc.y, z.y, s.y, a.lo, a.hi),
-              requant(acc2 - kc.z, z.z, s.z, a.lo, a.hi), requant(acc3 - kc.w, z.w, s.w, a.lo, a.hi));
 }
 
 bool pwconv_dp4a_eligible(const ConvArgs &a) {
-    return !a.depthwise && !a.is_u8 && a.KH == 1 && a.KW == 1 && (a.Cin % 4) == 0 && (a.Cout % 4) == 0 && a.kcorr != nullptr;
+    return !a.depthwise && !a.is_u8 && a.KH == 1 && a.KW == 1 && (a.Cin % 4) == 0 && a.kcorr != nullptr;
 }
 cudaError_t launch_pwconv_dp4a(const ConvArgs &a, cudaStream_t s) {
-    const long long total = a.batch * a.OH * a.OW * (a.Cout / 4);
-    if (total <= 0) return cudaSuccess;
-    pwconv_dp4a_kernel<<<grid_for(total, 256), 256, 0, s>>>(a, total);
+    const int G = (a.Cout + 3) / 4;
+    const long long per = (long long)a.OH * a.OW * G;
+    if (per <= 0 || a.batch <= 0) return cudaSuccess;
+    pwconv_dp4a_kernel<<<grid2(per, 256, a.batch), 256, 0, s>>>(a, (uint32_t)per, FastDiv((uint32_t)G), FastDiv((uint32_t)a.OW));
     return cudaGetLastError();
 }
 

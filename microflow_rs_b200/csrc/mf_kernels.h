@@ -5,6 +5,24 @@
 
 namespace mf {
 
+// n / d for n < 2^31 with one mul.hi + shift (d fixed per launch; verified exhaustively on the host)
+struct FastDiv {
+    uint32_t d = 1, mul = 0, shr = 0;
+    FastDiv() = default;
+    explicit FastDiv(uint32_t div) : d(div ? div : 1) {
+        if (d == 1) return;
+        uint32_t l = 0;
+        while ((1ull << l) < d) ++l;
+        const uint32_t p = 31 + l;
+        mul = (uint32_t)(((1ull << p) + d - 1) / d);
+        shr = p - 32;
+    }
+#ifdef __CUDACC__
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : (__umulhi(n, mul) >> shr); }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t &q, uint32_t &r) const { q = div(n); r = n - q * d; }
+#endif
+};
+
 // One quantized conv / depthwise-conv layer on `batch` independent NHWC samples.
 struct ConvArgs {
     const uint8_t *in = nullptr;
@@ -65,9 +83,11 @@ cudaError_t launch_dequantize(const uint8_t *in, float *out, size_t n, float sca
 // ---- SIMT fast kernels (int8, weight zero-point 0): coalesced NHWC, dp4a -------------------------------
 bool dwconv_c4_eligible(const ConvArgs &a);      // depthwise, Cin == Cout, C % 4 == 0
 cudaError_t launch_dwconv_c4(const ConvArgs &a, cudaStream_t s);
+bool dwconv3x3_rows_eligible(const ConvArgs &a); // + 3x3, stride 1x1 or 2x2: sliding 3x3 window down a column strip
+cudaError_t launch_dwconv3x3_rows(const ConvArgs &a, cudaStream_t s);
 bool dwconv_cin1_eligible(const ConvArgs &a);    // depthwise with Cin == 1 (depth multiplier), Cout % 4 == 0, Cout <= 16
 cudaError_t launch_dwconv_cin1(const ConvArgs &a, cudaStream_t s);
-bool pwconv_dp4a_eligible(const ConvArgs &a);    // 1x1 stride-1 conv, Cin % 4 == 0, Cout % 4 == 0
+bool pwconv_dp4a_eligible(const ConvArgs &a);    // 1x1 conv (any stride), Cin % 4 == 0, any Cout
 cudaError_t launch_pwconv_dp4a(const ConvArgs &a, cudaStream_t s);
 bool fc_warp_eligible(const FcArgs &a);          // K % 16 == 0, N <= 8
 cudaError_t launch_fc_warp(const FcArgs &a, cudaStream_t s);

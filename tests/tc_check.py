@@ -47,7 +47,7 @@ def main():
                 print(json.dumps(res)); return
         res["ok"] = True
     elif which == "conv3x3":
-        shapes = [(2, 16, 16, 128, 128), (1, 8, 24, 128, 64), (2, 9, 21, 128, 128), (1, 5, 3, 256, 32), (1, 2, 2, 128, 256)]
+        shapes = [(2, 16, 16, 128, 128), (1, 8, 24, 128, 64), (2, 9, 21, 128, 128), (1, 5, 3, 256, 32), (1, 2, 2, 128, 64), (3, 40, 40, 128, 128)]
         for (B, H, W, Cin, Cout) in shapes:
             x, w, in_zp, c0, c1, act = conv_case(r, B, H, W, Cin, Cout, 3, "relu6", in_zp=-128 if Cout == 128 else None)
             got = mf.ops.conv_2d(x, in_zp, w, [0], 0.0235294, -128, act, "same", (1, 1), c0, c1, (H, W), impl=0)

@@ -142,15 +142,22 @@ def test_conv_generic_vs_oracle(case):
 
 FAST_SIMT_CASES = [
     # shapes of person_detect / speech depthwise layers (scaled-down spatial extents keep the oracle fast) + odd ones
-    (3, 12, 12, 8, 8, 3, 3, 1, 1, "same", "relu6", True, "dwconv_c4"),
-    (3, 12, 12, 16, 16, 3, 3, 2, 2, "same", "relu6", True, "dwconv_c4"),
-    (2, 6, 6, 128, 128, 3, 3, 1, 1, "same", "relu6", True, "dwconv_c4"),
-    (2, 3, 3, 256, 256, 3, 3, 1, 1, "same", "relu6", True, "dwconv_c4"),
+    (3, 12, 12, 8, 8, 3, 3, 1, 1, "same", "relu6", True, "dwconv3x3_rows"),
+    (3, 12, 12, 16, 16, 3, 3, 2, 2, "same", "relu6", True, "dwconv3x3_rows"),
+    (2, 6, 6, 128, 128, 3, 3, 1, 1, "same", "relu6", True, "dwconv3x3_rows"),
+    (2, 3, 3, 256, 256, 3, 3, 1, 1, "same", "relu6", True, "dwconv3x3_rows"),
     (2, 7, 9, 12, 12, 5, 3, 2, 1, "same", "relu", True, "dwconv_c4"),
-    (2, 9, 7, 4, 4, 3, 3, 1, 1, "valid", "none", True, "dwconv_c4"),
+    (2, 9, 7, 4, 4, 3, 3, 1, 1, "valid", "none", True, "dwconv3x3_rows"),
     (3, 96, 96, 1, 8, 3, 3, 2, 2, "same", "relu6", True, "dwconv_cin1"),     # person_detect layer 0
     (3, 49, 40, 1, 8, 10, 8, 2, 2, "same", "relu", True, "dwconv_cin1"),     # speech layer 1
     (2, 11, 13, 1, 16, 3, 5, 1, 2, "valid", "none", True, "dwconv_cin1"),
+    (2, 48, 48, 8, 8, 3, 3, 1, 1, "same", "relu", True, "dwconv3x3_rows"),          # several row strips, clamp != full int8 range
+    (2, 24, 24, 32, 32, 3, 3, 2, 2, "same", "relu6", True, "dwconv3x3_rows"),       # stride 2 over several strips
+    (2, 13, 11, 8, 8, 3, 3, 2, 2, "valid", "relu6", True, "dwconv3x3_rows"),
+    (2, 17, 5, 4, 4, 3, 3, 1, 1, "same", "none", True, "dwconv3x3_rows"),
+    (2, 9, 9, 8, 8, 3, 3, 2, 1, "same", "none", True, "dwconv_c4"),                 # mixed strides stay on the generic-shape fast kernel
+    (3, 1, 1, 256, 2, 1, 1, 1, 1, "same", "none", False, "pwconv_dp4a"),            # person_detect's last conv (Cout = 2)
+    (2, 4, 4, 16, 7, 1, 1, 1, 1, "same", "relu", False, "pwconv_dp4a"),
     (3, 12, 12, 8, 16, 1, 1, 1, 1, "same", "relu6", False, "pwconv_dp4a|conv_tc"),   # person_detect layer 2 shape
     (2, 5, 5, 12, 20, 1, 1, 1, 1, "same", "none", False, "pwconv_dp4a"),
     (2, 6, 6, 8, 4, 1, 1, 2, 2, "same", "relu", False, "pwconv_dp4a"),

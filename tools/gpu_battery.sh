@@ -1,0 +1,47 @@
+#!/bin/bash
+# Standard GPU session (run under gpurun): parity tests, smoke, benches, ncu launch list + full captures.
+# Usage: tools/gpu_battery.sh [tests|bench|prof|all]...   (default: all).  Outputs land in gpurun_out/.
+set -u
+mkdir -p gpurun_out
+what="${*:-all}"
+has() { [[ " $what " == *" $1 "* || " $what " == *" all "* ]]; }
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
+if has tests; then
+  timeout 500 python -m pytest tests/test_gpu_tc.py -q -m gpu 2>&1 | tail -25 > gpurun_out/t_tc.log
+  timeout 700 python -m pytest tests/test_gpu_ops.py -q -m gpu 2>&1 | tail -40 > gpurun_out/t_ops.log
+  timeout 900 python -m pytest tests/test_gpu_models.py -q -m gpu 2>&1 | tail -60 > gpurun_out/t_models.log
+  timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
+fi
+if has bench; then
+  timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_pd.json 2> gpurun_out/bench_pd.err
+  timeout 300 python bench.py --workload speech --steps 20 --warmup 5 --no-conv2d > gpurun_out/bench_speech.json 2> gpurun_out/bench_speech.err
+  for c in 1024 2048 8192; do
+    timeout 200 python bench.py --steps 10 --warmup 3 --chunk $c --no-cpu-baseline --no-conv2d > gpurun_out/bench_pd_chunk$c.json 2>> gpurun_out/bench_pd.err
+  done
+  timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+fi
+if has prof; then
+  timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-conv2d > gpurun_out/ncu_bench.log 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:dwconv3x3_rows -s 26 -c 2 -f -o gpurun_out/prof_dw \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-conv2d > gpurun_out/ncu_dw.log 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 28 -c 3 -f -o gpurun_out/prof_tc_pw \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-conv2d > gpurun_out/ncu_tc.log 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 5 -c 1 -f -o gpurun_out/prof_conv3x3 \
+      python -m microflow_rs_b200._convbench 16 4 > gpurun_out/ncu_conv3x3.log 2>&1
+fi
+tail -n 4 gpurun_out/t_tc.log gpurun_out/t_ops.log gpurun_out/t_models.log gpurun_out/smoke.log 2>/dev/null
+for f in gpurun_out/bench_pd.json gpurun_out/bench_speech.json gpurun_out/bench_pd_chunk*.json gpurun_out/bench_ref.json; do
+  [ -f "$f" ] && python - "$f" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    r = d.get("roofline") or {}
+    c = (d.get("conv2d") or {}).get("roofline") or {}
+    print(sys.argv[1], "value=%.4g e2e=%.4g ms/step=%.3f dom=%s frac=%.3f conv2d=%s clocks=%s" % (
+        d["value"], (d.get("e2e") or {}).get("value", 0), d["ms_per_step"], r.get("kernel"), r.get("frac", 0), c.get("frac"), d.get("clocks")))
+except Exception as e:
+    print(sys.argv[1], "unreadable:", e)
+PY
+done
+tail -n 3 gpurun_out/*.err 2>/dev/null | tail -20
