@@ -28,6 +28,7 @@
 
 #include "mf_conv_tc.h"
 #include "mf_device.cuh"
+#include "mf_kernels.h"   // FastDiv
 
 namespace mf {
 
@@ -45,6 +46,7 @@ struct ConvTcParams {
     const int32_t *corr;
     int N, CB, KH, KW, TW, TH, tw_log2, off_r, off_c, ncls, stages;
     int tiles_x, tiles_y;
+    FastDiv fd_img, fd_tx;     // tile -> (image, ty, tx) without integer division
     long long num_tiles, OW, OH;
     float lo, hi;
     uint32_t idesc, stage_bytes, b_block_bytes, tmem_cols, nkb;
@@ -132,7 +134,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <bool FULL>
+template <bool BIG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvTcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -179,8 +181,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const long long tiles_per_img = (long long)p.tiles_x * p.tiles_y;
-
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
@@ -188,15 +188,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (uint32_t kb = 0; kb < p.nkb; ++kb) tma_load_2d(smem_u32(sB + (size_t)kb * p.b_block_bytes), &tmap_b, bfull_bar, (int)(kb * 128), 0);
             uint32_t s = 0, ph = 0;
             for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int b = (int)(tile / tiles_per_img);
-                const int rem = (int)(tile - (long long)b * tiles_per_img);
-                const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+                uint32_t b, rem, ty, tx;
+                p.fd_img.divmod((uint32_t)tile, b, rem);
+                p.fd_tx.divmod(rem, ty, tx);
                 for (int n = 0; n < p.KW; ++n)
                     for (int cb = 0; cb < p.CB; ++cb) {
                         mbar_wait(empty_bar(s), ph ^ 1);
                         mbar_expect_tx(full_bar(s), p.stage_bytes);
-                        tma_load_4d(smem_u32(sA + (size_t)s * p.stage_bytes), &tmap_a, full_bar(s), cb * 128, tx * p.TW + n - p.off_c,
-                                    ty * p.TH - p.off_r, b);
+                        tma_load_4d(smem_u32(sA + (size_t)s * p.stage_bytes), &tmap_a, full_bar(s), cb * 128, (int)tx * p.TW + n - p.off_c,
+                                    (int)ty * p.TH - p.off_r, (int)b);
                         if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
                     }
             }
@@ -241,12 +241,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int cg = (warp - 4) >> 2;
         const int row = (int)(q * 32 + lane);
         const int rr = row >> p.tw_log2, rc = row & (p.TW - 1);
+        const float lo = p.lo, hi = p.hi;
         uint32_t it = 0;
         for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const uint32_t acc = it & 1, aph = (it >> 1) & 1;
-            const int b = (int)(tile / tiles_per_img);
-            const int rem = (int)(tile - (long long)b * tiles_per_img);
-            const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+            uint32_t b, rem, ty, tx;
+            p.fd_img.divmod((uint32_t)tile, b, rem);
+            p.fd_tx.divmod(rem, ty, tx);
             const long long oy = (long long)ty * p.TH + rr, ox = (long long)tx * p.TW + rc;
             const bool valid = oy < p.OH && ox < p.OW;
             int cls = 0;
@@ -266,10 +267,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const float4 z = *reinterpret_cast<const float4 *>(s_c0z + c0 + 4 * g);
                     const float4 sc = *reinterpret_cast<const float4 *>(s_c1 + c0 + 4 * g);
                     const int4 kc = *reinterpret_cast<const int4 *>(corr + c0 + 4 * g);
-                    const int y0 = requant_t<FULL>((int)r[4 * g + 0] - kc.x, z.x, sc.x, p.lo, p.hi);
-                    const int y1 = requant_t<FULL>((int)r[4 * g + 1] - kc.y, z.y, sc.y, p.lo, p.hi);
-                    const int y2 = requant_t<FULL>((int)r[4 * g + 2] - kc.z, z.z, sc.z, p.lo, p.hi);
-                    const int y3 = requant_t<FULL>((int)r[4 * g + 3] - kc.w, z.w, sc.w, p.lo, p.hi);
+                    const int y0 = requant_nx<BIG>((int)r[4 * g + 0] - kc.x, z.x, sc.x, lo, hi);
+                    const int y1 = requant_nx<BIG>((int)r[4 * g + 1] - kc.y, z.y, sc.y, lo, hi);
+                    const int y2 = requant_nx<BIG>((int)r[4 * g + 2] - kc.z, z.z, sc.z, lo, hi);
+                    const int y3 = requant_nx<BIG>((int)r[4 * g + 3] - kc.w, z.w, sc.w, lo, hi);
                     w[g] = pack4(y0, y1, y2, y3);
                 }
                 if (valid) {
@@ -443,6 +444,9 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     k.tiles_x = (int)((l.OW + p.TW - 1) / p.TW);
     k.tiles_y = (int)((l.OH + p.TH - 1) / p.TH);
     k.num_tiles = (long long)k.tiles_x * k.tiles_y * l.B;
+    if (k.num_tiles >= (1ll << 31)) { if (why) *why = "too many tiles for one launch"; return cudaErrorInvalidValue; }
+    k.fd_img = FastDiv((uint32_t)(k.tiles_x * k.tiles_y));
+    k.fd_tx = FastDiv((uint32_t)k.tiles_x);
     k.OW = l.OW; k.OH = l.OH;
     k.lo = p.lo; k.hi = p.hi;
     // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 @4, a/b format INT8 = 1 @7/@10,
@@ -462,7 +466,7 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     });
     if (attr_err != cudaSuccess) return attr_err;
     const unsigned grid = (unsigned)(k.num_tiles < num_sms ? k.num_tiles : num_sms);
-    if (p.lo == -128.f && p.hi == 127.f) conv_tc_kernel<true><<<grid, kThreads, p.smem_bytes, s>>>(ta, tb, k);
+    if (p.big_acc) conv_tc_kernel<true><<<grid, kThreads, p.smem_bytes, s>>>(ta, tb, k);
     else conv_tc_kernel<false><<<grid, kThreads, p.smem_bytes, s>>>(ta, tb, k);
     return cudaGetLastError();
 }

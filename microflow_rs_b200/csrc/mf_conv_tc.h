@@ -40,6 +40,7 @@ struct ConvTcPlan {
     const float *d_c1 = nullptr;       // [N]
     const int32_t *d_corr = nullptr;   // [ncls][N]  in_zp * (sum of weights over the taps valid for that border class)
     float lo = -128.f, hi = 127.f;
+    bool big_acc = false;              // |acc - corr| may exceed 2^22: use the general exact int->float in the epilogue
     alignas(64) unsigned char tmap_b[128];  // CUtensorMap of the weight matrix
 };
 

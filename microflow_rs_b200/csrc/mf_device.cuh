@@ -46,18 +46,38 @@ __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
     return __byte_perm(lo, hi, 0x5410);
 }
 
-// requant for layers whose clamp is the whole int8 range (every conv of person_detect: ReLU6's upper bound quantizes
-// to 127 and the lower bound is the zero point -128): the saturating F2I.S8 conversion replaces both FMNMX.
-// cvt.rzi.sat.s8.f32 == trunc then saturate to [-128,127], NaN -> 0 (exactly Rust's `as i8`).
-__device__ __forceinline__ int requant_full_i8(int acc, float c0z, float c1) {
-    float t = __fadd_rn(c0z, __fmul_rn(c1, __int2float_rn(acc)));
-    float s = __fadd_rn(t, round_bias(t));
-    int y;
-    asm("cvt.rzi.sat.s8.f32 %0, %1;" : "=r"(y) : "f"(s));
-    return y;
+// ------------------------------------------------------------------------------------------------------------
+// XU-free variants for the hot kernels.  On sm_100 I2F / F2I / IDP.4A all issue to the XU pipe, which sustains only a few
+// lanes per clock per SM (ncu: XU at 130-150 % "of peak" in every first-generation kernel of this repo, profiles/).
+// The same results are obtained on the FMA / ALU pipes with exact bit tricks (each verified exhaustively on the host
+// against (float)x / roundf -- see DESIGN.md "XU-free epilogue"):
+//   * i2f_exact<false>(x), |x| <= 2^22 : as_float(x + 0x4B400000) - 1.5*2^23   (ulp is 1 in [2^23, 2^24))
+//   * i2f_exact<true>(x), any int32    : x = hi*4096 + lo; hi*4096 and lo are built the same way in two binades and the
+//                                        single RN add of the two exact parts is the correctly rounded value of x
+//   * round_clamp_nx(t): clamp first (commutes with rounding), then u = RZ(|tc| + (1.5*2^22 + 0.5)) lands on the 0.5-grid
+//     of [2^22, 2^23): its mantissa holds floor(2|tc| + 1), whose half is floor(|tc| + 0.5) = |roundf(tc)|.
+// ------------------------------------------------------------------------------------------------------------
+template <bool BIG> __device__ __forceinline__ float i2f_exact(int x) {
+    if (!BIG) return __fadd_rn(__int_as_float(x + 0x4B400000), -12582912.0f);
+    const float fh = __fadd_rn(__int_as_float((x >> 12) + 0x51400000), -51539607552.0f);   // hi * 4096 exactly
+    const float fl = __fadd_rn(__int_as_float((x & 0xFFF) | 0x4B400000), -12582912.0f);     // lo exactly
+    return __fadd_rn(fh, fl);
 }
-template <bool FULL> __device__ __forceinline__ int requant_t(int acc, float c0z, float c1, float lo, float hi) {
-    return FULL ? requant_full_i8(acc, c0z, c1) : requant(acc, c0z, c1, lo, hi);
+__device__ __forceinline__ int round_clamp_nx(float t, float lo, float hi) {
+    const float tc = fminf(fmaxf(t, lo), hi);
+    const float u = __fadd_rz(fabsf(tc), 6291456.5f);
+    const int n = (__float_as_int(u) >> 1) & 0x1FF;
+    return tc < 0.0f ? -n : n;
+}
+template <bool BIG> __device__ __forceinline__ int requant_nx(int acc, float c0z, float c1, float lo, float hi) {
+    const float t = __fadd_rn(c0z, __fmul_rn(c1, i2f_exact<BIG>(acc)));
+    return round_clamp_nx(t, lo, hi);
+}
+// sign-extended byte k of a packed word: one PRMT (selector msb = replicate the sign of the selected byte)
+template <int K> __device__ __forceinline__ int sx8(uint32_t w) {
+    int r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0u), "r"((uint32_t)(((8 | K) * 0x1110) | K)));
+    return r;
 }
 
 }  // namespace mf

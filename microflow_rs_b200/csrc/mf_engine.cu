@@ -2,6 +2,7 @@
 #include "mf_engine.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace mf {
@@ -64,6 +65,14 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
             else for (size_t k = 0; k < (size_t)taps * L.Cin; ++k) s += elem_i(L.w[(size_t)co * taps * L.Cin + k], L.is_u8);
             kcorr[(size_t)co] = L.in_zp * s;
         }
+        // can |acc - kcorr| exceed 2^22 ?  (bound: sum |w| * 128 + |kcorr|)  -> selects the general exact int->float
+        big_acc = false;
+        for (int co = 0; co < Cout; ++co) {
+            long long sa = 0;
+            if (dw) for (int t = 0; t < taps; ++t) sa += std::abs(elem_i(L.w[(size_t)t * Cout + co], L.is_u8));
+            else for (size_t k = 0; k < (size_t)taps * L.Cin; ++k) sa += std::abs(elem_i(L.w[(size_t)co * taps * L.Cin + k], L.is_u8));
+            if (sa * 128 + std::llabs((long long)kcorr[(size_t)co]) > (1ll << 22)) big_acc = true;
+        }
         o_w = bb.add(L.w.data(), L.w.size());
         o_wzp = bb.add(wzp.data(), wzp.size() * 4);
         o_c0z = bb.add(c0z.data(), c0z.size() * 4);
@@ -77,7 +86,8 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
         if (impl == 1) { why_not_fast = "generic kernels forced"; return; }
         if (L.is_u8 || !wz0) { why_not_fast = "uint8 or non-zero weight zero-point: generic kernel"; return; }
         if (dw) {
-            if (L.Cin == L.Cout && L.Cout % 4 == 0)
+            if (big_acc) why_not_fast = "accumulator range beyond 2^22: generic kernel";
+            else if (L.Cin == L.Cout && L.Cout % 4 == 0)
                 kernel = (L.KH == 3 && L.KW == 3 && L.sh == L.sw && (L.sh == 1 || L.sh == 2)) ? Kernel::DwConv3x3Rows : Kernel::DwConvC4;
             else if (L.Cin == 1 && L.Cout % 4 == 0 && L.Cout >= 4 && L.Cout <= 16) kernel = Kernel::DwConvCin1;
             else why_not_fast = "depthwise shape not covered by a fast kernel";
@@ -93,7 +103,7 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
                     tc_P = P;
                     tc.P = P; tc.N = P * L.Cout; tc.Cout = L.Cout; tc.C = P * L.Cin; tc.CB = tc.C / 128;
                     tc.KH = tc.KW = 1; tc.TW = 128; tc.TH = 1; tc.off_r = tc.off_c = 0; tc.ncls = 1;
-                    tc.lo = (float)L.act_lo; tc.hi = (float)L.act_hi;
+                    tc.lo = (float)L.act_lo; tc.hi = (float)L.act_hi; tc.big_acc = big_acc;
                     std::vector<uint8_t> wm = conv_tc_pack_pointwise(L.w.data(), L.Cout, L.Cin, P);
                     std::vector<float> ez((size_t)tc.N), es((size_t)tc.N);
                     std::vector<int32_t> ec((size_t)tc.N);
@@ -118,7 +128,7 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
                     const long long work = (long long)((L.OW + tw - 1) / tw) * tw * ((L.OH + th - 1) / th) * th;
                     if (best < 0 || work < best) { best = work; tc.TW = tw; tc.TH = th; }
                 }
-                tc.lo = (float)L.act_lo; tc.hi = (float)L.act_hi;
+                tc.lo = (float)L.act_lo; tc.hi = (float)L.act_hi; tc.big_acc = big_acc;
                 std::vector<int32_t> corr = conv_tc_border_corr_3x3(L.w.data(), L.Cout, L.Cin, L.in_zp, L.H, L.W);
                 o_tc_w = o_w;  // OHWI is already the [N][K_total] matrix
                 o_tc_c0z = o_c0z; o_tc_c1 = o_c1;
@@ -168,6 +178,7 @@ bool LayerExec::resolve(const uint8_t *d, std::string *err) {
         a.off_r = L.pad == MF_PAD_SAME ? (L.KH - 1) / 2 : 0;   // src/tensor.rs:193
         a.off_c = L.pad == MF_PAD_SAME ? (L.KW - 1) / 2 : 0;
         a.in_zp = L.in_zp; a.lo = (float)L.act_lo; a.hi = (float)L.act_hi; a.is_u8 = L.is_u8; a.depthwise = L.op == MF_OP_DEPTHWISE_CONV_2D;
+        a.big_acc = big_acc;
         if (kernel == Kernel::ConvTcPointwise || kernel == Kernel::ConvTc3x3) {
             tc.d_wmat = at(o_tc_w);
             tc.d_c0z = reinterpret_cast<const float *>(at(o_tc_c0z));

@@ -45,6 +45,7 @@ struct LayerExec {
     size_t o_tc_w = SIZE_MAX, o_tc_c0z = SIZE_MAX, o_tc_c1 = SIZE_MAX, o_tc_corr = SIZE_MAX;
     ConvTcPlan tc;
     int tc_P = 1;
+    bool big_acc = false;   // |acc - kcorr| may exceed 2^22
     // resolved launch arguments
     ConvArgs conv;
     FcArgs fc;

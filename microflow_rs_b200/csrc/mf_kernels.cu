@@ -200,8 +200,8 @@ static inline dim3 grid2(long long per_sample, int block, long long batch) {
 // ------------------------------------------------------------------------------------------------
 // depthwise conv, Cin == Cout = C, C % 4 == 0, int8, w_zp == 0, any kernel / stride / padding.
 // One thread = 4 consecutive channels (one 32-bit word) of one output pixel; a warp covers 128 contiguous
-// output bytes and reads 128 contiguous input bytes per tap (stride 1).  The 4 MACs of different channels are
-// 4 dp4a against a byte-masked weight word (no unpacking of the activations).
+// output bytes and reads 128 contiguous input bytes per tap (stride 1).  Bytes are sign-extended with one PRMT each
+// and multiplied with IMAD (IDP.4A issues to the slow XU pipe on sm_100 and is avoided in every hot loop).
 // ------------------------------------------------------------------------------------------------
 template <int KH_T, int KW_T>
 __global__ void __launch_bounds__(256) dwconv_c4_kernel(ConvArgs a, uint32_t words_per_sample, FastDiv fd_g, FastDiv fd_ow) {
@@ -230,20 +230,20 @@ __global__ void __launch_bounds__(256) dwconv_c4_kernel(ConvArgs a, uint32_t wor
                 const bool ok = rok && (unsigned)c < (unsigned)a.W;
                 const uint32_t v = ok ? __ldg(inw + ((size_t)r * a.W + c) * G + g) : izw;
                 const uint32_t wv = __ldg(ww + (size_t)(m * KW + n) * G + g);
-                acc0 = __dp4a((int)v, (int)(wv & 0x000000ffu), acc0);
-                acc1 = __dp4a((int)v, (int)(wv & 0x0000ff00u), acc1);
-                acc2 = __dp4a((int)v, (int)(wv & 0x00ff0000u), acc2);
-                acc3 = __dp4a((int)v, (int)(wv & 0xff000000u), acc3);
+                acc0 += sx8<0>(v) * sx8<0>(wv);
+                acc1 += sx8<1>(v) * sx8<1>(wv);
+                acc2 += sx8<2>(v) * sx8<2>(wv);
+                acc3 += sx8<3>(v) * sx8<3>(wv);
             }
         }
         reinterpret_cast<uint32_t *>(a.out)[(size_t)b * words_per_sample + idx] =
-            pack4(requant(acc0 - kc.x, z.x, s.x, a.lo, a.hi), requant(acc1 - kc.y, z.y, s.y, a.lo, a.hi),
-                  requant(acc2 - kc.z, z.z, s.z, a.lo, a.hi), requant(acc3 - kc.w, z.w, s.w, a.lo, a.hi));
+            pack4(requant_nx<false>(acc0 - kc.x, z.x, s.x, a.lo, a.hi), requant_nx<false>(acc1 - kc.y, z.y, s.y, a.lo, a.hi),
+                  requant_nx<false>(acc2 - kc.z, z.z, s.z, a.lo, a.hi), requant_nx<false>(acc3 - kc.w, z.w, s.w, a.lo, a.hi));
     }
 }
 
 bool dwconv_c4_eligible(const ConvArgs &a) {
-    return a.depthwise && !a.is_u8 && a.Cin == a.Cout && (a.Cout % 4) == 0 && a.kcorr != nullptr;
+    return a.depthwise && !a.is_u8 && a.Cin == a.Cout && (a.Cout % 4) == 0 && a.kcorr != nullptr && !a.big_acc;
 }
 cudaError_t launch_dwconv_c4(const ConvArgs &a, cudaStream_t s) {
     const long long per = (long long)a.OH * a.OW * (a.Cout / 4);
@@ -257,11 +257,12 @@ cudaError_t launch_dwconv_c4(const ConvArgs &a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // depthwise 3x3 (every person_detect depthwise layer but the first), stride 1x1 or 2x2.
 // One thread = one 4-channel word of one output column, walking DOWN a strip of output rows with the 3x3 input
-// window held in 9 registers: each new output row loads 3 (stride 1) or 6 (stride 2) words instead of 9, and the
-// 36 byte-masked weight words, the epilogue constants and all index math are hoisted out of the row loop.
+// window held UNPACKED in 36 registers (three rotating row arrays): each new output row loads 3 (stride 1) or 6
+// (stride 2) words instead of 9 and unpacks every byte once (PRMT sign-extend); the 36 sign-extended weights, the
+// epilogue constants and all index math are hoisted out of the row loop; MACs are IMAD, the epilogue is XU-free.
 // Lanes run along (column, channel-word), i.e. along contiguous NHWC memory: every load and store is coalesced.
 // ------------------------------------------------------------------------------------------------
-template <int S, bool FULL>
+template <int S>
 __global__ void __launch_bounds__(128) dwconv3x3_rows_kernel(ConvArgs a, uint32_t threads_per_sample, uint32_t rows_per_strip, FastDiv fd_xw, FastDiv fd_g) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= threads_per_sample) return;
@@ -270,11 +271,11 @@ __global__ void __launch_bounds__(128) dwconv3x3_rows_kernel(ConvArgs a, uint32_
     fd_xw.divmod(t, strip, x);
     fd_g.divmod(x, j, g);
     const uint32_t *ww = reinterpret_cast<const uint32_t *>(a.w);
-    uint32_t wm[9][4];
+    int wi[9][4];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         const uint32_t wv = __ldg(ww + (size_t)k * G + g);
-        wm[k][0] = wv & 0x000000ffu; wm[k][1] = wv & 0x0000ff00u; wm[k][2] = wv & 0x00ff0000u; wm[k][3] = wv & 0xff000000u;
+        wi[k][0] = sx8<0>(wv); wi[k][1] = sx8<1>(wv); wi[k][2] = sx8<2>(wv); wi[k][3] = sx8<3>(wv);
     }
     const int4 kc = __ldg(reinterpret_cast<const int4 *>(a.kcorr) + g);
     const float4 z = __ldg(reinterpret_cast<const float4 *>(a.c0z) + g);
@@ -285,43 +286,52 @@ __global__ void __launch_bounds__(128) dwconv3x3_rows_kernel(ConvArgs a, uint32_
     const int i0 = (int)(strip * rows_per_strip);
     const int i1 = min(a.OH, i0 + (int)rows_per_strip);
     const size_t row_words = (size_t)a.W * G;
+    const float lo = a.lo, hi = a.hi;
 
     for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
         const uint32_t *inw = reinterpret_cast<const uint32_t *>(a.in) + (size_t)b * a.H * row_words + (ptrdiff_t)c0 * G + g;
         uint32_t *outw = reinterpret_cast<uint32_t *>(a.out) + ((size_t)b * a.OH * a.OW + j) * G + g;
-        auto load_row = [&](int r, uint32_t &v0, uint32_t &v1, uint32_t &v2) {
+        auto load_row = [&](int r, int (&d)[12]) {   // d[n * 4 + k] = channel k of window column n
             const bool rok = (unsigned)r < (unsigned)a.H;
             const uint32_t *p = inw + (ptrdiff_t)r * (ptrdiff_t)row_words;
-            v0 = (rok && cok0) ? __ldg(p) : izw;
-            v1 = (rok && cok1) ? __ldg(p + G) : izw;
-            v2 = (rok && cok2) ? __ldg(p + 2 * G) : izw;
+            const uint32_t v0 = (rok && cok0) ? __ldg(p) : izw;
+            const uint32_t v1 = (rok && cok1) ? __ldg(p + G) : izw;
+            const uint32_t v2 = (rok && cok2) ? __ldg(p + 2 * G) : izw;
+            d[0] = sx8<0>(v0); d[1] = sx8<1>(v0); d[2] = sx8<2>(v0); d[3] = sx8<3>(v0);
+            d[4] = sx8<0>(v1); d[5] = sx8<1>(v1); d[6] = sx8<2>(v1); d[7] = sx8<3>(v1);
+            d[8] = sx8<0>(v2); d[9] = sx8<1>(v2); d[10] = sx8<2>(v2); d[11] = sx8<3>(v2);
         };
-        uint32_t w00, w01, w02, w10, w11, w12, w20, w21, w22;
-        int r = S * i0 - a.off_r;
-        load_row(r, w00, w01, w02);
-        load_row(r + 1, w10, w11, w12);
-        for (int i = i0; i < i1; ++i) {
-            load_row(r + 2, w20, w21, w22);
+        auto emit = [&](const int (&r0)[12], const int (&r1)[12], const int (&r2)[12], int i) {
             int acc[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                int s = 0;
-                s = __dp4a((int)w00, (int)wm[0][k], s); s = __dp4a((int)w01, (int)wm[1][k], s); s = __dp4a((int)w02, (int)wm[2][k], s);
-                s = __dp4a((int)w10, (int)wm[3][k], s); s = __dp4a((int)w11, (int)wm[4][k], s); s = __dp4a((int)w12, (int)wm[5][k], s);
-                s = __dp4a((int)w20, (int)wm[6][k], s); s = __dp4a((int)w21, (int)wm[7][k], s); s = __dp4a((int)w22, (int)wm[8][k], s);
+                int s = r0[k] * wi[0][k];
+                s += r0[4 + k] * wi[1][k]; s += r0[8 + k] * wi[2][k];
+                s += r1[k] * wi[3][k]; s += r1[4 + k] * wi[4][k]; s += r1[8 + k] * wi[5][k];
+                s += r2[k] * wi[6][k]; s += r2[4 + k] * wi[7][k]; s += r2[8 + k] * wi[8][k];
                 acc[k] = s;
             }
-            outw[(size_t)i * a.OW * G] =
-                pack4(requant_t<FULL>(acc[0] - kc.x, z.x, sc.x, a.lo, a.hi), requant_t<FULL>(acc[1] - kc.y, z.y, sc.y, a.lo, a.hi),
-                      requant_t<FULL>(acc[2] - kc.z, z.z, sc.z, a.lo, a.hi), requant_t<FULL>(acc[3] - kc.w, z.w, sc.w, a.lo, a.hi));
-            if (S == 1) {
-                w00 = w10; w01 = w11; w02 = w12;
-                w10 = w20; w11 = w21; w12 = w22;
-                r += 1;
-            } else {
-                w00 = w20; w01 = w21; w02 = w22;
-                r += 2;
-                if (i + 1 < i1) load_row(r + 1, w10, w11, w12);
+            outw[(size_t)i * a.OW * G] = pack4(requant_nx<false>(acc[0] - kc.x, z.x, sc.x, lo, hi), requant_nx<false>(acc[1] - kc.y, z.y, sc.y, lo, hi),
+                                              requant_nx<false>(acc[2] - kc.z, z.z, sc.z, lo, hi), requant_nx<false>(acc[3] - kc.w, z.w, sc.w, lo, hi));
+        };
+        int ra[12], rb[12], rc[12];
+        int r = S * i0 - a.off_r;
+        int i = i0;
+        if (S == 1) {
+            load_row(r, ra);
+            load_row(r + 1, rb);
+            while (true) {
+                load_row(r + 2, rc); emit(ra, rb, rc, i); if (++i >= i1) break;
+                load_row(r + 3, ra); emit(rb, rc, ra, i); if (++i >= i1) break;
+                load_row(r + 4, rb); emit(rc, ra, rb, i); if (++i >= i1) break;
+                r += 3;
+            }
+        } else {
+            load_row(r, ra);
+            while (true) {
+                load_row(r + 1, rb); load_row(r + 2, rc); emit(ra, rb, rc, i); if (++i >= i1) break;
+                load_row(r + 3, rb); load_row(r + 4, ra); emit(rc, rb, ra, i); if (++i >= i1) break;
+                r += 4;
             }
         }
     }
@@ -340,36 +350,33 @@ cudaError_t launch_dwconv3x3_rows(const ConvArgs &a, cudaStream_t s) {
     const uint32_t strips = (uint32_t)((a.OH + rows - 1) / rows);
     const long long per = (long long)strips * xw;
     const FastDiv fxw(xw), fg((uint32_t)G);
-    const bool full = a.lo == -128.f && a.hi == 127.f;
     const dim3 grid = grid2(per, 128, a.batch);
-    if (a.sh == 1) {
-        if (full) dwconv3x3_rows_kernel<1, true><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
-        else dwconv3x3_rows_kernel<1, false><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
-    } else {
-        if (full) dwconv3x3_rows_kernel<2, true><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
-        else dwconv3x3_rows_kernel<2, false><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
-    }
+    if (a.sh == 1) dwconv3x3_rows_kernel<1><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
+    else dwconv3x3_rows_kernel<2><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
 // depthwise conv with a single input channel and a depth multiplier (person_detect layer 0: 3x3 s2 -> 8 ch,
 // speech layer 1: 10x8 s2 -> 8 ch).  Output channel c reads input channel 0 (depthwise_conv_2d.rs:67).
-// One thread = one output pixel, all COUT channels; the weights of 4 channels sit in one word and the activation
-// byte is moved to the matching byte lane, so each dp4a is one exact MAC without unpacking the weights.
+// One thread = one output pixel, all COUT channels.  The sign-extended weights sit in shared memory as int32
+// [tap][COUT] (broadcast LDS.128); the activation byte arrives sign-extended from LDG.S8; MACs are IMAD.
 // ------------------------------------------------------------------------------------------------
 template <int COUT, int KH_T, int KW_T>
 __global__ void __launch_bounds__(128) dwconv_cin1_kernel(ConvArgs a, uint32_t px_per_sample, FastDiv fd_ow) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= px_per_sample) return;
+    extern __shared__ int4 w_s4[];                       // [taps][COUT / 4]
     constexpr int Q = COUT / 4;
     const int KH = KH_T ? KH_T : a.KH, KW = KW_T ? KW_T : a.KW;
+    for (int e = threadIdx.x; e < KH * KW * COUT; e += blockDim.x) reinterpret_cast<int *>(w_s4)[e] = (int)(int8_t)a.w[e];
+    __syncthreads();
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= px_per_sample) return;
     uint32_t i, j;
     fd_ow.divmod(idx, i, j);
-    const uint32_t *ww = reinterpret_cast<const uint32_t *>(a.w);
     const int r0 = a.sh * (int)i - a.off_r, c0 = a.sw * (int)j - a.off_c;
+    const float lo = a.lo, hi = a.hi;
     for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
-        const uint8_t *in = a.in + (size_t)b * a.H * a.W;
+        const int8_t *in = reinterpret_cast<const int8_t *>(a.in) + (size_t)b * a.H * a.W;
         int acc[COUT];
 #pragma unroll
         for (int c = 0; c < COUT; ++c) acc[c] = 0;
@@ -381,15 +388,11 @@ __global__ void __launch_bounds__(128) dwconv_cin1_kernel(ConvArgs a, uint32_t p
             for (int n = 0; n < KW; ++n) {
                 const int c = c0 + n;
                 const bool ok = rok && (unsigned)c < (unsigned)a.W;
-                const uint32_t v = ok ? (uint32_t)__ldg(in + (size_t)r * a.W + c) : (uint32_t)(a.in_zp & 0xff);
-                const uint32_t v1 = v << 8, v2 = v << 16, v3 = v << 24;
+                const int v = ok ? (int)__ldg(in + (size_t)r * a.W + c) : a.in_zp;
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    const int wv = (int)__ldg(ww + (size_t)(m * KW + n) * Q + q);
-                    acc[4 * q + 0] = __dp4a(wv, (int)v, acc[4 * q + 0]);
-                    acc[4 * q + 1] = __dp4a(wv, (int)v1, acc[4 * q + 1]);
-                    acc[4 * q + 2] = __dp4a(wv, (int)v2, acc[4 * q + 2]);
-                    acc[4 * q + 3] = __dp4a(wv, (int)v3, acc[4 * q + 3]);
+                    const int4 wv = w_s4[(m * KW + n) * Q + q];
+                    acc[4 * q + 0] += v * wv.x; acc[4 * q + 1] += v * wv.y; acc[4 * q + 2] += v * wv.z; acc[4 * q + 3] += v * wv.w;
                 }
             }
         }
@@ -399,14 +402,15 @@ __global__ void __launch_bounds__(128) dwconv_cin1_kernel(ConvArgs a, uint32_t p
             const int4 kc = __ldg(reinterpret_cast<const int4 *>(a.kcorr) + q);
             const float4 z = __ldg(reinterpret_cast<const float4 *>(a.c0z) + q);
             const float4 s = __ldg(reinterpret_cast<const float4 *>(a.c1) + q);
-            out[q] = pack4(requant(acc[4 * q + 0] - kc.x, z.x, s.x, a.lo, a.hi), requant(acc[4 * q + 1] - kc.y, z.y, s.y, a.lo, a.hi),
-                           requant(acc[4 * q + 2] - kc.z, z.z, s.z, a.lo, a.hi), requant(acc[4 * q + 3] - kc.w, z.w, s.w, a.lo, a.hi));
+            out[q] = pack4(requant_nx<false>(acc[4 * q + 0] - kc.x, z.x, s.x, lo, hi), requant_nx<false>(acc[4 * q + 1] - kc.y, z.y, s.y, lo, hi),
+                           requant_nx<false>(acc[4 * q + 2] - kc.z, z.z, s.z, lo, hi), requant_nx<false>(acc[4 * q + 3] - kc.w, z.w, s.w, lo, hi));
         }
     }
 }
 
 bool dwconv_cin1_eligible(const ConvArgs &a) {
-    return a.depthwise && !a.is_u8 && a.Cin == 1 && (a.Cout % 4) == 0 && a.Cout >= 4 && a.Cout <= 16 && a.kcorr != nullptr;
+    return a.depthwise && !a.is_u8 && a.Cin == 1 && (a.Cout % 4) == 0 && a.Cout >= 4 && a.Cout <= 16 && a.kcorr != nullptr && !a.big_acc &&
+           (size_t)a.KH * a.KW * a.Cout * 4 <= 40 * 1024;
 }
 cudaError_t launch_dwconv_cin1(const ConvArgs &a, cudaStream_t s) {
     const long long per = (long long)a.OH * a.OW;
@@ -414,15 +418,16 @@ cudaError_t launch_dwconv_cin1(const ConvArgs &a, cudaStream_t s) {
     const dim3 grid = grid2(per, 128, a.batch);
     const FastDiv fow((uint32_t)a.OW);
     const uint32_t n = (uint32_t)per;
+    const size_t sm = (size_t)a.KH * a.KW * a.Cout * 4;
     const bool k33 = a.KH == 3 && a.KW == 3;
     switch (a.Cout) {
-        case 4: dwconv_cin1_kernel<4, 0, 0><<<grid, 128, 0, s>>>(a, n, fow); break;
+        case 4: dwconv_cin1_kernel<4, 0, 0><<<grid, 128, sm, s>>>(a, n, fow); break;
         case 8:
-            if (k33) dwconv_cin1_kernel<8, 3, 3><<<grid, 128, 0, s>>>(a, n, fow);
-            else dwconv_cin1_kernel<8, 0, 0><<<grid, 128, 0, s>>>(a, n, fow);
+            if (k33) dwconv_cin1_kernel<8, 3, 3><<<grid, 128, sm, s>>>(a, n, fow);
+            else dwconv_cin1_kernel<8, 0, 0><<<grid, 128, sm, s>>>(a, n, fow);
             break;
-        case 12: dwconv_cin1_kernel<12, 0, 0><<<grid, 128, 0, s>>>(a, n, fow); break;
-        case 16: dwconv_cin1_kernel<16, 0, 0><<<grid, 128, 0, s>>>(a, n, fow); break;
+        case 12: dwconv_cin1_kernel<12, 0, 0><<<grid, 128, sm, s>>>(a, n, fow); break;
+        case 16: dwconv_cin1_kernel<16, 0, 0><<<grid, 128, sm, s>>>(a, n, fow); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -456,7 +461,7 @@ __global__ void __launch_bounds__(256) pwconv_dp4a_kernel(ConvArgs a, uint32_t i
         }
         const int accs[4] = {acc0, acc1, acc2, acc3};
         uint8_t *o = a.out + ((size_t)b * a.OH * a.OW + p) * a.Cout + co;
-        for (int u = 0; u < nco; ++u) o[u] = (uint8_t)requant(accs[u] - a.kcorr[co + u], a.c0z[co + u], a.c1[co + u], a.lo, a.hi);
+        for (int u = 0; u < nco; ++u) o[u] = (uint8_t)requant_nx<true>(accs[u] - a.kcorr[co + u], a.c0z[co + u], a.c1[co + u], a.lo, a.hi);
     }
 }
 

@@ -37,6 +37,7 @@ struct ConvArgs {
     int in_zp = 0;
     float lo = -128.f, hi = 127.f;
     int is_u8 = 0, depthwise = 0;
+    int big_acc = 0;                // 1 if |acc - kcorr| can exceed 2^22 (selects the general exact int->float)
     long long batch = 0;
 };
 
