@@ -4,7 +4,7 @@
 //   * 3x3 stride-1 SAME convolutions with Cin a multiple of 128  (BASELINE config 5: 224x224x128 -> 128)
 //   * every 1x1 convolution of person_detect but the last (256 -> 2), as a "packed pixel" GEMM (see mf_conv_tc.h)
 //
-// Pipeline inside one persistent CTA (256 threads, 1 CTA / SM):
+// Pipeline inside one persistent CTA (640 threads, 1 CTA / SM):
 //   warp 0 (one lane)  TMA producer : cp.async.bulk.tensor.4d  global -> smem ring (SWIZZLE_128B), mbarrier tx
 //   warp 1 (one lane)  MMA issuer   : tcgen05.mma.cta_group::1.kind::i8, D in TMEM (2 accumulator buffers)
 //   warp 2             TMEM alloc / dealloc
@@ -39,11 +39,17 @@ constexpr int kEpiWarps = 16;
 constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr uint32_t kSmemLimit = 232448;  // 227 KB usable per CTA on sm_100
 
+// Per-channel epilogue tables, passed by value as a kernel parameter: they live in the constant bank, are read with
+// warp-uniform indices (every lane of a warp handles the same output column), and cost no shared memory -- which is
+// what lets the 3x3 configuration (147 KB of resident weights) afford a 4th TMA stage.
+struct ConvTcTables {
+    float c0z[256];
+    float c1[256];
+    int32_t corr[9 * 256];   // [ncls][N] with row pitch N
+};
+
 struct ConvTcParams {
     uint8_t *out;
-    const float *c0z;
-    const float *c1;
-    const int32_t *corr;
     int N, CB, KH, KW, TW, TH, tw_log2, off_r, off_c, ncls, stages;
     int tiles_x, tiles_y;
     FastDiv fd_img, fd_tx;     // tile -> (image, ty, tx) without integer division
@@ -136,15 +142,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // ------------------------------------------------------------------------------------------------
 template <bool BIG>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvTcParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ ConvTcTables tab,
+               const ConvTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();   // SWIZZLE_128B atoms need a 1024-byte aligned base
     uint8_t *sB = smem;
     uint8_t *sA = sB + (size_t)p.nkb * p.b_block_bytes;
-    float *s_c0z = reinterpret_cast<float *>(sA + (size_t)p.stages * p.stage_bytes);
-    float *s_c1 = s_c0z + p.N;
-    int32_t *s_corr = reinterpret_cast<int32_t *>(s_c1 + p.N);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_corr + (size_t)p.ncls * p.N);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + (size_t)p.stages * p.stage_bytes);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 5);
 
     const uint32_t bar0 = smem_u32(bars);
@@ -170,11 +174,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (warp >= 4) {  // per-channel epilogue tables -> smem
-        const int t = threadIdx.x - 128;
-        for (int k = t; k < p.N; k += 32 * kEpiWarps) { s_c0z[k] = p.c0z[k]; s_c1[k] = p.c1[k]; }
-        for (int k = t; k < p.ncls * p.N; k += 32 * kEpiWarps) s_corr[k] = p.corr[k];
     }
     tc_fence_before();
     __syncthreads();
@@ -252,7 +251,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const bool valid = oy < p.OH && ox < p.OW;
             int cls = 0;
             if (p.ncls == 9) cls = 3 * (oy == 0 ? 0 : (oy == p.OH - 1 ? 2 : 1)) + (ox == 0 ? 0 : (ox == p.OW - 1 ? 2 : 1));
-            const int32_t *corr = s_corr + (size_t)cls * p.N;
+            const int32_t *corr = tab.corr + cls * p.N;
             uint8_t *orow = p.out + (((long long)b * p.OH + oy) * p.OW + ox) * p.N;
 
             mbar_wait(tfull_bar(acc), aph);
@@ -264,8 +263,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 uint32_t w[8];
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
-                    const float4 z = *reinterpret_cast<const float4 *>(s_c0z + c0 + 4 * g);
-                    const float4 sc = *reinterpret_cast<const float4 *>(s_c1 + c0 + 4 * g);
+                    const float4 z = *reinterpret_cast<const float4 *>(tab.c0z + c0 + 4 * g);
+                    const float4 sc = *reinterpret_cast<const float4 *>(tab.c1 + c0 + 4 * g);
                     const int4 kc = *reinterpret_cast<const int4 *>(corr + c0 + 4 * g);
                     const int y0 = requant_nx<BIG>((int)r[4 * g + 0] - kc.x, z.x, sc.x, lo, hi);
                     const int y1 = requant_nx<BIG>((int)r[4 * g + 1] - kc.y, z.y, sc.y, lo, hi);
@@ -334,8 +333,7 @@ bool encode_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *
 size_t plan_smem(const ConvTcPlan &p, int stages) {
     const size_t b_bytes = (size_t)p.KH * p.KW * p.CB * p.N * 128;
     const size_t stage = (size_t)(p.TH + p.KH - 1) * p.TW * 128;
-    const size_t tables = (size_t)p.N * 8 + (size_t)p.ncls * p.N * 4;
-    return 1024 + b_bytes + stage * stages + tables + (2 * kMaxStages + 5) * 8 + 16;
+    return b_bytes + stage * stages + (2 * kMaxStages + 5) * 8 + 16;
 }
 
 }  // namespace
@@ -383,11 +381,13 @@ bool conv_tc_available(std::string *why) { return get_encode_fn(why) != nullptr;
 bool conv_tc_finalize_plan(ConvTcPlan &p, std::string *why) {
     auto no = [&](const char *m) { if (why) *why = m; return false; };
     if (p.N % 32 != 0 || p.N < 32 || p.N > 256) return no("N must be a multiple of 32 in [32,256]");
+    if (p.ncls != 1 && p.ncls != 9) return no("border classes must be 1 or 9");
+    if ((int)p.h_c0z.size() != p.N || (int)p.h_c1.size() != p.N || (int)p.h_corr.size() != p.ncls * p.N) return no("epilogue tables have the wrong size");
     if (p.TH * p.TW != 128 || (p.TW & (p.TW - 1)) != 0 || p.TW < 8) return no("tile must be TH x TW = 128 pixels with TW a power of two >= 8");
     if (p.C != 128 * p.CB) return no("row bytes must be 128 * CB");
     if (p.TH + p.KH - 1 > 256) return no("patch too tall for one TMA box");
     int stages = 0;
-    for (int s = 4; s >= 2; --s)
+    for (int s = 6; s >= 2; --s)
         if (plan_smem(p, s) <= kSmemLimit) { stages = s; break; }
     if (!stages) return no("weights + pipeline stages do not fit in 227 KB of shared memory");
     p.stages = stages;
@@ -436,7 +436,11 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     }
 
     ConvTcParams k{};
-    k.out = l.out; k.c0z = p.d_c0z; k.c1 = p.d_c1; k.corr = p.d_corr;
+    k.out = l.out;
+    ConvTcTables tab;
+    std::memcpy(tab.c0z, p.h_c0z.data(), (size_t)p.N * 4);
+    std::memcpy(tab.c1, p.h_c1.data(), (size_t)p.N * 4);
+    std::memcpy(tab.corr, p.h_corr.data(), (size_t)p.ncls * p.N * 4);
     k.N = p.N; k.CB = p.CB; k.KH = p.KH; k.KW = p.KW; k.TW = p.TW; k.TH = p.TH;
     k.tw_log2 = 0;
     while ((1 << k.tw_log2) < p.TW) ++k.tw_log2;
@@ -466,8 +470,8 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     });
     if (attr_err != cudaSuccess) return attr_err;
     const unsigned grid = (unsigned)(k.num_tiles < num_sms ? k.num_tiles : num_sms);
-    if (p.big_acc) conv_tc_kernel<true><<<grid, kThreads, p.smem_bytes, s>>>(ta, tb, k);
-    else conv_tc_kernel<false><<<grid, kThreads, p.smem_bytes, s>>>(ta, tb, k);
+    if (p.big_acc) conv_tc_kernel<true><<<grid, kThreads, p.smem_bytes, s>>>(ta, tb, tab, k);
+    else conv_tc_kernel<false><<<grid, kThreads, p.smem_bytes, s>>>(ta, tb, tab, k);
     return cudaGetLastError();
 }
 

@@ -34,11 +34,11 @@ struct ConvTcPlan {
     int ncls = 1;       // border classes (1, or 9 for 3x3)
     int stages = 2;
     size_t smem_bytes = 0;
-    // device buffers owned by the model blob
+    // device buffer owned by the model blob
     const uint8_t *d_wmat = nullptr;   // [N][K_total] bytes, K_total = KH*KW*C
-    const float *d_c0z = nullptr;      // [N]
-    const float *d_c1 = nullptr;       // [N]
-    const int32_t *d_corr = nullptr;   // [ncls][N]  in_zp * (sum of weights over the taps valid for that border class)
+    // epilogue tables (host copies; they travel to the kernel as __grid_constant__ parameters = constant bank)
+    std::vector<float> h_c0z, h_c1;    // [N]
+    std::vector<int32_t> h_corr;       // [ncls][N]  in_zp * (sum of weights over the taps valid for that border class)
     float lo = -128.f, hi = 127.f;
     bool big_acc = false;              // |acc - corr| may exceed 2^22: use the general exact int->float in the epilogue
     alignas(64) unsigned char tmap_b[128];  // CUtensorMap of the weight matrix

@@ -109,9 +109,7 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
                     std::vector<int32_t> ec((size_t)tc.N);
                     for (int n = 0; n < tc.N; ++n) { ez[(size_t)n] = c0z[(size_t)(n % Cout)]; es[(size_t)n] = c1[(size_t)(n % Cout)]; ec[(size_t)n] = kcorr[(size_t)(n % Cout)]; }
                     o_tc_w = bb.add(wm.data(), wm.size());
-                    o_tc_c0z = bb.add(ez.data(), ez.size() * 4);
-                    o_tc_c1 = bb.add(es.data(), es.size() * 4);
-                    o_tc_corr = bb.add(ec.data(), ec.size() * 4);
+                    tc.h_c0z = ez; tc.h_c1 = es; tc.h_corr = ec;
                     kernel = Kernel::ConvTcPointwise;
                     return;
                 }
@@ -131,8 +129,7 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
                 tc.lo = (float)L.act_lo; tc.hi = (float)L.act_hi; tc.big_acc = big_acc;
                 std::vector<int32_t> corr = conv_tc_border_corr_3x3(L.w.data(), L.Cout, L.Cin, L.in_zp, L.H, L.W);
                 o_tc_w = o_w;  // OHWI is already the [N][K_total] matrix
-                o_tc_c0z = o_c0z; o_tc_c1 = o_c1;
-                o_tc_corr = bb.add(corr.data(), corr.size() * 4);
+                tc.h_c0z = c0z; tc.h_c1 = c1; tc.h_corr = corr;
                 kernel = Kernel::ConvTc3x3;
                 return;
             } else {
@@ -181,9 +178,6 @@ bool LayerExec::resolve(const uint8_t *d, std::string *err) {
         a.big_acc = big_acc;
         if (kernel == Kernel::ConvTcPointwise || kernel == Kernel::ConvTc3x3) {
             tc.d_wmat = at(o_tc_w);
-            tc.d_c0z = reinterpret_cast<const float *>(at(o_tc_c0z));
-            tc.d_c1 = reinterpret_cast<const float *>(at(o_tc_c1));
-            tc.d_corr = reinterpret_cast<const int32_t *>(at(o_tc_corr));
             std::string why;
             if (!conv_tc_finalize_plan(tc, &why)) {  // fall back to the SIMT path, never to the CPU
                 why_not_fast = "tensor core plan rejected: " + why;

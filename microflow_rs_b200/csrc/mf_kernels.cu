@@ -285,23 +285,30 @@ __global__ void __launch_bounds__(128) dwconv3x3_rows_kernel(ConvArgs a, uint32_
     const bool cok0 = (unsigned)c0 < (unsigned)a.W, cok1 = (unsigned)(c0 + 1) < (unsigned)a.W, cok2 = (unsigned)(c0 + 2) < (unsigned)a.W;
     const int i0 = (int)(strip * rows_per_strip);
     const int i1 = min(a.OH, i0 + (int)rows_per_strip);
-    const size_t row_words = (size_t)a.W * G;
+    const int row_words = a.W * G, out_row_words = a.OW * G;
     const float lo = a.lo, hi = a.hi;
+    const int H = a.H;
 
     for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
-        const uint32_t *inw = reinterpret_cast<const uint32_t *>(a.in) + (size_t)b * a.H * row_words + (ptrdiff_t)c0 * G + g;
-        uint32_t *outw = reinterpret_cast<uint32_t *>(a.out) + ((size_t)b * a.OH * a.OW + j) * G + g;
-        auto load_row = [&](int r, int (&d)[12]) {   // d[n * 4 + k] = channel k of window column n
-            const bool rok = (unsigned)r < (unsigned)a.H;
-            const uint32_t *p = inw + (ptrdiff_t)r * (ptrdiff_t)row_words;
-            const uint32_t v0 = (rok && cok0) ? __ldg(p) : izw;
-            const uint32_t v1 = (rok && cok1) ? __ldg(p + G) : izw;
-            const uint32_t v2 = (rok && cok2) ? __ldg(p + 2 * G) : izw;
+        int r = S * i0 - a.off_r;                                  // input row of the next load
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(a.in) + (size_t)b * H * row_words + (ptrdiff_t)r * row_words + (ptrdiff_t)c0 * G + g;
+        uint32_t *o = reinterpret_cast<uint32_t *>(a.out) + ((size_t)b * a.OH + i0) * out_row_words + (size_t)j * G + g;
+        // raw (packed) loads are issued one row ahead of their first use so that their latency hides behind the MACs and
+        // the epilogue of the previous output row; pointers advance by increments (no per-load 64-bit multiply)
+        auto ld = [&](uint32_t &v0, uint32_t &v1, uint32_t &v2) {
+            const bool rok = (unsigned)r < (unsigned)H;
+            v0 = (rok && cok0) ? __ldg(p) : izw;
+            v1 = (rok && cok1) ? __ldg(p + G) : izw;
+            v2 = (rok && cok2) ? __ldg(p + 2 * G) : izw;
+            p += row_words;
+            r += 1;
+        };
+        auto unpack = [&](uint32_t v0, uint32_t v1, uint32_t v2, int (&d)[12]) {   // d[n * 4 + k] = channel k of window column n
             d[0] = sx8<0>(v0); d[1] = sx8<1>(v0); d[2] = sx8<2>(v0); d[3] = sx8<3>(v0);
             d[4] = sx8<0>(v1); d[5] = sx8<1>(v1); d[6] = sx8<2>(v1); d[7] = sx8<3>(v1);
             d[8] = sx8<0>(v2); d[9] = sx8<1>(v2); d[10] = sx8<2>(v2); d[11] = sx8<3>(v2);
         };
-        auto emit = [&](const int (&r0)[12], const int (&r1)[12], const int (&r2)[12], int i) {
+        auto emit = [&](const int (&r0)[12], const int (&r1)[12], const int (&r2)[12]) {
             int acc[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -311,27 +318,32 @@ __global__ void __launch_bounds__(128) dwconv3x3_rows_kernel(ConvArgs a, uint32_
                 s += r2[k] * wi[6][k]; s += r2[4 + k] * wi[7][k]; s += r2[8 + k] * wi[8][k];
                 acc[k] = s;
             }
-            outw[(size_t)i * a.OW * G] = pack4(requant_nx<false>(acc[0] - kc.x, z.x, sc.x, lo, hi), requant_nx<false>(acc[1] - kc.y, z.y, sc.y, lo, hi),
-                                              requant_nx<false>(acc[2] - kc.z, z.z, sc.z, lo, hi), requant_nx<false>(acc[3] - kc.w, z.w, sc.w, lo, hi));
+            *o = pack4(requant_nx<false>(acc[0] - kc.x, z.x, sc.x, lo, hi), requant_nx<false>(acc[1] - kc.y, z.y, sc.y, lo, hi),
+                       requant_nx<false>(acc[2] - kc.z, z.z, sc.z, lo, hi), requant_nx<false>(acc[3] - kc.w, z.w, sc.w, lo, hi));
+            o += out_row_words;
         };
         int ra[12], rb[12], rc[12];
-        int r = S * i0 - a.off_r;
-        int i = i0;
+        uint32_t q0, q1, q2, s0, s1, s2;
+        int left = i1 - i0;                                         // output rows still to produce
         if (S == 1) {
-            load_row(r, ra);
-            load_row(r + 1, rb);
+            ld(q0, q1, q2); unpack(q0, q1, q2, ra);
+            ld(q0, q1, q2); unpack(q0, q1, q2, rb);
+            ld(q0, q1, q2);
             while (true) {
-                load_row(r + 2, rc); emit(ra, rb, rc, i); if (++i >= i1) break;
-                load_row(r + 3, ra); emit(rb, rc, ra, i); if (++i >= i1) break;
-                load_row(r + 4, rb); emit(rc, ra, rb, i); if (++i >= i1) break;
-                r += 3;
+                unpack(q0, q1, q2, rc); if (left > 1) ld(q0, q1, q2); emit(ra, rb, rc); if (--left == 0) break;
+                unpack(q0, q1, q2, ra); if (left > 1) ld(q0, q1, q2); emit(rb, rc, ra); if (--left == 0) break;
+                unpack(q0, q1, q2, rb); if (left > 1) ld(q0, q1, q2); emit(rc, ra, rb); if (--left == 0) break;
             }
         } else {
-            load_row(r, ra);
+            ld(q0, q1, q2); unpack(q0, q1, q2, ra);
+            ld(q0, q1, q2); ld(s0, s1, s2);
             while (true) {
-                load_row(r + 1, rb); load_row(r + 2, rc); emit(ra, rb, rc, i); if (++i >= i1) break;
-                load_row(r + 3, rb); load_row(r + 4, ra); emit(rc, rb, ra, i); if (++i >= i1) break;
-                r += 4;
+                unpack(q0, q1, q2, rb); unpack(s0, s1, s2, rc);
+                if (left > 1) { ld(q0, q1, q2); ld(s0, s1, s2); }
+                emit(ra, rb, rc); if (--left == 0) break;
+                unpack(q0, q1, q2, rb); unpack(s0, s1, s2, ra);
+                if (left > 1) { ld(q0, q1, q2); ld(s0, s1, s2); }
+                emit(rc, rb, ra); if (--left == 0) break;
             }
         }
     }

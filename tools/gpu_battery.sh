@@ -45,3 +45,19 @@ except Exception as e:
 PY
 done
 tail -n 3 gpurun_out/*.err 2>/dev/null | tail -20
+if has cpuscale; then
+  python - > gpurun_out/cpu_scaling.txt 2>&1 <<'PY'
+import sys, time, os
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+import numpy as np, oracle
+from conftest import MODELS, splitmix_bytes
+o = oracle.Model(MODELS / "person_detect.tflite", fast=True)
+print("nproc", os.cpu_count(), "affinity", len(os.sched_getaffinity(0)))
+for th in (1, 4, 16, 32, 64, 128):
+    n = 16 * th
+    xs = splitmix_bytes(3, n * o.in_elems).reshape(n, -1)
+    t = time.perf_counter(); o.predict_many_quantized(xs, threads=th); dt = time.perf_counter() - t
+    print(th, "threads:", n / dt, "inf/s", (n / dt) / th, "per thread")
+PY
+  cat gpurun_out/cpu_scaling.txt
+fi
