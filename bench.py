@@ -164,11 +164,6 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-class _DevMem:
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-
 def conv2d_roofline(torch, mf, peaks, steps, warmup, batch=16):
     """BASELINE config 5: synthetic Conv2D 224x224x128 -> 128, k3 s1 SAME, int8, ReLU6 on the tcgen05 kernel."""
     H = W = 224
@@ -224,10 +219,9 @@ def main():
     # ---- init: ONE NCCL broadcast of the static weights/constants blob from rank 0 (ranks != 0 clear theirs first)
     ptr, nbytes = m.blob()
     if world > 1 and nbytes:
-        blob = torch.as_tensor(_DevMem(ptr, nbytes), device=f"cuda:{local_rank}")
-        if rank != 0:
-            blob.zero_()
-        dist.broadcast(blob, src=0)
+        from microflow_rs_b200 import sharding
+        blob = torch.as_tensor(sharding.DeviceBytes(ptr, nbytes), device=f"cuda:{local_rank}")
+        sharding.broadcast_weights(dist, blob, rank)
         torch.cuda.synchronize()
 
     ie, oe = m.in_elems, m.out_elems
