@@ -323,26 +323,34 @@ __global__ void __launch_bounds__(128) dwconv3x3_rows_kernel(ConvArgs a, uint32_
             o += out_row_words;
         };
         int ra[12], rb[12], rc[12];
-        uint32_t q0, q1, q2, s0, s1, s2;
+        uint32_t q0, q1, q2, s0, s1, s2, t0, t1, t2, u0, u1, u2;
         int left = i1 - i0;                                         // output rows still to produce
+        // rows needed beyond the prologue: stride 1 -> `left` more rows, stride 2 -> 2 * left; `avail` counts rows not yet requested
         if (S == 1) {
             ld(q0, q1, q2); unpack(q0, q1, q2, ra);
             ld(q0, q1, q2); unpack(q0, q1, q2, rb);
-            ld(q0, q1, q2);
+            int avail = left;                                       // window rows r+2 .. r+1+left
+            ld(q0, q1, q2); --avail;                                // row for output 0
+            if (avail > 0) { ld(s0, s1, s2); --avail; }            // row for output 1 (two rows in flight from here on)
             while (true) {
-                unpack(q0, q1, q2, rc); if (left > 1) ld(q0, q1, q2); emit(ra, rb, rc); if (--left == 0) break;
-                unpack(q0, q1, q2, ra); if (left > 1) ld(q0, q1, q2); emit(rb, rc, ra); if (--left == 0) break;
-                unpack(q0, q1, q2, rb); if (left > 1) ld(q0, q1, q2); emit(rc, ra, rb); if (--left == 0) break;
+                unpack(q0, q1, q2, rc); if (avail > 0) { ld(q0, q1, q2); --avail; } emit(ra, rb, rc); if (--left == 0) break;
+                unpack(s0, s1, s2, ra); if (avail > 0) { ld(s0, s1, s2); --avail; } emit(rb, rc, ra); if (--left == 0) break;
+                unpack(q0, q1, q2, rb); if (avail > 0) { ld(q0, q1, q2); --avail; } emit(rc, ra, rb); if (--left == 0) break;
+                unpack(s0, s1, s2, rc); if (avail > 0) { ld(s0, s1, s2); --avail; } emit(ra, rb, rc); if (--left == 0) break;
+                unpack(q0, q1, q2, ra); if (avail > 0) { ld(q0, q1, q2); --avail; } emit(rb, rc, ra); if (--left == 0) break;
+                unpack(s0, s1, s2, rb); if (avail > 0) { ld(s0, s1, s2); --avail; } emit(rc, ra, rb); if (--left == 0) break;
             }
         } else {
             ld(q0, q1, q2); unpack(q0, q1, q2, ra);
-            ld(q0, q1, q2); ld(s0, s1, s2);
+            int avail = left;                                       // pairs of rows not yet requested
+            ld(q0, q1, q2); ld(s0, s1, s2); --avail;                // pair for output 0
+            if (avail > 0) { ld(t0, t1, t2); ld(u0, u1, u2); --avail; }   // pair for output 1
             while (true) {
                 unpack(q0, q1, q2, rb); unpack(s0, s1, s2, rc);
-                if (left > 1) { ld(q0, q1, q2); ld(s0, s1, s2); }
+                if (avail > 0) { ld(q0, q1, q2); ld(s0, s1, s2); --avail; }
                 emit(ra, rb, rc); if (--left == 0) break;
-                unpack(q0, q1, q2, rb); unpack(s0, s1, s2, ra);
-                if (left > 1) { ld(q0, q1, q2); ld(s0, s1, s2); }
+                unpack(t0, t1, t2, rb); unpack(u0, u1, u2, ra);
+                if (avail > 0) { ld(t0, t1, t2); ld(u0, u1, u2); --avail; }
                 emit(rc, rb, ra); if (--left == 0) break;
             }
         }
