@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <utility>
@@ -75,20 +76,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a protocol bug must trap (launch failure) instead of hanging the GPU.
+// Bounded wait: a protocol bug must trap (launch failure) instead of hanging the GPU.  try_wait suspends the thread in
+// hardware for up to the hinted time, so waiting warps do not burn issue slots that the working warps need.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
-    const long long t0 = clock64();
-    while (true) {
+    for (uint32_t spins = 0;; ++spins) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(20000u)
             : "memory");
         if (done) break;
-        if (clock64() - t0 > 8000000000ll) __trap();
+        if (spins > (1u << 22)) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
@@ -143,7 +144,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <bool BIG>
+// KH_T/KW_T/CB_T != 0: compile-time loop bounds, so the single MMA-issuing thread spends ~3 scalar instructions per MMA
+// (descriptor = base + constant); XUG = how many of the 8 four-value groups of each 32-column chunk take the XU epilogue.
+template <bool BIG, int XUG, int KH_T, int KW_T, int CB_T>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ ConvTcTables tab,
                const ConvTcParams p) {
@@ -162,6 +165,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     auto tempty_bar = [&](uint32_t a) { return bar0 + 8u * (2 * kMaxStages + 3 + a); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KH = KH_T ? KH_T : p.KH, KW = KW_T ? KW_T : p.KW, CB = CB_T ? CB_T : p.CB;
 
     if (warp == kWarpTma && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
@@ -193,8 +197,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 uint32_t b, rem, ty, tx;
                 p.fd_img.divmod((uint32_t)tile, b, rem);
                 p.fd_tx.divmod(rem, ty, tx);
-                for (int n = 0; n < p.KW; ++n)
-                    for (int cb = 0; cb < p.CB; ++cb) {
+                for (int n = 0; n < KW; ++n)
+                    for (int cb = 0; cb < CB; ++cb) {
                         mbar_wait(empty_bar(s), ph ^ 1);
                         mbar_expect_tx(full_bar(s), p.stage_bytes);
                         tma_load_4d(smem_u32(sA + (size_t)s * p.stage_bytes), &tmap_a, full_bar(s), cb * 128, (int)tx * p.TW + n - p.off_c,
@@ -213,24 +217,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint64_t desc_hi = make_desc(0);
             const uint32_t a0 = smem_u32(sA) >> 4, b0 = smem_u32(sB) >> 4;
             const uint32_t stage16 = p.stage_bytes >> 4, bblk16 = p.b_block_bytes >> 4, arow16 = (uint32_t)p.TW * 8u;   // TW rows * 128 B / 16
+            if (a0 + (uint32_t)p.stages * stage16 >= (1u << 14) || b0 + p.nkb * bblk16 >= (1u << 14)) __trap();     // descriptor start field would overflow
             for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const uint32_t acc = it & 1, aph = (it >> 1) & 1;
                 mbar_wait(tempty_bar(acc), aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.N;
                 uint32_t accumulate = 0;
-                for (int n = 0; n < p.KW; ++n)
-                    for (int cb = 0; cb < p.CB; ++cb) {
+#pragma unroll
+                for (int n = 0; n < KW; ++n)
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb) {
                         mbar_wait(full_bar(s), ph);
                         tc_fence_after();
-                        uint32_t a_row = a0 + s * stage16;
-                        uint32_t b_blk = b0 + (uint32_t)(n * p.CB + cb) * bblk16;
-                        const uint32_t b_step = (uint32_t)(p.KW * p.CB) * bblk16;       // next kernel row: kb += KW * CB
-                        for (int m = 0; m < p.KH; ++m, a_row += arow16, b_blk += b_step) {
+                        const uint64_t adesc = desc_hi | (uint64_t)(a0 + s * stage16);                       // start field never carries:
+                        const uint64_t bdesc = desc_hi | (uint64_t)(b0 + (uint32_t)(n * CB + cb) * bblk16);  // smem < 256 KB -> (addr >> 4) < 2^14
+#pragma unroll
+                        for (int m = 0; m < KH; ++m) {
 #pragma unroll
                             for (uint32_t ks = 0; ks < 4; ++ks) {
-                                tc_mma_i8(d_tmem, desc_hi | (uint64_t)((a_row + 2 * ks) & 0x3FFFu), desc_hi | (uint64_t)((b_blk + 2 * ks) & 0x3FFFu), p.idesc,
-                                          accumulate);
+                                tc_mma_i8(d_tmem, adesc + (uint64_t)((uint32_t)m * arow16 + 2 * ks), bdesc + (uint64_t)((uint32_t)(m * KW * CB) * bblk16 + 2 * ks),
+                                          p.idesc, accumulate);
                                 accumulate = 1;
                             }
                         }
@@ -272,10 +279,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const float4 z = *reinterpret_cast<const float4 *>(tab.c0z + c0 + 4 * g);
                     const float4 sc = *reinterpret_cast<const float4 *>(tab.c1 + c0 + 4 * g);
                     const int4 kc = *reinterpret_cast<const int4 *>(corr + c0 + 4 * g);
-                    const int y0 = requant_nx<BIG>((int)r[4 * g + 0] - kc.x, z.x, sc.x, lo, hi);
-                    const int y1 = requant_nx<BIG>((int)r[4 * g + 1] - kc.y, z.y, sc.y, lo, hi);
-                    const int y2 = requant_nx<BIG>((int)r[4 * g + 2] - kc.z, z.z, sc.z, lo, hi);
-                    const int y3 = requant_nx<BIG>((int)r[4 * g + 3] - kc.w, z.w, sc.w, lo, hi);
+                    const int y0 = (g < XUG ? requant_xu<true>((int)r[4 * g + 0] - kc.x, z.x, sc.x, lo, hi) : requant_nx<BIG>((int)r[4 * g + 0] - kc.x, z.x, sc.x, lo, hi));
+                    const int y1 = (g < XUG ? requant_xu<true>((int)r[4 * g + 1] - kc.y, z.y, sc.y, lo, hi) : requant_nx<BIG>((int)r[4 * g + 1] - kc.y, z.y, sc.y, lo, hi));
+                    const int y2 = (g < XUG ? requant_xu<true>((int)r[4 * g + 2] - kc.z, z.z, sc.z, lo, hi) : requant_nx<BIG>((int)r[4 * g + 2] - kc.z, z.z, sc.z, lo, hi));
+                    const int y3 = (g < XUG ? requant_xu<true>((int)r[4 * g + 3] - kc.w, z.w, sc.w, lo, hi) : requant_nx<BIG>((int)r[4 * g + 3] - kc.w, z.w, sc.w, lo, hi));
                     w[g] = pack4(y0, y1, y2, y3);
                 }
                 if (valid) {
@@ -468,16 +475,42 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     k.tmem_cols = 2 * p.N <= 32 ? 32 : (2 * p.N <= 64 ? 64 : (2 * p.N <= 128 ? 128 : (2 * p.N <= 256 ? 256 : 512)));
     if (k.num_tiles <= 0) return cudaSuccess;
 
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
-    });
-    if (attr_err != cudaSuccess) return attr_err;
+    // epilogue mix: XU path needs the full int8 clamp range (F2I.S8 saturation); MF_TC_XUG overrides the default group count
+    static const int env_xug = [] { const char *e = std::getenv("MF_TC_XUG"); return e ? std::atoi(e) : -1; }();
+    const bool full = p.lo == -128.f && p.hi == 127.f;
+    int xug = env_xug >= 0 ? env_xug : 5;
+    if (!full) xug = 0;
+    xug = xug >= 8 ? 8 : (xug >= 5 ? 5 : 0);
+    const int shape = (p.KH == 3 && p.KW == 3 && p.CB == 1) ? 1 : ((p.KH == 1 && p.KW == 1 && p.CB == 1) ? 2 : ((p.KH == 1 && p.KW == 1 && p.CB == 2) ? 3 : 0));
+    using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const ConvTcTables, const ConvTcParams);
+    KernelFn fn = nullptr;
+#define MF_TC_PICK(BIGV, XUV)                                                                               \
+    switch (shape) {                                                                                        \
+        case 1: fn = conv_tc_kernel<BIGV, XUV, 3, 3, 1>; break;                                             \
+        case 2: fn = conv_tc_kernel<BIGV, XUV, 1, 1, 1>; break;                                             \
+        case 3: fn = conv_tc_kernel<BIGV, XUV, 1, 1, 2>; break;                                             \
+        default: fn = conv_tc_kernel<BIGV, XUV, 0, 0, 0>; break;                                            \
+    }
+    if (p.big_acc) {
+        if (xug == 8) { MF_TC_PICK(true, 8) } else if (xug == 5) { MF_TC_PICK(true, 5) } else { MF_TC_PICK(true, 0) }
+    } else {
+        if (xug == 8) { MF_TC_PICK(false, 8) } else if (xug == 5) { MF_TC_PICK(false, 5) } else { MF_TC_PICK(false, 0) }
+    }
+#undef MF_TC_PICK
+    static std::mutex attr_mu;
+    static std::vector<KernelFn> attr_done;
+    {
+        std::lock_guard<std::mutex> lock(attr_mu);
+        bool have = false;
+        for (auto f : attr_done) have = have || f == fn;
+        if (!have) {
+            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
+            if (e != cudaSuccess) return e;
+            attr_done.push_back(fn);
+        }
+    }
     const unsigned grid = (unsigned)(k.num_tiles < num_sms ? k.num_tiles : num_sms);
-    if (p.big_acc) conv_tc_kernel<true><<<grid, kThreads, p.smem_bytes, s>>>(ta, tb, tab, k);
-    else conv_tc_kernel<false><<<grid, kThreads, p.smem_bytes, s>>>(ta, tb, tab, k);
+    fn<<<grid, kThreads, p.smem_bytes, s>>>(ta, tb, tab, k);
     return cudaGetLastError();
 }
 

@@ -73,6 +73,18 @@ template <bool BIG> __device__ __forceinline__ int requant_nx(int acc, float c0z
     const float t = __fadd_rn(c0z, __fmul_rn(c1, i2f_exact<BIG>(acc)));
     return round_clamp_nx(t, lo, hi);
 }
+// XU variant for int8 outputs: I2F + F2I (two XU-pipe instructions, ~7 issue slots per value instead of 13-17).
+// FULL: the clamp is the whole int8 range, so the saturating F2I.S8 replaces both FMNMX
+// (cvt.rzi.sat.s8.f32 == trunc then saturate to [-128,127], NaN -> 0, exactly Rust's `as i8`).
+template <bool FULL> __device__ __forceinline__ int requant_xu(int acc, float c0z, float c1, float lo, float hi) {
+    if (!FULL) return requant(acc, c0z, c1, lo, hi);
+    const float t = __fadd_rn(c0z, __fmul_rn(c1, __int2float_rn(acc)));
+    const float s = __fadd_rn(t, round_bias(t));
+    int y;
+    asm("cvt.rzi.sat.s8.f32 %0, %1;" : "=r"(y) : "f"(s));
+    return y;
+}
+
 // sign-extended byte k of a packed word: one PRMT (selector msb = replicate the sign of the selected byte)
 template <int K> __device__ __forceinline__ int sx8(uint32_t w) {
     int r;

@@ -11,6 +11,8 @@
 //
 // Reference semantics: src/ops/conv_2d.rs:50-107, depthwise_conv_2d.rs:50-104, fully_connected.rs:42-81,
 // average_pool_2d.rs:46-65, softmax.rs:20-26, src/tensor.rs:180-228 (view), src/quantize.rs:16-29.
+#include <cstdlib>
+
 #include "mf_device.cuh"
 #include "mf_kernels.h"
 
@@ -262,8 +264,8 @@ cudaError_t launch_dwconv_c4(const ConvArgs &a, cudaStream_t s) {
 // epilogue constants and all index math are hoisted out of the row loop; MACs are IMAD, the epilogue is XU-free.
 // Lanes run along (column, channel-word), i.e. along contiguous NHWC memory: every load and store is coalesced.
 // ------------------------------------------------------------------------------------------------
-template <int S>
-__global__ void __launch_bounds__(128) dwconv3x3_rows_kernel(ConvArgs a, uint32_t threads_per_sample, uint32_t rows_per_strip, FastDiv fd_xw, FastDiv fd_g) {
+template <int S, int XU>   // XU = how many of the 4 channels of each output word take the XU (I2F + F2I.S8) epilogue
+__global__ void __launch_bounds__(128, 4) dwconv3x3_rows_kernel(ConvArgs a, uint32_t threads_per_sample, uint32_t rows_per_strip, FastDiv fd_xw, FastDiv fd_g) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= threads_per_sample) return;
     const int G = a.Cout >> 2;
@@ -318,8 +320,10 @@ __global__ void __launch_bounds__(128) dwconv3x3_rows_kernel(ConvArgs a, uint32_
                 s += r2[k] * wi[6][k]; s += r2[4 + k] * wi[7][k]; s += r2[8 + k] * wi[8][k];
                 acc[k] = s;
             }
-            *o = pack4(requant_nx<false>(acc[0] - kc.x, z.x, sc.x, lo, hi), requant_nx<false>(acc[1] - kc.y, z.y, sc.y, lo, hi),
-                       requant_nx<false>(acc[2] - kc.z, z.z, sc.z, lo, hi), requant_nx<false>(acc[3] - kc.w, z.w, sc.w, lo, hi));
+            *o = pack4(XU > 0 ? requant_xu<true>(acc[0] - kc.x, z.x, sc.x, lo, hi) : requant_nx<false>(acc[0] - kc.x, z.x, sc.x, lo, hi),
+                       XU > 1 ? requant_xu<true>(acc[1] - kc.y, z.y, sc.y, lo, hi) : requant_nx<false>(acc[1] - kc.y, z.y, sc.y, lo, hi),
+                       XU > 2 ? requant_xu<true>(acc[2] - kc.z, z.z, sc.z, lo, hi) : requant_nx<false>(acc[2] - kc.z, z.z, sc.z, lo, hi),
+                       XU > 3 ? requant_xu<true>(acc[3] - kc.w, z.w, sc.w, lo, hi) : requant_nx<false>(acc[3] - kc.w, z.w, sc.w, lo, hi));
             o += out_row_words;
         };
         int ra[12], rb[12], rc[12];
@@ -371,8 +375,19 @@ cudaError_t launch_dwconv3x3_rows(const ConvArgs &a, cudaStream_t s) {
     const long long per = (long long)strips * xw;
     const FastDiv fxw(xw), fg((uint32_t)G);
     const dim3 grid = grid2(per, 128, a.batch);
-    if (a.sh == 1) dwconv3x3_rows_kernel<1><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
-    else dwconv3x3_rows_kernel<2><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
+    static const int env_xu = [] { const char *e = std::getenv("MF_DW_XU"); return e ? std::atoi(e) : -1; }();
+    int xu = env_xu >= 0 ? env_xu : 2;
+    if (!(a.lo == -128.f && a.hi == 127.f)) xu = 0;             // the XU epilogue relies on F2I.S8 saturation = full int8 clamp
+    xu = xu >= 4 ? 4 : (xu >= 2 ? 2 : 0);
+    if (a.sh == 1) {
+        if (xu == 4) dwconv3x3_rows_kernel<1, 4><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
+        else if (xu == 2) dwconv3x3_rows_kernel<1, 2><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
+        else dwconv3x3_rows_kernel<1, 0><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
+    } else {
+        if (xu == 4) dwconv3x3_rows_kernel<2, 4><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
+        else if (xu == 2) dwconv3x3_rows_kernel<2, 2><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
+        else dwconv3x3_rows_kernel<2, 0><<<grid, 128, 0, s>>>(a, (uint32_t)per, rows, fxw, fg);
+    }
     return cudaGetLastError();
 }
 

@@ -61,3 +61,18 @@ for th in (1, 4, 16, 32, 64, 128):
 PY
   cat gpurun_out/cpu_scaling.txt
 fi
+if has exp; then
+  : > gpurun_out/exp.txt
+  for x in 0 5 8; do
+    echo "== conv3x3 MF_TC_XUG=$x" >> gpurun_out/exp.txt
+    MF_TC_XUG=$x timeout 200 python -m microflow_rs_b200._convbench 16 10 2>&1 | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_launch'], d['roofline']['frac'], d['verified_vs_generic_kernel'])" >> gpurun_out/exp.txt 2>&1
+  done
+  for dw in 0 2 4; do for tc in 0 5 8; do
+    echo "== person_detect MF_DW_XU=$dw MF_TC_XUG=$tc" >> gpurun_out/exp.txt
+    MF_DW_XU=$dw MF_TC_XUG=$tc timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-conv2d 2>&1 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('value %.4g' % d['value'], {k: round(v['ms_per_step'],3) for k,v in d['kernels'].items() if v['ms_per_step']>0.1})" >> gpurun_out/exp.txt 2>&1
+  done; done
+  cat gpurun_out/exp.txt
+fi
