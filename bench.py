@@ -324,10 +324,13 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
             "config": {"workload": f"{wl}.tflite int8, batch {batch} per GPU (BASELINE configs[2])" if wl == "person_detect" else f"{wl}.tflite int8, batch {batch} per GPU",
                        "global_batch": batch * world, "parallelism": f"dp{world} (independent samples, contiguous shards, one NCCL weight broadcast at init)",
-                       "l2": f"inputs rotate over {R} device batches ({R * batch * ie / 1e6:.0f} MB > 126 MB L2)", "chunk": args.chunk or 4096},
+                       "l2": f"inputs rotate over {R} device batches ({R * batch * ie / 1e6:.0f} MB > 126 MB L2)", "chunk": args.chunk or 8192},
             "e2e": {"value": e2e_val, "unit": "inferences/s", "h2d_bytes_per_step": batch * ie, "d2h_bytes_per_step": batch * oe * 4,
                     "api": "mf_predict_many_quantized (pinned host buffers)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "layers": [{"i": i, "op": L["op"], "kernel": L["kernel"], "us_per_step": round(1e3 * float(t) / args.steps, 2),
+                        "GBps": round((L["bytes"] - L["weight_bytes"]) * batch * args.steps / (float(t) * 1e-3) / 1e9, 1) if t > 0 else None}
+                       for i, (L, t) in enumerate(zip(m.layers, layer_ms)) if not L["kernel"].startswith("none")],
             "model_level": {"int8_TOPS": value * 2 * sum(L["macs"] for L in m.layers) / 1e12,
                             "layerwise_GBps": value * sum(L["bytes"] - L["weight_bytes"] for L in m.layers) / 1e9,
                             "compulsory_GBps": value * (ie + oe * 4) / 1e9},

@@ -147,10 +147,14 @@ int predict_many_host(mf_model *m, const void *in_q, const float *in_f32, size_t
     MF_CUDA(cudaSetDevice(m->device));
     const size_t ie = m->spec.in_elems, oe = m->spec.out_elems;
     const size_t le = m->softmax_tail >= 0 ? m->layers[(size_t)m->softmax_tail].spec.in_elems : 0;
+    // host path: pieces small enough that the H2D of piece c+1 overlaps the compute of piece c (two streams), large enough
+    // to keep the per-launch fixed costs amortised
+    size_t piece = std::min(m->chunk, std::max<size_t>(1024, (n + 1) / 2));
+    if (piece > 4096) piece = 4096;
     size_t ci = 0;
-    for (size_t off = 0; off < n; off += m->chunk, ++ci) {
+    for (size_t off = 0; off < n; off += piece, ++ci) {
         Slot &s = m->slot[ci & 1];
-        const size_t cn = std::min(m->chunk, n - off);
+        const size_t cn = std::min(piece, n - off);
         if (in_f32) {   // predict(): quantize the f32 input on the device (src/tensor.rs:80-86, :246-256)
             MF_CUDA(cudaMemcpyAsync(s.in_f32, in_f32 + off * ie, cn * ie * sizeof(float), cudaMemcpyHostToDevice, s.stream));
             cudaError_t e = launch_quantize(s.in_f32, s.in_q, cn * ie, m->spec.in_scale, (float)m->spec.in_zp, m->spec.is_u8_in, s.stream);
@@ -217,7 +221,7 @@ int create_model(const uint8_t *buf, size_t len, const mf_options *opt, mf_model
         }
     m->blob_bytes = bb.bytes().size();
     if (have_device) {
-        m->chunk = o.chunk ? o.chunk : 4096;
+        m->chunk = o.chunk ? o.chunk : 8192;
         if (m->blob_bytes) {
             MF_CUDA(cudaMalloc(&m->d_blob, m->blob_bytes));
             MF_CUDA(cudaMemcpy(m->d_blob, bb.bytes().data(), m->blob_bytes, cudaMemcpyHostToDevice));

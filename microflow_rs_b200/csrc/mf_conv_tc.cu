@@ -478,7 +478,7 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     // epilogue mix: XU path needs the full int8 clamp range (F2I.S8 saturation); MF_TC_XUG overrides the default group count
     static const int env_xug = [] { const char *e = std::getenv("MF_TC_XUG"); return e ? std::atoi(e) : -1; }();
     const bool full = p.lo == -128.f && p.hi == 127.f;
-    int xug = env_xug >= 0 ? env_xug : 5;
+    int xug = env_xug >= 0 ? env_xug : 8;
     if (!full) xug = 0;
     xug = xug >= 8 ? 8 : (xug >= 5 ? 5 : 0);
     const int shape = (p.KH == 3 && p.KW == 3 && p.CB == 1) ? 1 : ((p.KH == 1 && p.KW == 1 && p.CB == 1) ? 2 : ((p.KH == 1 && p.KW == 1 && p.CB == 2) ? 3 : 0));

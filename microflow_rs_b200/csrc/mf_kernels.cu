@@ -331,11 +331,12 @@ __global__ void __launch_bounds__(128, 4) dwconv3x3_rows_kernel(ConvArgs a, uint
         int left = i1 - i0;                                         // output rows still to produce
         // rows needed beyond the prologue: stride 1 -> `left` more rows, stride 2 -> 2 * left; `avail` counts rows not yet requested
         if (S == 1) {
-            ld(q0, q1, q2); unpack(q0, q1, q2, ra);
-            ld(q0, q1, q2); unpack(q0, q1, q2, rb);
-            int avail = left;                                       // window rows r+2 .. r+1+left
+            // prologue: all four first rows are requested before any of them is unpacked (one exposed latency, not three)
+            int avail = left;                                       // window rows beyond the first two: r+2 .. r+1+left
+            ld(t0, t1, t2); ld(u0, u1, u2);
             ld(q0, q1, q2); --avail;                                // row for output 0
             if (avail > 0) { ld(s0, s1, s2); --avail; }            // row for output 1 (two rows in flight from here on)
+            unpack(t0, t1, t2, ra); unpack(u0, u1, u2, rb);
             while (true) {
                 unpack(q0, q1, q2, rc); if (avail > 0) { ld(q0, q1, q2); --avail; } emit(ra, rb, rc); if (--left == 0) break;
                 unpack(s0, s1, s2, ra); if (avail > 0) { ld(s0, s1, s2); --avail; } emit(rb, rc, ra); if (--left == 0) break;
@@ -345,10 +346,12 @@ __global__ void __launch_bounds__(128, 4) dwconv3x3_rows_kernel(ConvArgs a, uint
                 unpack(s0, s1, s2, rb); if (avail > 0) { ld(s0, s1, s2); --avail; } emit(rc, ra, rb); if (--left == 0) break;
             }
         } else {
-            ld(q0, q1, q2); unpack(q0, q1, q2, ra);
+            uint32_t v0, v1, v2;
             int avail = left;                                       // pairs of rows not yet requested
+            ld(v0, v1, v2);
             ld(q0, q1, q2); ld(s0, s1, s2); --avail;                // pair for output 0
             if (avail > 0) { ld(t0, t1, t2); ld(u0, u1, u2); --avail; }   // pair for output 1
+            unpack(v0, v1, v2, ra);
             while (true) {
                 unpack(q0, q1, q2, rb); unpack(s0, s1, s2, rc);
                 if (avail > 0) { ld(q0, q1, q2); ld(s0, s1, s2); --avail; }
@@ -368,15 +371,16 @@ cudaError_t launch_dwconv3x3_rows(const ConvArgs &a, cudaStream_t s) {
     if (a.batch <= 0) return cudaSuccess;
     const int G = a.Cout / 4;
     const uint32_t xw = (uint32_t)(a.OW * G);
-    // strips of output rows: long enough to amortise the 2 extra window rows, short enough to fill the machine
-    uint32_t rows = a.OH <= 12 ? (uint32_t)a.OH : 8u;
-    if ((long long)xw * a.batch < 148 * 4 * 128) rows = a.OH >= 4 ? (uint32_t)((a.OH + 1) / 2) : (uint32_t)a.OH;
+    // strips of output rows: each strip pays an exposed load latency and ~80 instructions of setup once, so they should be
+    // as long as the machine still fills: whole columns when that leaves >= 8 CTAs of 128 threads per SM
+    uint32_t rows = (uint32_t)a.OH;
+    while (rows > 4 && (long long)xw * a.batch * ((a.OH + rows - 1) / rows) < 148ll * 8 * 128) rows = (rows + 1) / 2;
     const uint32_t strips = (uint32_t)((a.OH + rows - 1) / rows);
     const long long per = (long long)strips * xw;
     const FastDiv fxw(xw), fg((uint32_t)G);
     const dim3 grid = grid2(per, 128, a.batch);
     static const int env_xu = [] { const char *e = std::getenv("MF_DW_XU"); return e ? std::atoi(e) : -1; }();
-    int xu = env_xu >= 0 ? env_xu : 2;
+    int xu = env_xu >= 0 ? env_xu : 4;
     if (!(a.lo == -128.f && a.hi == 127.f)) xu = 0;             // the XU epilogue relies on F2I.S8 saturation = full int8 clamp
     xu = xu >= 4 ? 4 : (xu >= 2 ? 2 : 0);
     if (a.sh == 1) {
