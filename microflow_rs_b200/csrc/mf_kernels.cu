@@ -266,6 +266,12 @@ cudaError_t launch_dwconv_c4(const ConvArgs &a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 template <int S, int XU>   // XU = how many of the 4 channels of each output word take the XU (I2F + F2I.S8) epilogue
 __global__ void __launch_bounds__(128, 4) dwconv3x3_rows_kernel(ConvArgs a, uint32_t threads_per_sample, uint32_t rows_per_strip, FastDiv fd_xw, FastDiv fd_g) {
+    // Input rows travel global -> shared through a private cp.async ring per thread (DEPTH rows x 3 words): the loads of
+    // rows r+2 .. r+DEPTH+1 are in flight while row r is being multiplied, at zero register cost, so the DRAM latency
+    // (~1 us under load) is covered even at 16 resident warps per SM.  Every thread only reads what it copied itself:
+    // cp.async.wait_group is the only synchronisation.
+    constexpr int DEPTH = (S == 1) ? 4 : 6;
+    __shared__ uint32_t ring[DEPTH][3][128];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= threads_per_sample) return;
     const int G = a.Cout >> 2;
@@ -290,25 +296,36 @@ __global__ void __launch_bounds__(128, 4) dwconv3x3_rows_kernel(ConvArgs a, uint
     const int row_words = a.W * G, out_row_words = a.OW * G;
     const float lo = a.lo, hi = a.hi;
     const int H = a.H;
+    const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(&ring[0][0][threadIdx.x]);
 
     for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
-        int r = S * i0 - a.off_r;                                  // input row of the next load
-        const uint32_t *p = reinterpret_cast<const uint32_t *>(a.in) + (size_t)b * H * row_words + (ptrdiff_t)r * row_words + (ptrdiff_t)c0 * G + g;
+        const int r_first = S * i0 - a.off_r;
+        const int total = (S == 1) ? (i1 - i0) + 2 : 2 * (i1 - i0) + 1;       // input rows this strip consumes
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(a.in) + (size_t)b * H * row_words + (ptrdiff_t)r_first * row_words + (ptrdiff_t)c0 * G + g;
         uint32_t *o = reinterpret_cast<uint32_t *>(a.out) + ((size_t)b * a.OH + i0) * out_row_words + (size_t)j * G + g;
-        // raw (packed) loads are issued one row ahead of their first use so that their latency hides behind the MACs and
-        // the epilogue of the previous output row; pointers advance by increments (no per-load 64-bit multiply)
-        auto ld = [&](uint32_t &v0, uint32_t &v1, uint32_t &v2) {
-            const bool rok = (unsigned)r < (unsigned)H;
-            v0 = (rok && cok0) ? __ldg(p) : izw;
-            v1 = (rok && cok1) ? __ldg(p + G) : izw;
-            v2 = (rok && cok2) ? __ldg(p + 2 * G) : izw;
+        int issued = 0, taken = 0;
+        auto issue = [&]() {      // request input row r_first + issued (one commit group per row, empty past the end)
+            if (issued < total && (unsigned)(r_first + issued) < (unsigned)H) {
+                const uint32_t dst = ring0 + (uint32_t)(issued % DEPTH) * (3 * 128 * 4);
+                if (cok0) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(p) : "memory");
+                if (cok1) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 512), "l"(p + G) : "memory");
+                if (cok2) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 1024), "l"(p + 2 * G) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
             p += row_words;
-            r += 1;
+            ++issued;
         };
-        auto unpack = [&](uint32_t v0, uint32_t v1, uint32_t v2, int (&d)[12]) {   // d[n * 4 + k] = channel k of window column n
+        auto take = [&](int (&d)[12]) {   // d[n * 4 + k] = channel k of window column n of input row r_first + taken
+            asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+            const bool rok = (unsigned)(r_first + taken) < (unsigned)H;
+            const int slot = taken % DEPTH;
+            const uint32_t v0 = (rok && cok0) ? ring[slot][0][threadIdx.x] : izw;
+            const uint32_t v1 = (rok && cok1) ? ring[slot][1][threadIdx.x] : izw;
+            const uint32_t v2 = (rok && cok2) ? ring[slot][2][threadIdx.x] : izw;
             d[0] = sx8<0>(v0); d[1] = sx8<1>(v0); d[2] = sx8<2>(v0); d[3] = sx8<3>(v0);
             d[4] = sx8<0>(v1); d[5] = sx8<1>(v1); d[6] = sx8<2>(v1); d[7] = sx8<3>(v1);
             d[8] = sx8<0>(v2); d[9] = sx8<1>(v2); d[10] = sx8<2>(v2); d[11] = sx8<3>(v2);
+            ++taken;
         };
         auto emit = [&](const int (&r0)[12], const int (&r1)[12], const int (&r2)[12]) {
             int acc[4];
@@ -327,40 +344,26 @@ __global__ void __launch_bounds__(128, 4) dwconv3x3_rows_kernel(ConvArgs a, uint
             o += out_row_words;
         };
         int ra[12], rb[12], rc[12];
-        uint32_t q0, q1, q2, s0, s1, s2, t0, t1, t2, u0, u1, u2;
         int left = i1 - i0;                                         // output rows still to produce
-        // rows needed beyond the prologue: stride 1 -> `left` more rows, stride 2 -> 2 * left; `avail` counts rows not yet requested
+#pragma unroll
+        for (int k = 0; k < DEPTH; ++k) issue();
+        // every take() is followed by one issue(): exactly DEPTH groups stay in flight, so wait_group<DEPTH-1> == "my row landed"
         if (S == 1) {
-            // prologue: all four first rows are requested before any of them is unpacked (one exposed latency, not three)
-            int avail = left;                                       // window rows beyond the first two: r+2 .. r+1+left
-            ld(t0, t1, t2); ld(u0, u1, u2);
-            ld(q0, q1, q2); --avail;                                // row for output 0
-            if (avail > 0) { ld(s0, s1, s2); --avail; }            // row for output 1 (two rows in flight from here on)
-            unpack(t0, t1, t2, ra); unpack(u0, u1, u2, rb);
+            take(ra); issue();
+            take(rb); issue();
             while (true) {
-                unpack(q0, q1, q2, rc); if (avail > 0) { ld(q0, q1, q2); --avail; } emit(ra, rb, rc); if (--left == 0) break;
-                unpack(s0, s1, s2, ra); if (avail > 0) { ld(s0, s1, s2); --avail; } emit(rb, rc, ra); if (--left == 0) break;
-                unpack(q0, q1, q2, rb); if (avail > 0) { ld(q0, q1, q2); --avail; } emit(rc, ra, rb); if (--left == 0) break;
-                unpack(s0, s1, s2, rc); if (avail > 0) { ld(s0, s1, s2); --avail; } emit(ra, rb, rc); if (--left == 0) break;
-                unpack(q0, q1, q2, ra); if (avail > 0) { ld(q0, q1, q2); --avail; } emit(rb, rc, ra); if (--left == 0) break;
-                unpack(s0, s1, s2, rb); if (avail > 0) { ld(s0, s1, s2); --avail; } emit(rc, ra, rb); if (--left == 0) break;
+                take(rc); issue(); emit(ra, rb, rc); if (--left == 0) break;
+                take(ra); issue(); emit(rb, rc, ra); if (--left == 0) break;
+                take(rb); issue(); emit(rc, ra, rb); if (--left == 0) break;
             }
         } else {
-            uint32_t v0, v1, v2;
-            int avail = left;                                       // pairs of rows not yet requested
-            ld(v0, v1, v2);
-            ld(q0, q1, q2); ld(s0, s1, s2); --avail;                // pair for output 0
-            if (avail > 0) { ld(t0, t1, t2); ld(u0, u1, u2); --avail; }   // pair for output 1
-            unpack(v0, v1, v2, ra);
+            take(ra); issue();
             while (true) {
-                unpack(q0, q1, q2, rb); unpack(s0, s1, s2, rc);
-                if (avail > 0) { ld(q0, q1, q2); ld(s0, s1, s2); --avail; }
-                emit(ra, rb, rc); if (--left == 0) break;
-                unpack(t0, t1, t2, rb); unpack(u0, u1, u2, ra);
-                if (avail > 0) { ld(t0, t1, t2); ld(u0, u1, u2); --avail; }
-                emit(rc, rb, ra); if (--left == 0) break;
+                take(rb); issue(); take(rc); issue(); emit(ra, rb, rc); if (--left == 0) break;
+                take(rb); issue(); take(ra); issue(); emit(rc, rb, ra); if (--left == 0) break;
             }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");      // drain before the ring is reused for the next sample
     }
 }
 
