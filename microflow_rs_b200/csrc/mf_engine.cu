@@ -221,7 +221,11 @@ cudaError_t LayerExec::run(const uint8_t *in, uint8_t *out, long long batch, int
             if (kernel == Kernel::ConvGeneric) return launch_conv_generic(a, s);
             if (kernel == Kernel::PwConvDp4a) return launch_pwconv_dp4a(a, s);
             if (kernel == Kernel::DwConvC4) return launch_dwconv_c4(a, s);
-            if (kernel == Kernel::DwConv3x3Rows) return launch_dwconv3x3_rows(a, s);
+            if (kernel == Kernel::DwConv3x3Rows) {
+                static const bool no_smem = std::getenv("MF_DW_NO_SMEM") != nullptr;
+                if (!no_smem && dwconv3x3_smem_eligible(a)) return launch_dwconv3x3_smem(a, num_sms, s);
+                return launch_dwconv3x3_rows(a, s);
+            }
             return launch_dwconv_cin1(a, s);
         }
         case Kernel::ConvTcPointwise: {

@@ -367,6 +367,172 @@ __global__ void __launch_bounds__(128, 4) dwconv3x3_rows_kernel(ConvArgs a, uint
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// depthwise 3x3, sample-resident variant (the fast path at large batch).
+// A sample's whole input tensor is contiguous in HBM (1-36 KB for every layer of person_detect), so ONE cp.async.bulk
+// (TMA 1-D bulk copy, mbarrier-tracked) brings it into shared memory; a ring of NB sample buffers per CTA keeps the next
+// samples in flight while the current one is computed.  Compute threads then issue no global loads and no address
+// arithmetic: one thread = one 4-channel word of one output column (x = j * G + g < OW * G), it walks down its row strip
+// with the 3x3 window unpacked in registers and reads 3 words per new input row from shared memory (neighbouring columns
+// are neighbouring words; image borders are the zero-point).  Stores are coalesced 128-byte rows.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDwSmemThreads = 192;
+
+__device__ __forceinline__ void sm_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+        if (done) break;
+        if (spins > (1u << 22)) __trap();
+    }
+}
+
+template <int S, int XU>
+__global__ void __launch_bounds__(kDwSmemThreads, 3) dwconv3x3_smem_kernel(ConvArgs a, uint32_t in_bytes, uint32_t buf_stride, int nbuf, int xw, int nstrip,
+                                                                         int rows_per_strip) {
+    extern __shared__ __align__(128) uint8_t dsm[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(dsm);                 // nbuf mbarriers (<= 8)
+    uint8_t *bufs = dsm + 128;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+    const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(bufs);
+    const int tid = threadIdx.x;
+    const long long first = blockIdx.x, step = gridDim.x;
+    if (tid == 0) {
+        for (int k = 0; k < nbuf; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * k), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto request = [&](long long b, int slot) {                         // thread 0 only
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * slot), "r"(in_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf0 + (uint32_t)slot * buf_stride),
+                     "l"(a.in + (size_t)b * in_bytes), "r"(in_bytes), "r"(bar0 + 8u * slot)
+                     : "memory");
+    };
+    if (tid == 0)
+        for (int k = 0; k < nbuf; ++k)
+            if (first + (long long)k * step < a.batch) request(first + (long long)k * step, k);
+
+    const int G = a.Cout >> 2;
+    const bool active = tid < xw * nstrip;
+    const int strip = active ? tid / xw : 0;
+    const int x = active ? tid - strip * xw : 0;
+    const int j = x / G, g = x - j * G;
+    const uint32_t *ww = reinterpret_cast<const uint32_t *>(a.w);
+    int wi[9][4];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const uint32_t wv = __ldg(ww + (size_t)k * G + g);
+        wi[k][0] = sx8<0>(wv); wi[k][1] = sx8<1>(wv); wi[k][2] = sx8<2>(wv); wi[k][3] = sx8<3>(wv);
+    }
+    const int4 kc = __ldg(reinterpret_cast<const int4 *>(a.kcorr) + g);
+    const float4 z = __ldg(reinterpret_cast<const float4 *>(a.c0z) + g);
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(a.c1) + g);
+    const uint32_t izw = (uint32_t)(a.in_zp & 0xff) * 0x01010101u;
+    const int c0 = S * j - a.off_c;
+    const bool cok0 = (unsigned)c0 < (unsigned)a.W, cok1 = (unsigned)(c0 + 1) < (unsigned)a.W, cok2 = (unsigned)(c0 + 2) < (unsigned)a.W;
+    const int i0 = strip * rows_per_strip;
+    const int i1 = active ? min(a.OH, i0 + rows_per_strip) : i0;
+    const int row_words = a.W * G, out_row_words = a.OW * G;
+    const int col_off = c0 * G + g;                                     // word offset of window column 0 inside an input row (may be < 0)
+    const float lo = a.lo, hi = a.hi;
+    const int H = a.H;
+    const int r_first = S * i0 - a.off_r;
+
+    uint32_t it = 0;
+    for (long long b = first; b < a.batch; b += step, ++it) {
+        const int slot = (int)(it % (uint32_t)nbuf);
+        sm_mbar_wait(bar0 + 8u * slot, (it / (uint32_t)nbuf) & 1u);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(bufs + (size_t)slot * buf_stride);
+        if (i1 > i0) {
+            uint32_t *o = reinterpret_cast<uint32_t *>(a.out) + ((size_t)b * a.OH + i0) * out_row_words + x;
+            int r = r_first;
+            const uint32_t *p = src + r * row_words + col_off;           // only dereferenced where the predicates allow
+            auto take = [&](int (&d)[12]) {                             // d[n * 4 + k] = channel k of window column n of input row r
+                const bool rok = (unsigned)r < (unsigned)H;
+                const uint32_t v0 = (rok && cok0) ? p[0] : izw;
+                const uint32_t v1 = (rok && cok1) ? p[G] : izw;
+                const uint32_t v2 = (rok && cok2) ? p[2 * G] : izw;
+                d[0] = sx8<0>(v0); d[1] = sx8<1>(v0); d[2] = sx8<2>(v0); d[3] = sx8<3>(v0);
+                d[4] = sx8<0>(v1); d[5] = sx8<1>(v1); d[6] = sx8<2>(v1); d[7] = sx8<3>(v1);
+                d[8] = sx8<0>(v2); d[9] = sx8<1>(v2); d[10] = sx8<2>(v2); d[11] = sx8<3>(v2);
+                p += row_words;
+                ++r;
+            };
+            auto emit = [&](const int (&r0)[12], const int (&r1)[12], const int (&r2)[12]) {
+                int acc[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int s = r0[k] * wi[0][k];
+                    s += r0[4 + k] * wi[1][k]; s += r0[8 + k] * wi[2][k];
+                    s += r1[k] * wi[3][k]; s += r1[4 + k] * wi[4][k]; s += r1[8 + k] * wi[5][k];
+                    s += r2[k] * wi[6][k]; s += r2[4 + k] * wi[7][k]; s += r2[8 + k] * wi[8][k];
+                    acc[k] = s;
+                }
+                *o = pack4(XU > 0 ? requant_xu<true>(acc[0] - kc.x, z.x, sc.x, lo, hi) : requant_nx<false>(acc[0] - kc.x, z.x, sc.x, lo, hi),
+                           XU > 1 ? requant_xu<true>(acc[1] - kc.y, z.y, sc.y, lo, hi) : requant_nx<false>(acc[1] - kc.y, z.y, sc.y, lo, hi),
+                           XU > 2 ? requant_xu<true>(acc[2] - kc.z, z.z, sc.z, lo, hi) : requant_nx<false>(acc[2] - kc.z, z.z, sc.z, lo, hi),
+                           XU > 3 ? requant_xu<true>(acc[3] - kc.w, z.w, sc.w, lo, hi) : requant_nx<false>(acc[3] - kc.w, z.w, sc.w, lo, hi));
+                o += out_row_words;
+            };
+            int ra[12], rb[12], rc[12];
+            int left = i1 - i0;
+            if (S == 1) {
+                take(ra); take(rb);
+                while (true) {
+                    take(rc); emit(ra, rb, rc); if (--left == 0) break;
+                    take(ra); emit(rb, rc, ra); if (--left == 0) break;
+                    take(rb); emit(rc, ra, rb); if (--left == 0) break;
+                }
+            } else {
+                take(ra);
+                while (true) {
+                    take(rb); take(rc); emit(ra, rb, rc); if (--left == 0) break;
+                    take(rb); take(ra); emit(rc, rb, ra); if (--left == 0) break;
+                }
+            }
+        }
+        __syncthreads();                                                 // every thread is done reading this buffer
+        if (tid == 0 && b + (long long)nbuf * step < a.batch) request(b + (long long)nbuf * step, slot);
+    }
+}
+
+// shapes the sample-resident kernel takes: 3x3, stride 1x1 / 2x2, one block spans the full output width, whole input fits a ring buffer
+bool dwconv3x3_smem_eligible(const ConvArgs &a) {
+    if (!(dwconv_c4_eligible(a) && a.KH == 3 && a.KW == 3 && a.sh == a.sw && (a.sh == 1 || a.sh == 2))) return false;
+    const long long in_bytes = (long long)a.H * a.W * a.Cin;
+    const int xw = a.OW * (a.Cout / 4);
+    return in_bytes % 16 == 0 && in_bytes <= 48 * 1024 && xw <= kDwSmemThreads && a.batch >= 148 * 2 && ((uintptr_t)a.in % 16) == 0;
+}
+cudaError_t launch_dwconv3x3_smem(const ConvArgs &a, int num_sms, cudaStream_t s) {
+    const uint32_t in_bytes = (uint32_t)(a.H * a.W * a.Cin);
+    const uint32_t buf_stride = (in_bytes + 127u) & ~127u;
+    const int xw = a.OW * (a.Cout / 4);
+    int nstrip = kDwSmemThreads / xw;
+    if (nstrip > a.OH) nstrip = a.OH;
+    const int rows = (a.OH + nstrip - 1) / nstrip;
+    nstrip = (a.OH + rows - 1) / rows;
+    int nbuf = in_bytes <= 12 * 1024 ? 4 : (in_bytes <= 24 * 1024 ? 3 : 2);
+    const size_t smem = 128 + (size_t)nbuf * buf_stride;
+    static const int env_xu = [] { const char *e = std::getenv("MF_DW_XU"); return e ? std::atoi(e) : -1; }();
+    int xu = env_xu >= 0 ? env_xu : 4;
+    if (!(a.lo == -128.f && a.hi == 127.f)) xu = 0;
+    xu = xu >= 4 ? 4 : 0;
+    using Fn = void (*)(ConvArgs, uint32_t, uint32_t, int, int, int, int);
+    Fn fn = a.sh == 1 ? (xu ? dwconv3x3_smem_kernel<1, 4> : dwconv3x3_smem_kernel<1, 0>) : (xu ? dwconv3x3_smem_kernel<2, 4> : dwconv3x3_smem_kernel<2, 0>);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 + 4 * 48 * 1024));
+    if (e != cudaSuccess) return e;
+    // persistent CTAs: as many as fit an SM (3 by registers / launch bounds, fewer if the sample ring is large); samples are
+    // taken grid-stride
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm > 3) per_sm = 3;
+    if (per_sm < 1) per_sm = 1;
+    long long ctas = (long long)num_sms * per_sm;
+    if (ctas > a.batch) ctas = a.batch;
+    fn<<<(unsigned)ctas, kDwSmemThreads, smem, s>>>(a, in_bytes, buf_stride, nbuf, xw, nstrip, rows);
+    return cudaGetLastError();
+}
+
 bool dwconv3x3_rows_eligible(const ConvArgs &a) {
     return dwconv_c4_eligible(a) && a.KH == 3 && a.KW == 3 && a.sh == a.sw && (a.sh == 1 || a.sh == 2);
 }

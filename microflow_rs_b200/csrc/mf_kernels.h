@@ -86,6 +86,8 @@ bool dwconv_c4_eligible(const ConvArgs &a);      // depthwise, Cin == Cout, C % 
 cudaError_t launch_dwconv_c4(const ConvArgs &a, cudaStream_t s);
 bool dwconv3x3_rows_eligible(const ConvArgs &a); // + 3x3, stride 1x1 or 2x2: sliding 3x3 window down a column strip
 cudaError_t launch_dwconv3x3_rows(const ConvArgs &a, cudaStream_t s);
+bool dwconv3x3_smem_eligible(const ConvArgs &a); // + whole sample staged in shared memory by cp.async.bulk (large batches)
+cudaError_t launch_dwconv3x3_smem(const ConvArgs &a, int num_sms, cudaStream_t s);
 bool dwconv_cin1_eligible(const ConvArgs &a);    // depthwise with Cin == 1 (depth multiplier), Cout % 4 == 0, Cout <= 16
 cudaError_t launch_dwconv_cin1(const ConvArgs &a, cudaStream_t s);
 bool pwconv_dp4a_eligible(const ConvArgs &a);    // 1x1 conv (any stride), Cin % 4 == 0, any Cout

@@ -155,7 +155,14 @@ FAST_SIMT_CASES = [
     (2, 24, 24, 32, 32, 3, 3, 2, 2, "same", "relu6", True, "dwconv3x3_rows"),       # stride 2 over several strips
     (2, 13, 11, 8, 8, 3, 3, 2, 2, "valid", "relu6", True, "dwconv3x3_rows"),
     (2, 17, 5, 4, 4, 3, 3, 1, 1, "same", "none", True, "dwconv3x3_rows"),
-    (2, 9, 9, 8, 8, 3, 3, 2, 1, "same", "none", True, "dwconv_c4"),                 # mixed strides stay on the generic-shape fast kernel
+    (2, 9, 9, 8, 8, 3, 3, 2, 1, "same", "none", True, "dwconv_c4"),
+    # batch >= 296 switches the 3x3 depthwise to the sample-resident (cp.async.bulk) kernel
+    (300, 12, 12, 8, 8, 3, 3, 1, 1, "same", "relu6", True, "dwconv3x3_rows"),
+    (300, 8, 8, 32, 32, 3, 3, 2, 2, "same", "relu6", True, "dwconv3x3_rows"),
+    (333, 6, 6, 128, 128, 3, 3, 1, 1, "same", "relu", True, "dwconv3x3_rows"),
+    (300, 9, 7, 16, 16, 3, 3, 1, 1, "valid", "none", True, "dwconv3x3_rows"),
+    (300, 11, 13, 8, 8, 3, 3, 2, 2, "valid", "relu6", True, "dwconv3x3_rows"),
+    (300, 3, 3, 256, 256, 3, 3, 1, 1, "same", "relu6", True, "dwconv3x3_rows"),                 # mixed strides stay on the generic-shape fast kernel
     (3, 1, 1, 256, 2, 1, 1, 1, 1, "same", "none", False, "pwconv_dp4a"),            # person_detect's last conv (Cout = 2)
     (2, 4, 4, 16, 7, 1, 1, 1, 1, "same", "relu", False, "pwconv_dp4a"),
     (3, 12, 12, 8, 16, 1, 1, 1, 1, "same", "relu6", False, "pwconv_dp4a|conv_tc"),   # person_detect layer 2 shape
