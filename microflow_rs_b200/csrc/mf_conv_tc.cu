@@ -60,6 +60,7 @@ struct ConvTcParams {
     long long num_tiles, OW, OH;
     float lo, hi;
     uint32_t idesc, stage_bytes, b_block_bytes, tmem_cols, nkb;
+    uint32_t out_stage_off;    // byte offset of the output staging buffers in dynamic smem (STAGE_OUT kernels)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -146,7 +147,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // ------------------------------------------------------------------------------------------------
 // KH_T/KW_T/CB_T != 0: compile-time loop bounds, so the single MMA-issuing thread spends ~3 scalar instructions per MMA
 // (descriptor = base + constant); XUG = how many of the 8 four-value groups of each 32-column chunk take the XU epilogue.
-template <bool BIG, int XUG, int KH_T, int KW_T, int CB_T>
+// STAGE_OUT: the int8 output tile goes through shared memory (padded rows, double buffered) and is written back with fully
+// coalesced 16-byte-per-lane stores (512 contiguous bytes per warp instruction) instead of one 32-byte piece per row.
+template <bool BIG, int XUG, int KH_T, int KW_T, int CB_T, bool STAGE_OUT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ ConvTcTables tab,
                const ConvTcParams p) {
@@ -154,7 +157,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if ((smem_u32(smem) & 1023u) != 0) __trap();   // SWIZZLE_128B atoms need a 1024-byte aligned base
     uint8_t *sB = smem;
     uint8_t *sA = sB + (size_t)p.nkb * p.b_block_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + (size_t)p.stages * p.stage_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + (size_t)p.stages * p.stage_bytes);   // 256 bytes reserved; staging buffers follow
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 5);
 
     const uint32_t bar0 = smem_u32(bars);
@@ -266,6 +269,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (p.ncls == 9) cls = 3 * (oy == 0 ? 0 : (oy == p.OH - 1 ? 2 : 1)) + (ox == 0 ? 0 : (ox == p.OW - 1 ? 2 : 1));
             const int32_t *corr = tab.corr + cls * p.N;
             uint8_t *orow = p.out + (((long long)b * p.OH + oy) * p.OW + ox) * p.N;
+            const int out_pitch = p.N + 16;                                   // +16 B: conflict-free STS.128 across rows
+            uint8_t *s_out = smem + p.out_stage_off + (size_t)(it & 1) * (128u * (uint32_t)out_pitch);
 
             mbar_wait(tfull_bar(acc), aph);
             tc_fence_after();
@@ -285,7 +290,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const int y3 = (g < XUG ? requant_xu<true>((int)r[4 * g + 3] - kc.w, z.w, sc.w, lo, hi) : requant_nx<BIG>((int)r[4 * g + 3] - kc.w, z.w, sc.w, lo, hi));
                     w[g] = pack4(y0, y1, y2, y3);
                 }
-                if (valid) {
+                if (STAGE_OUT) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(s_out + (size_t)row * out_pitch + c0);
+                    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                } else if (valid) {
                     uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
                     dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
                     dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
@@ -294,6 +303,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (STAGE_OUT) {
+                // all 16 epilogue warps have filled this tile's staging buffer -> cooperative, coalesced write-back.
+                // (pointwise tiles only: TH == 1, so the tile's 128 output rows are contiguous in global memory.)
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+                const int vec_per_row = p.N >> 4;
+                const long long row0 = (long long)tx * p.TW;
+                uint8_t *gbase = p.out + row0 * p.N;
+                const int rows_valid = (int)((p.OW - row0) < 128 ? (p.OW - row0) : 128);
+                for (int v = threadIdx.x; v < 128 * vec_per_row; v += 32 * kEpiWarps) {
+                    const int r = v / vec_per_row, cv = v - r * vec_per_row;
+                    if (r < rows_valid)
+                        *reinterpret_cast<uint4 *>(gbase + (size_t)v * 16) = *reinterpret_cast<const uint4 *>(s_out + (size_t)r * out_pitch + cv * 16);
+                }
+            }
         }
     }
 
@@ -343,10 +366,12 @@ bool encode_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *
     return true;
 }
 
+bool plan_stage_out(const ConvTcPlan &p) { return p.KH == 1 && p.KW == 1 && p.TH == 1; }
 size_t plan_smem(const ConvTcPlan &p, int stages) {
     const size_t b_bytes = (size_t)p.KH * p.KW * p.CB * p.N * 128;
     const size_t stage = (size_t)(p.TH + p.KH - 1) * p.TW * 128;
-    return b_bytes + stage * stages + (2 * kMaxStages + 5) * 8 + 16;
+    const size_t out_stage = plan_stage_out(p) ? 2 * 128 * (size_t)(p.N + 16) : 0;
+    return b_bytes + stage * stages + 256 + out_stage;
 }
 
 }  // namespace
@@ -472,6 +497,7 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     k.stage_bytes = (uint32_t)((p.TH + p.KH - 1) * p.TW * 128);
     k.b_block_bytes = (uint32_t)(p.N * 128);
     k.nkb = (uint32_t)(p.KH * p.KW * p.CB);
+    k.out_stage_off = (uint32_t)((size_t)p.KH * p.KW * p.CB * p.N * 128 + (size_t)p.stages * k.stage_bytes + 256);
     k.tmem_cols = 2 * p.N <= 32 ? 32 : (2 * p.N <= 64 ? 64 : (2 * p.N <= 128 ? 128 : (2 * p.N <= 256 ? 256 : 512)));
     if (k.num_tiles <= 0) return cudaSuccess;
 
@@ -484,12 +510,14 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     const int shape = (p.KH == 3 && p.KW == 3 && p.CB == 1) ? 1 : ((p.KH == 1 && p.KW == 1 && p.CB == 1) ? 2 : ((p.KH == 1 && p.KW == 1 && p.CB == 2) ? 3 : 0));
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const ConvTcTables, const ConvTcParams);
     KernelFn fn = nullptr;
+    static const bool no_stage = std::getenv("MF_TC_NO_STAGE") != nullptr;
+    const bool stage_out = plan_stage_out(p) && !no_stage && shape >= 2;
 #define MF_TC_PICK(BIGV, XUV)                                                                               \
     switch (shape) {                                                                                        \
-        case 1: fn = conv_tc_kernel<BIGV, XUV, 3, 3, 1>; break;                                             \
-        case 2: fn = conv_tc_kernel<BIGV, XUV, 1, 1, 1>; break;                                             \
-        case 3: fn = conv_tc_kernel<BIGV, XUV, 1, 1, 2>; break;                                             \
-        default: fn = conv_tc_kernel<BIGV, XUV, 0, 0, 0>; break;                                            \
+        case 1: fn = conv_tc_kernel<BIGV, XUV, 3, 3, 1, false>; break;                                      \
+        case 2: fn = stage_out ? conv_tc_kernel<BIGV, XUV, 1, 1, 1, true> : conv_tc_kernel<BIGV, XUV, 1, 1, 1, false>; break; \
+        case 3: fn = stage_out ? conv_tc_kernel<BIGV, XUV, 1, 1, 2, true> : conv_tc_kernel<BIGV, XUV, 1, 1, 2, false>; break; \
+        default: fn = conv_tc_kernel<BIGV, XUV, 0, 0, 0, false>; break;                                     \
     }
     if (p.big_acc) {
         if (xug == 8) { MF_TC_PICK(true, 8) } else if (xug == 5) { MF_TC_PICK(true, 5) } else { MF_TC_PICK(true, 0) }

@@ -23,7 +23,7 @@ fi
 if has prof; then
   timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-conv2d > gpurun_out/ncu_bench.log 2>&1
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:dwconv3x3_rows -s 26 -c 2 -f -o gpurun_out/prof_dw \
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:dwconv3x3 -s 26 -c 2 -f -o gpurun_out/prof_dw \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-conv2d > gpurun_out/ncu_dw.log 2>&1
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 28 -c 3 -f -o gpurun_out/prof_tc_pw \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-conv2d > gpurun_out/ncu_tc.log 2>&1
