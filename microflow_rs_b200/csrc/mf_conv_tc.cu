@@ -510,8 +510,10 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     const int shape = (p.KH == 3 && p.KW == 3 && p.CB == 1) ? 1 : ((p.KH == 1 && p.KW == 1 && p.CB == 1) ? 2 : ((p.KH == 1 && p.KW == 1 && p.CB == 2) ? 3 : 0));
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const ConvTcTables, const ConvTcParams);
     KernelFn fn = nullptr;
-    static const bool no_stage = std::getenv("MF_TC_NO_STAGE") != nullptr;
-    const bool stage_out = plan_stage_out(p) && !no_stage && shape >= 2;
+    // measured on B200 (gpurun session 10): staging + one extra barrier per tile is SLOWER than the direct 32-byte-per-row stores
+    // (pointwise layers 0.91 vs 0.79 ms per 8192-sample step), so it is opt-in
+    static const bool want_stage = std::getenv("MF_TC_STAGE") != nullptr;
+    const bool stage_out = plan_stage_out(p) && want_stage && shape >= 2;
 #define MF_TC_PICK(BIGV, XUV)                                                                               \
     switch (shape) {                                                                                        \
         case 1: fn = conv_tc_kernel<BIGV, XUV, 3, 3, 1, false>; break;                                      \

@@ -76,3 +76,10 @@ print('value %.4g' % d['value'], {k: round(v['ms_per_step'],3) for k,v in d['ker
   done; done
   cat gpurun_out/exp.txt
 fi
+if has layers; then
+  timeout 300 python tools/layer_bench.py 8192 > gpurun_out/layer_bench.txt 2>&1
+  MF_DW_NO_SMEM=1 timeout 200 python tools/layer_bench.py 8192 L1_dw8,L5_dw32,L13_dw128 >> gpurun_out/layer_bench.txt 2>&1
+  MF_TC_XUG=0 timeout 200 python tools/layer_bench.py 8192 L2_pw8_16,L6_pw32_32,L14_pw128 >> gpurun_out/layer_bench.txt 2>&1
+  MF_TC_XUG=5 timeout 200 python tools/layer_bench.py 8192 L2_pw8_16,L6_pw32_32,L14_pw128 >> gpurun_out/layer_bench.txt 2>&1
+  cat gpurun_out/layer_bench.txt
+fi
