@@ -157,7 +157,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if ((smem_u32(smem) & 1023u) != 0) __trap();   // SWIZZLE_128B atoms need a 1024-byte aligned base
     uint8_t *sB = smem;
     uint8_t *sA = sB + (size_t)p.nkb * p.b_block_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + (size_t)p.stages * p.stage_bytes);   // 256 bytes reserved; staging buffers follow
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + (size_t)p.stages * p.stage_bytes);   // 256 bytes reserved
+    // epilogue tables: copied once per CTA from the parameter (constant) bank into shared memory -- register-indexed LDC in the
+    // hot loop stalls on the MIO queue (ncu, profiles/), broadcast LDS.128 does not
+    float *s_c0z = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(bars) + 256);
+    float *s_c1 = s_c0z + p.N;
+    int32_t *s_corr = reinterpret_cast<int32_t *>(s_c1 + p.N);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 5);
 
     const uint32_t bar0 = smem_u32(bars);
@@ -184,6 +189,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == kWarpAlloc) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp < kEpiWarps) {
+        for (int k = threadIdx.x; k < p.N; k += 32 * kEpiWarps) { s_c0z[k] = tab.c0z[k]; s_c1[k] = tab.c1[k]; }
+        for (int k = threadIdx.x; k < p.ncls * p.N; k += 32 * kEpiWarps) s_corr[k] = tab.corr[k];
     }
     tc_fence_before();
     __syncthreads();
@@ -267,7 +276,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const bool valid = oy < p.OH && ox < p.OW;
             int cls = 0;
             if (p.ncls == 9) cls = 3 * (oy == 0 ? 0 : (oy == p.OH - 1 ? 2 : 1)) + (ox == 0 ? 0 : (ox == p.OW - 1 ? 2 : 1));
-            const int32_t *corr = tab.corr + cls * p.N;
+            const int32_t *corr = s_corr + cls * p.N;
             uint8_t *orow = p.out + (((long long)b * p.OH + oy) * p.OW + ox) * p.N;
             const int out_pitch = p.N + 16;                                   // +16 B: conflict-free STS.128 across rows
             uint8_t *s_out = smem + p.out_stage_off + (size_t)(it & 1) * (128u * (uint32_t)out_pitch);
@@ -281,8 +290,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 uint32_t w[8];
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
-                    const float4 z = *reinterpret_cast<const float4 *>(tab.c0z + c0 + 4 * g);
-                    const float4 sc = *reinterpret_cast<const float4 *>(tab.c1 + c0 + 4 * g);
+                    const float4 z = *reinterpret_cast<const float4 *>(s_c0z + c0 + 4 * g);
+                    const float4 sc = *reinterpret_cast<const float4 *>(s_c1 + c0 + 4 * g);
                     const int4 kc = *reinterpret_cast<const int4 *>(corr + c0 + 4 * g);
                     const int y0 = (g < XUG ? requant_xu<true>((int)r[4 * g + 0] - kc.x, z.x, sc.x, lo, hi) : requant_nx<BIG>((int)r[4 * g + 0] - kc.x, z.x, sc.x, lo, hi));
                     const int y1 = (g < XUG ? requant_xu<true>((int)r[4 * g + 1] - kc.y, z.y, sc.y, lo, hi) : requant_nx<BIG>((int)r[4 * g + 1] - kc.y, z.y, sc.y, lo, hi));
@@ -366,12 +375,16 @@ bool encode_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *
     return true;
 }
 
-bool plan_stage_out(const ConvTcPlan &p) { return p.KH == 1 && p.KW == 1 && p.TH == 1; }
+bool plan_stage_out(const ConvTcPlan &p) {
+    static const bool want_stage = std::getenv("MF_TC_STAGE") != nullptr;   // opt-in: measured slower than direct stores (session 10)
+    return want_stage && p.KH == 1 && p.KW == 1 && p.TH == 1;
+}
 size_t plan_smem(const ConvTcPlan &p, int stages) {
     const size_t b_bytes = (size_t)p.KH * p.KW * p.CB * p.N * 128;
     const size_t stage = (size_t)(p.TH + p.KH - 1) * p.TW * 128;
     const size_t out_stage = plan_stage_out(p) ? 2 * 128 * (size_t)(p.N + 16) : 0;
-    return b_bytes + stage * stages + 256 + out_stage;
+    const size_t tables = (size_t)p.N * 8 + (size_t)p.ncls * p.N * 4;
+    return b_bytes + stage * stages + 256 + tables + out_stage;
 }
 
 }  // namespace
@@ -497,7 +510,7 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     k.stage_bytes = (uint32_t)((p.TH + p.KH - 1) * p.TW * 128);
     k.b_block_bytes = (uint32_t)(p.N * 128);
     k.nkb = (uint32_t)(p.KH * p.KW * p.CB);
-    k.out_stage_off = (uint32_t)((size_t)p.KH * p.KW * p.CB * p.N * 128 + (size_t)p.stages * k.stage_bytes + 256);
+    k.out_stage_off = (uint32_t)((size_t)p.KH * p.KW * p.CB * p.N * 128 + (size_t)p.stages * k.stage_bytes + 256 + (size_t)p.N * 8 + (size_t)p.ncls * p.N * 4);
     k.tmem_cols = 2 * p.N <= 32 ? 32 : (2 * p.N <= 64 ? 64 : (2 * p.N <= 128 ? 128 : (2 * p.N <= 256 ? 256 : 512)));
     if (k.num_tiles <= 0) return cudaSuccess;
 
@@ -512,8 +525,7 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     KernelFn fn = nullptr;
     // measured on B200 (gpurun session 10): staging + one extra barrier per tile is SLOWER than the direct 32-byte-per-row stores
     // (pointwise layers 0.91 vs 0.79 ms per 8192-sample step), so it is opt-in
-    static const bool want_stage = std::getenv("MF_TC_STAGE") != nullptr;
-    const bool stage_out = plan_stage_out(p) && want_stage && shape >= 2;
+    const bool stage_out = plan_stage_out(p) && shape >= 2;
 #define MF_TC_PICK(BIGV, XUV)                                                                               \
     switch (shape) {                                                                                        \
         case 1: fn = conv_tc_kernel<BIGV, XUV, 3, 3, 1, false>; break;                                      \

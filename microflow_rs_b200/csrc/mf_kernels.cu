@@ -195,8 +195,15 @@ cudaError_t launch_dequantize(const uint8_t *in, float *out, size_t n, float sca
 // FAST kernels.  Grid: blockIdx.y = sample (grid-stride), blockIdx.x * blockDim.x + threadIdx.x = 32-bit index inside
 // the sample, decoded with FastDiv (no 64-bit div/mod on the device).
 // ================================================================================================
+// gridDim.y is capped so that the launch is ~16 CTAs per SM: every CTA then loops over many samples and its prologue
+// (weights to registers / shared memory, index decode, epilogue constants) is paid once, not once per sample
 static inline dim3 grid2(long long per_sample, int block, long long batch) {
-    return dim3((unsigned)((per_sample + block - 1) / block), (unsigned)(batch < 65535 ? batch : 65535), 1);
+    const long long gx = (per_sample + block - 1) / block;
+    long long gy = (148ll * 16 + gx - 1) / gx;
+    if (gy > batch) gy = batch;
+    if (gy > 65535) gy = 65535;
+    if (gy < 1) gy = 1;
+    return dim3((unsigned)gx, (unsigned)gy, 1);
 }
 
 // ------------------------------------------------------------------------------------------------

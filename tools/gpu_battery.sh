@@ -83,3 +83,12 @@ if has layers; then
   MF_TC_XUG=5 timeout 200 python tools/layer_bench.py 8192 L2_pw8_16,L6_pw32_32,L14_pw128 >> gpurun_out/layer_bench.txt 2>&1
   cat gpurun_out/layer_bench.txt
 fi
+if has prof2; then
+  timeout 300 ncu --set full --clock-control none --cache-control none --import-source on -k regex:conv_tc -s 10 -c 1 -f -o gpurun_out/prof_pw_nc \
+      python tools/layer_bench.py 8192 L2_pw8_16 > gpurun_out/ncu_pw_nc.log 2>&1
+  timeout 300 ncu --set full --clock-control none --cache-control none --import-source on -k regex:dwconv3x3_smem -s 10 -c 1 -f -o gpurun_out/prof_dw_nc \
+      python tools/layer_bench.py 8192 L1_dw8 > gpurun_out/ncu_dw_nc.log 2>&1
+  timeout 300 ncu --set full --clock-control none --cache-control none --import-source on -k regex:cin1 -s 10 -c 1 -f -o gpurun_out/prof_cin1_nc \
+      python tools/layer_bench.py 8192 L0_dw_cin1 > gpurun_out/ncu_cin1_nc.log 2>&1
+  tail -n 2 gpurun_out/ncu_pw_nc.log gpurun_out/ncu_dw_nc.log gpurun_out/ncu_cin1_nc.log
+fi
