@@ -325,7 +325,7 @@ def main():
             "config": {"workload": f"{wl}.tflite int8, batch {batch} per GPU (BASELINE configs[2])" if wl == "person_detect" else f"{wl}.tflite int8, batch {batch} per GPU",
                        "global_batch": batch * world, "parallelism": f"dp{world} (independent samples, contiguous shards, one NCCL weight broadcast at init)",
                        "l2": f"inputs rotate over {R} device batches ({R * batch * ie / 1e6:.0f} MB > 126 MB L2)", "chunk": args.chunk or 8192},
-            "e2e": {"value": e2e_val, "unit": "inferences/s", "h2d_bytes_per_step": batch * ie, "d2h_bytes_per_step": batch * oe * 4,
+            "e2e": {"value": e2e_val, "unit": "inferences/s", "h2d_bytes_per_step": world * batch * ie, "d2h_bytes_per_step": world * batch * oe * 4,
                     "api": "mf_predict_many_quantized (pinned host buffers)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "layers": [{"i": i, "op": L["op"], "kernel": L["kernel"], "us_per_step": round(1e3 * float(t) / args.steps, 2),
