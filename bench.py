@@ -274,23 +274,33 @@ def main():
     ms = float(t.item())
     value = world * batch * args.steps / (ms * 1e-3)
 
-    # ---- e2e through the public C-ABI with HOST buffers (H2D of the inputs and D2H of the result inside the timed region)
-    host_out = mf.PinnedBuffer((batch, oe), np.float32)
+    # ---- e2e through the public C-ABI with HOST buffers (H2D of the inputs and D2H of the result inside the timed region).
+    # `e2e.value`: K back-to-back mf_predict_many_quantized_async calls + one mf_model_synchronize (the H2D of call k+1 overlaps
+    # the kernels of call k; every step still copies its own inputs in and its own results out).  `e2e.blocking`: the same K
+    # steps through the blocking mf_predict_many_quantized (each call returns only after its results are on the host).
+    host_out = [mf.PinnedBuffer((batch, oe), np.float32) for _ in range(2)]
     for i in range(3):
-        m.predict_many_quantized(host_in[i % len(host_in)].array, out=host_out.array)
+        m.predict_many_quantized(host_in[i % len(host_in)].array, out=host_out[i & 1].array)
     barrier()
     sampler.window(True)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        m.predict_many_quantized(host_in[i % len(host_in)].array, out=host_out.array)
+        m.predict_many_quantized(host_in[i % len(host_in)].array, out=host_out[i & 1].array)
     torch.cuda.synchronize()
+    e2e_block_s = time.perf_counter() - t0
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        m.predict_many_quantized_async(host_in[i % len(host_in)].array, host_out[i & 1].array)
+    m.synchronize()
     e2e_s = time.perf_counter() - t0
     sampler.window(False)
     clocks = sampler.stop()
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    t = torch.tensor([e2e_s, e2e_block_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * batch * args.steps / float(t.item())
+    e2e_val = world * batch * args.steps / float(t[0].item())
+    e2e_block_val = world * batch * args.steps / float(t[1].item())
 
     if rank == 0:
         # ---- roofline of the dominant kernel: group layers by kernel, take the largest share of the step
@@ -326,7 +336,7 @@ def main():
                        "global_batch": batch * world, "parallelism": f"dp{world} (independent samples, contiguous shards, one NCCL weight broadcast at init)",
                        "l2": f"inputs rotate over {R} device batches ({R * batch * ie / 1e6:.0f} MB > 126 MB L2)", "chunk": args.chunk or 8192},
             "e2e": {"value": e2e_val, "unit": "inferences/s", "h2d_bytes_per_step": world * batch * ie, "d2h_bytes_per_step": world * batch * oe * 4,
-                    "api": "mf_predict_many_quantized (pinned host buffers)"},
+                    "api": "mf_predict_many_quantized_async x K + mf_model_synchronize (pinned host buffers)", "blocking": e2e_block_val},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "layers": [{"i": i, "op": L["op"], "kernel": L["kernel"], "us_per_step": round(1e3 * float(t) / args.steps, 2),
                         "GBps": round((L["bytes"] - L["weight_bytes"]) * batch * args.steps / (float(t) * 1e-3) / 1e9, 1) if t > 0 else None}

@@ -133,6 +133,9 @@ int mf_predict_quantized(mf_model *m, const void *in_q, float *out_f32);
 /* host buffers (pinned or pageable); H2D / compute / D2H are pipelined in chunks inside the call */
 int mf_predict_many(mf_model *m, const float *in_f32, size_t n, float *out_f32);
 int mf_predict_many_quantized(mf_model *m, const void *in_q, size_t n, float *out_f32);
+/* same, but returns as soon as the copies and kernels are enqueued; the host buffers must be PINNED (mf_host_alloc) and stay
+ * valid until mf_model_synchronize().  Back-to-back calls pipeline: the H2D of call k+1 overlaps the kernels of call k. */
+int mf_predict_many_quantized_async(mf_model *m, const void *in_q, size_t n, float *out_f32);
 /* strict-parity variant: final quantized output (out_q, out_elems bytes/sample) and, optionally, the input of
  * the trailing softmax ("logits", may be NULL) */
 int mf_predict_many_logits(mf_model *m, const void *in_q, size_t n, void *out_q, void *logits_q);

@@ -85,7 +85,7 @@ class _PoolDesc(C.Structure):
 ABI_SYMBOLS = [
     "mf_abi_version", "mf_last_error", "mf_status_string", "mf_device_count", "mf_model_create_from_tflite", "mf_model_create_from_file",
     "mf_model_destroy", "mf_model_io_info", "mf_model_num_layers", "mf_model_layer_info", "mf_model_layer_constants", "mf_model_dump",
-    "mf_predict", "mf_predict_quantized", "mf_predict_many", "mf_predict_many_quantized", "mf_predict_many_logits", "mf_predict_many_device",
+    "mf_predict", "mf_predict_quantized", "mf_predict_many", "mf_predict_many_quantized", "mf_predict_many_quantized_async", "mf_predict_many_logits", "mf_predict_many_device",
     "mf_predict_trace", "mf_model_synchronize", "mf_model_set_profiling", "mf_model_layer_times_ms", "mf_model_launch_count", "mf_model_blob",
     "mf_host_alloc", "mf_host_free", "mf_op_conv_2d", "mf_op_conv_2d_create", "mf_op_run_device", "mf_op_kernel_name", "mf_op_destroy", "mf_op_fully_connected", "mf_op_average_pool_2d", "mf_op_softmax", "mf_op_quantize",
     "mf_op_dequantize",
@@ -124,6 +124,7 @@ def lib():
         L.mf_predict_quantized.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mf_predict_many.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.mf_predict_many_quantized.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.mf_predict_many_quantized_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.mf_predict_many_logits.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.mf_predict_many_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mf_predict_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -287,6 +288,11 @@ class Model:
         out = np.zeros((n, self.out_elems), np.float32) if out is None else out
         _check(lib().mf_predict_many_quantized(self._h, xs.ctypes.data, n, out.ctypes.data))
         return out
+
+    def predict_many_quantized_async(self, xs_pinned, out_pinned):
+        """Enqueue only (pinned numpy views from PinnedBuffer); call synchronize() before reading `out_pinned`."""
+        n = xs_pinned.size // self.in_elems
+        _check(lib().mf_predict_many_quantized_async(self._h, xs_pinned.ctypes.data, n, out_pinned.ctypes.data))
 
     def predict_many_logits(self, xs, want_logits=True):
         """Returns (final quantized output [n, out_elems], pre-softmax int8 logits or None)."""

@@ -59,6 +59,7 @@ struct mf_model {
     size_t prof_chunks = 0;
     uint64_t launches = 0;
     int softmax_tail = -1;                  // index of a trailing softmax layer (its input = "logits")
+    size_t slot_rr = 0;                     // round-robin position of the host-path stream slots
     std::mutex mu;
 };
 
@@ -138,7 +139,7 @@ int need_device(const mf_model *m) {
 }
 
 // host-buffer batched path: chunks alternate between two streams so H2D(c+1) overlaps compute(c) and D2H(c-1)
-int predict_many_host(mf_model *m, const void *in_q, const float *in_f32, size_t n, float *out_f32, void *out_q, void *logits) {
+int predict_many_host(mf_model *m, const void *in_q, const float *in_f32, size_t n, float *out_f32, void *out_q, void *logits, bool wait = true) {
     int rc = need_device(m);
     if (rc) return rc;
     if ((!in_q && !in_f32) || (!out_f32 && !out_q)) return fail(MF_ERR_INVALID_ARG, "null input or output buffer");
@@ -151,7 +152,7 @@ int predict_many_host(mf_model *m, const void *in_q, const float *in_f32, size_t
     // to keep the per-launch fixed costs amortised
     size_t piece = std::min(m->chunk, std::max<size_t>(1024, (n + 1) / 2));
     if (piece > 4096) piece = 4096;
-    size_t ci = 0;
+    size_t ci = m->slot_rr;
     for (size_t off = 0; off < n; off += piece, ++ci) {
         Slot &s = m->slot[ci & 1];
         const size_t cn = std::min(piece, n - off);
@@ -169,8 +170,11 @@ int predict_many_host(mf_model *m, const void *in_q, const float *in_f32, size_t
         if (out_q) MF_CUDA(cudaMemcpyAsync((uint8_t *)out_q + off * oe, s.out_q, cn * oe, cudaMemcpyDeviceToHost, s.stream));
         if (logits) MF_CUDA(cudaMemcpyAsync((uint8_t *)logits + off * le, s.logits, cn * le, cudaMemcpyDeviceToHost, s.stream));
     }
-    MF_CUDA(cudaStreamSynchronize(m->slot[0].stream));
-    MF_CUDA(cudaStreamSynchronize(m->slot[1].stream));
+    m->slot_rr = ci;                                   // the next call continues the slot rotation (pipelining across async calls)
+    if (wait) {
+        MF_CUDA(cudaStreamSynchronize(m->slot[0].stream));
+        MF_CUDA(cudaStreamSynchronize(m->slot[1].stream));
+    }
     return MF_OK;
 }
 
@@ -367,6 +371,9 @@ int mf_predict(mf_model *m, const float *in, float *out) { return predict_many_h
 int mf_predict_quantized(mf_model *m, const void *in_q, float *out) { return predict_many_host(m, in_q, nullptr, 1, out, nullptr, nullptr); }
 int mf_predict_many(mf_model *m, const float *in, size_t n, float *out) { return predict_many_host(m, nullptr, in, n, out, nullptr, nullptr); }
 int mf_predict_many_quantized(mf_model *m, const void *in_q, size_t n, float *out) { return predict_many_host(m, in_q, nullptr, n, out, nullptr, nullptr); }
+int mf_predict_many_quantized_async(mf_model *m, const void *in_q, size_t n, float *out) {
+    return predict_many_host(m, in_q, nullptr, n, out, nullptr, nullptr, /*wait=*/false);
+}
 int mf_predict_many_logits(mf_model *m, const void *in_q, size_t n, void *out_q, void *logits_q) {
     if (!out_q) return fail(MF_ERR_INVALID_ARG, "null out_q");
     return predict_many_host(m, in_q, nullptr, n, nullptr, out_q, logits_q);

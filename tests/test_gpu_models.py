@@ -124,3 +124,20 @@ def test_device_resident_api(gpu_models, ora):
     want_f, want_q = o.predict_many_quantized(xs, threads=oracle.max_threads())
     np.testing.assert_array_equal(d_out.cpu().numpy(), want_f)
     np.testing.assert_array_equal(d_q.cpu().numpy(), want_q)
+
+
+def test_async_predict_many_pipelines_and_matches_blocking(gpu_models, ora):
+    """mf_predict_many_quantized_async: several enqueued calls on pinned buffers, one synchronize, same bits as the blocking call."""
+    m, o = gpu_models["person_detect"], ora["person_detect"]
+    n = 700
+    ins = [mf.PinnedBuffer((n, o.in_elems), np.int8) for _ in range(3)]
+    outs = [mf.PinnedBuffer((n, o.out_elems), np.float32) for _ in range(3)]
+    for k, b in enumerate(ins):
+        b.array[:] = splitmix_bytes(0x5EED0100 + k, n * o.in_elems).reshape(n, -1)
+    for k in range(3):
+        m.predict_many_quantized_async(ins[k].array, outs[k].array)
+    m.synchronize()
+    for k in range(3):
+        np.testing.assert_array_equal(outs[k].array, m.predict_many_quantized(ins[k].array))
+    want, _ = o.predict_many_quantized(ins[1].array[:64], threads=oracle.max_threads())
+    np.testing.assert_array_equal(outs[1].array[:64], want)
