@@ -325,6 +325,7 @@ def main():
                 traffic = None
         roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                     "traffic": traffic, "peak_source": peak_src, "share_of_step": dom["ms"] / total_layer_ms,
+                    "traffic_note": "traffic = dram__bytes_read+write of ONE captured launch of this kernel (profiles/traffic_latest.json says which layer and its algorithmic bytes); achieved aggregates all layers that run on this kernel",
                     "note": "achieved = algorithmic bytes (layer input+output per sample x batch + weights once per launch) of this kernel's layers / its summed "
                             "CUDA-event time inside the timed region"}
         kernels = {k: {"ms_per_step": g["ms"] / args.steps, "share": g["ms"] / total_layer_ms, "GBps": g["bytes"] / (g["ms"] * 1e-3) / 1e9 if g["ms"] > 0 else None,
