@@ -19,6 +19,7 @@ const char *kernel_name(Kernel k) {
         case Kernel::DwConvCin1: return "dwconv_cin1_kernel";
         case Kernel::FcGeneric: return "fc_generic_kernel";
         case Kernel::FcWarp: return "fc_warp_kernel";
+        case Kernel::FcTc: return "conv_tc_kernel(fc)";
         case Kernel::PoolGeneric: return "pool_generic_kernel";
         case Kernel::Softmax: return "softmax_kernel";
     }
@@ -149,7 +150,30 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
         weight_bytes = L.w.size() + (size_t)L.Cout * 8;
         alg_bytes += weight_bytes;
         kernel = Kernel::FcGeneric;
-        if (impl != 1 && !L.is_u8 && L.Cin % 16 == 0 && L.Cout <= 8) kernel = Kernel::FcWarp;
+        if (impl == 1) return;
+        if (!L.is_u8 && L.Cin % 16 == 0 && L.Cout <= 8) { kernel = Kernel::FcWarp; return; }
+        // FullyConnected as the same tcgen05 GEMM as the pointwise convs: row = one sample (K bytes, K % 128 == 0), B = W [N][K].
+        // With w_zp == 0 the reference's accumulator x.W - w_zp*rowsum - c2[j] + c3 (fully_connected.rs:71) is acc - c2[j]
+        // (c3 = K*in_zp*w_zp = 0), i.e. exactly the conv epilogue with kcorr = c2; c1 is per-tensor and replicated.
+        if (impl == 0 && have_device && !L.is_u8 && L.w_zp[0] == 0 && L.c3 == 0 && L.Cin % 128 == 0 && L.Cout % 32 == 0 && L.Cout <= 256) {
+            long long big = 0;
+            for (int j = 0; j < L.Cout; ++j) {
+                long long sa = 0;
+                for (int k = 0; k < L.Cin; ++k) sa += std::abs(elem_i(L.w[(size_t)j * L.Cin + k], false));
+                big = std::max(big, sa * 128 + std::llabs((long long)L.c2[(size_t)j]));
+            }
+            big_acc = big > (1ll << 22);
+            tc = ConvTcPlan{};
+            tc_P = 1;
+            tc.P = 1; tc.N = L.Cout; tc.Cout = L.Cout; tc.C = L.Cin; tc.CB = L.Cin / 128;
+            tc.KH = tc.KW = 1; tc.TW = 128; tc.TH = 1; tc.off_r = tc.off_c = 0; tc.ncls = 1;
+            tc.lo = (float)L.act_lo; tc.hi = (float)L.act_hi; tc.big_acc = big_acc;
+            tc.h_c0z = c0z;
+            tc.h_c1.assign((size_t)L.Cout, L.c1[0]);
+            tc.h_corr = L.c2;
+            o_tc_w = o_w;   // TFLite [N][K] bytes are already the K-major B matrix
+            kernel = Kernel::FcTc;
+        }
         return;
     }
     if (L.op == MF_OP_AVERAGE_POOL_2D) { kernel = Kernel::PoolGeneric; return; }
@@ -192,6 +216,11 @@ bool LayerExec::resolve(const uint8_t *d, std::string *err) {
         a.c2 = reinterpret_cast<const int32_t *>(at(o_c2));
         a.c1 = L.c1[0]; a.c3 = L.c3; a.w_zp = L.w_zp[0]; a.K = L.Cin; a.N = L.Cout;
         a.lo = (float)L.act_lo; a.hi = (float)L.act_hi; a.is_u8 = L.is_u8;
+        if (kernel == Kernel::FcTc) {
+            tc.d_wmat = at(o_tc_w);
+            std::string why;
+            if (!conv_tc_finalize_plan(tc, &why)) { why_not_fast = "tensor core plan rejected: " + why; kernel = Kernel::FcGeneric; }
+        }
     } else if (L.op == MF_OP_AVERAGE_POOL_2D) {
         PoolArgs &a = pool;
         a = PoolArgs{};
@@ -226,6 +255,10 @@ cudaError_t LayerExec::run(const uint8_t *in, uint8_t *out, long long batch, int
                 if (!no_smem && dwconv3x3_smem_eligible(a)) return launch_dwconv3x3_smem(a, num_sms, s);
                 return launch_dwconv3x3_rows(a, s);
             }
+            {
+                static const bool no_smem = std::getenv("MF_DW_NO_SMEM") != nullptr;
+                if (!no_smem && dwconv_cin1_smem_eligible(a)) return launch_dwconv_cin1_smem(a, num_sms, s);
+            }
             return launch_dwconv_cin1(a, s);
         }
         case Kernel::ConvTcPointwise: {
@@ -239,6 +272,12 @@ cudaError_t LayerExec::run(const uint8_t *in, uint8_t *out, long long batch, int
             ConvTcLaunch l;
             l.in = in; l.out = out;
             l.W = l.OW = spec.W; l.H = l.OH = spec.H; l.B = batch;
+            return conv_tc_launch(tc, l, num_sms, s, err);
+        }
+        case Kernel::FcTc: {
+            ConvTcLaunch l;
+            l.in = in; l.out = out;
+            l.W = l.OW = batch; l.H = l.OH = 1; l.B = 1;
             return conv_tc_launch(tc, l, num_sms, s, err);
         }
         case Kernel::FcGeneric: case Kernel::FcWarp: {

@@ -22,6 +22,7 @@ enum class Kernel {
     DwConvCin1,
     FcGeneric,
     FcWarp,
+    FcTc,             // tcgen05 GEMM: [batch x K] x [N x K]^T (w_zp == 0, K % 128 == 0, N % 32 == 0)
     PoolGeneric,
     Softmax,
 };

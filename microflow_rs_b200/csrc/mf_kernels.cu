@@ -623,6 +623,116 @@ __global__ void __launch_bounds__(128) dwconv_cin1_kernel(ConvArgs a, uint32_t p
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cin == 1 depthwise 3x3 (person_detect layer 0), sample-resident variant: the 9 KB input image is brought into shared
+// memory by one cp.async.bulk per sample (ring of 4), one thread = one output column of a row strip, all COUT channels,
+// the 9 x COUT sign-extended weights live in registers, activations arrive sign-extended from LDS.S8.
+// ------------------------------------------------------------------------------------------------
+template <int COUT, int XU>
+__global__ void __launch_bounds__(kDwSmemThreads, 2) dwconv_cin1_smem_kernel(ConvArgs a, uint32_t in_bytes, uint32_t buf_stride, int nbuf, int nstrip, int rows_per_strip) {
+    extern __shared__ __align__(128) uint8_t dsm[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(dsm);
+    uint8_t *bufs = dsm + 128;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+    const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(bufs);
+    const int tid = threadIdx.x;
+    const long long first = blockIdx.x, step = gridDim.x;
+    if (tid == 0) {
+        for (int k = 0; k < nbuf; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * k), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto request = [&](long long b, int slot) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * slot), "r"(in_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf0 + (uint32_t)slot * buf_stride),
+                     "l"(a.in + (size_t)b * in_bytes), "r"(in_bytes), "r"(bar0 + 8u * slot)
+                     : "memory");
+    };
+    if (tid == 0)
+        for (int k = 0; k < nbuf; ++k)
+            if (first + (long long)k * step < a.batch) request(first + (long long)k * step, k);
+
+    constexpr int Q = COUT / 4;
+    const bool active = tid < a.OW * nstrip;
+    const int strip = active ? tid / a.OW : 0;
+    const int j = active ? tid - strip * a.OW : 0;
+    int wr[9][COUT];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) wr[t][c] = (int)(int8_t)__ldg(a.w + t * COUT + c);
+    int kcr[COUT];
+    float zr[COUT], sr[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) { kcr[c] = __ldg(a.kcorr + c); zr[c] = __ldg(a.c0z + c); sr[c] = __ldg(a.c1 + c); }
+    const int c0 = a.sw * j - a.off_c;
+    const bool cok0 = (unsigned)c0 < (unsigned)a.W, cok1 = (unsigned)(c0 + 1) < (unsigned)a.W, cok2 = (unsigned)(c0 + 2) < (unsigned)a.W;
+    const int i0 = strip * rows_per_strip;
+    const int i1 = active ? min(a.OH, i0 + rows_per_strip) : i0;
+    const float lo = a.lo, hi = a.hi;
+    const int H = a.H, W = a.W, iz = a.in_zp;
+
+    uint32_t it = 0;
+    for (long long b = first; b < a.batch; b += step, ++it) {
+        const int slot = (int)(it % (uint32_t)nbuf);
+        sm_mbar_wait(bar0 + 8u * slot, (it / (uint32_t)nbuf) & 1u);
+        const int8_t *src = reinterpret_cast<const int8_t *>(bufs + (size_t)slot * buf_stride);
+        uint32_t *o = reinterpret_cast<uint32_t *>(a.out) + (((size_t)b * a.OH + i0) * a.OW + j) * Q;
+        for (int i = i0; i < i1; ++i) {
+            int acc[COUT];
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) acc[c] = 0;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const int r = a.sh * i + m - a.off_r;
+                const bool rok = (unsigned)r < (unsigned)H;
+                const int8_t *p = src + r * W + c0;
+                const int v0 = (rok && cok0) ? (int)p[0] : iz, v1 = (rok && cok1) ? (int)p[1] : iz, v2 = (rok && cok2) ? (int)p[2] : iz;
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) acc[c] += v0 * wr[3 * m][c] + v1 * wr[3 * m + 1][c] + v2 * wr[3 * m + 2][c];
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                int y[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = 4 * q + u;
+                    y[u] = XU ? requant_xu<true>(acc[c] - kcr[c], zr[c], sr[c], lo, hi) : requant_nx<false>(acc[c] - kcr[c], zr[c], sr[c], lo, hi);
+                }
+                o[q] = pack4(y[0], y[1], y[2], y[3]);
+            }
+            o += (size_t)a.OW * Q;
+        }
+        __syncthreads();
+        if (tid == 0 && b + (long long)nbuf * step < a.batch) request(b + (long long)nbuf * step, slot);
+    }
+}
+
+bool dwconv_cin1_smem_eligible(const ConvArgs &a) {
+    const long long in_bytes = (long long)a.H * a.W;
+    return a.depthwise && !a.is_u8 && a.Cin == 1 && a.Cout == 8 && a.KH == 3 && a.KW == 3 && a.kcorr != nullptr && !a.big_acc && in_bytes % 16 == 0 &&
+           in_bytes <= 32 * 1024 && a.OW <= kDwSmemThreads && a.batch >= 148 * 2 && ((uintptr_t)a.in % 16) == 0;
+}
+cudaError_t launch_dwconv_cin1_smem(const ConvArgs &a, int num_sms, cudaStream_t s) {
+    const uint32_t in_bytes = (uint32_t)(a.H * a.W);
+    const uint32_t buf_stride = (in_bytes + 127u) & ~127u;
+    int nstrip = kDwSmemThreads / a.OW;
+    if (nstrip > a.OH) nstrip = a.OH;
+    const int rows = (a.OH + nstrip - 1) / nstrip;
+    nstrip = (a.OH + rows - 1) / rows;
+    const int nbuf = 4;
+    const size_t smem = 128 + (size_t)nbuf * buf_stride;
+    const bool full = a.lo == -128.f && a.hi == 127.f;
+    using Fn = void (*)(ConvArgs, uint32_t, uint32_t, int, int, int);
+    Fn fn = full ? dwconv_cin1_smem_kernel<8, 1> : dwconv_cin1_smem_kernel<8, 0>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 + 4 * 32 * 1024));
+    if (e != cudaSuccess) return e;
+    long long ctas = (long long)num_sms * 2;
+    if (ctas > a.batch) ctas = a.batch;
+    fn<<<(unsigned)ctas, kDwSmemThreads, smem, s>>>(a, in_bytes, buf_stride, nbuf, nstrip, rows);
+    return cudaGetLastError();
+}
+
 bool dwconv_cin1_eligible(const ConvArgs &a) {
     return a.depthwise && !a.is_u8 && a.Cin == 1 && (a.Cout % 4) == 0 && a.Cout >= 4 && a.Cout <= 16 && a.kcorr != nullptr && !a.big_acc &&
            (size_t)a.KH * a.KW * a.Cout * 4 <= 40 * 1024;

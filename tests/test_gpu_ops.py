@@ -162,7 +162,9 @@ FAST_SIMT_CASES = [
     (333, 6, 6, 128, 128, 3, 3, 1, 1, "same", "relu", True, "dwconv3x3_rows"),
     (300, 9, 7, 16, 16, 3, 3, 1, 1, "valid", "none", True, "dwconv3x3_rows"),
     (300, 11, 13, 8, 8, 3, 3, 2, 2, "valid", "relu6", True, "dwconv3x3_rows"),
-    (300, 3, 3, 256, 256, 3, 3, 1, 1, "same", "relu6", True, "dwconv3x3_rows"),                 # mixed strides stay on the generic-shape fast kernel
+    (300, 3, 3, 256, 256, 3, 3, 1, 1, "same", "relu6", True, "dwconv3x3_rows"),
+    (300, 32, 32, 1, 8, 3, 3, 2, 2, "same", "relu6", True, "dwconv_cin1"),        # sample-resident Cin=1 kernel (layer-0 shape, scaled down)
+    (300, 20, 16, 1, 8, 3, 3, 1, 1, "valid", "relu", True, "dwconv_cin1"),                 # mixed strides stay on the generic-shape fast kernel
     (3, 1, 1, 256, 2, 1, 1, 1, 1, "same", "none", False, "pwconv_dp4a"),            # person_detect's last conv (Cout = 2)
     (2, 4, 4, 16, 7, 1, 1, 1, 1, "same", "relu", False, "pwconv_dp4a"),
     (3, 12, 12, 8, 16, 1, 1, 1, 1, "same", "relu6", False, "pwconv_dp4a|conv_tc"),   # person_detect layer 2 shape
@@ -215,6 +217,23 @@ def test_fully_connected_vs_oracle(K, N, B, wzp, dtype):
         got = mf.ops.fully_connected(x, w, wzp, 0.1, 3, "relu", c0, c1, c2, c3, impl=impl)
         want = oracle.fully_connected(x, w, wzp, 0.1, 3, "relu", c0, c1, c2, c3)
         np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("K,N,B", [(128, 32, 300), (256, 64, 129), (384, 256, 40), (1152, 96, 33)])
+def test_fully_connected_on_tensor_core_vs_oracle(K, N, B):
+    """FullyConnected through the tcgen05 GEMM (w_zp == 0, K % 128 == 0, N % 32 == 0); K = 1152 exceeds the 2^22 accumulator bound."""
+    r = rng(K + N)
+    x = r.integers(-128, 128, (B, K)).astype(np.int8)
+    w = r.integers(-128, 128, (N, K)).astype(np.int8)
+    in_zp = int(r.integers(-128, 128))
+    c0 = r.uniform(-10, 10, N).astype(np.float32)
+    c1 = np.float32(1.0 / (K * 30.0))
+    c2 = (w.astype(np.int32).sum(1) * in_zp).astype(np.int32)
+    got = mf.ops.fully_connected(x, w, 0, 0.1, 3, "relu", c0, c1, c2, 0, impl=0)
+    assert "conv_tc" in mf.ops.last_kernel, mf.ops.last_kernel
+    want = oracle.fully_connected(x, w, 0, 0.1, 3, "relu", c0, c1, c2, 0)
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(mf.ops.fully_connected(x, w, 0, 0.1, 3, "relu", c0, c1, c2, 0, impl=1), want)
 
 
 @pytest.mark.parametrize("H,W,C,FH,FW,sh,sw,pad,dtype", [(3, 3, 256, 3, 3, 2, 2, "valid", np.int8), (7, 9, 5, 2, 3, 1, 2, "same", np.int8),
