@@ -468,18 +468,19 @@ __global__ void __launch_bounds__(kDwSmemThreads, 3) dwconv3x3_smem_kernel(ConvA
             };
             auto emit = [&](const int (&r0)[12], const int (&r1)[12], const int (&r2)[12]) {
                 int acc[4];
+                const int nk[4] = {-kc.x, -kc.y, -kc.z, -kc.w};          // the zero-point correction rides in the accumulator init
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    int s = r0[k] * wi[0][k];
+                    int s = r0[k] * wi[0][k] + nk[k];
                     s += r0[4 + k] * wi[1][k]; s += r0[8 + k] * wi[2][k];
                     s += r1[k] * wi[3][k]; s += r1[4 + k] * wi[4][k]; s += r1[8 + k] * wi[5][k];
                     s += r2[k] * wi[6][k]; s += r2[4 + k] * wi[7][k]; s += r2[8 + k] * wi[8][k];
                     acc[k] = s;
                 }
-                *o = pack4(XU > 0 ? requant_xu<true>(acc[0] - kc.x, z.x, sc.x, lo, hi) : requant_nx<false>(acc[0] - kc.x, z.x, sc.x, lo, hi),
-                           XU > 1 ? requant_xu<true>(acc[1] - kc.y, z.y, sc.y, lo, hi) : requant_nx<false>(acc[1] - kc.y, z.y, sc.y, lo, hi),
-                           XU > 2 ? requant_xu<true>(acc[2] - kc.z, z.z, sc.z, lo, hi) : requant_nx<false>(acc[2] - kc.z, z.z, sc.z, lo, hi),
-                           XU > 3 ? requant_xu<true>(acc[3] - kc.w, z.w, sc.w, lo, hi) : requant_nx<false>(acc[3] - kc.w, z.w, sc.w, lo, hi));
+                *o = pack4(XU > 0 ? requant_xu<true>(acc[0], z.x, sc.x, lo, hi) : requant_nx<false>(acc[0], z.x, sc.x, lo, hi),
+                           XU > 1 ? requant_xu<true>(acc[1], z.y, sc.y, lo, hi) : requant_nx<false>(acc[1], z.y, sc.y, lo, hi),
+                           XU > 2 ? requant_xu<true>(acc[2], z.z, sc.z, lo, hi) : requant_nx<false>(acc[2], z.z, sc.z, lo, hi),
+                           XU > 3 ? requant_xu<true>(acc[3], z.w, sc.w, lo, hi) : requant_nx<false>(acc[3], z.w, sc.w, lo, hi));
                 o += out_row_words;
             };
             int ra[12], rb[12], rc[12];
