@@ -395,24 +395,51 @@ __device__ __forceinline__ void sm_mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
-template <int S, int XU>
-__global__ void __launch_bounds__(kDwSmemThreads, 3) dwconv3x3_smem_kernel(ConvArgs a, uint32_t in_bytes, uint32_t buf_stride, int nbuf, int xw, int nstrip,
+// MACs run in fp32: an int8 x int8 product and a 9-term sum of them are exactly representable (|sum| < 2^24), so FFMA2
+// (two FMAs per issue slot) gives the same integers as IMAD at half the issue cost, the accumulator needs no I2F, and the
+// requantization arithmetic packs into FFMA2 / FADD2.  Unpacking a byte = XOR 0x80 per word, one PRMT that drops the byte
+// into the mantissa of 2^23, one (packed) subtract of 2^23 + 128.
+// Borders cost nothing in the row loop: each ring slot is [one row of in_zp][the sample][one row of in_zp], so rows -1 and
+// H are ordinary loads, and a window column that falls outside the image reads a zero-point word through a pointer whose
+// per-row stride is 0.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <int S, bool FULL, int MINB>
+__global__ void __launch_bounds__(kDwSmemThreads, MINB) dwconv3x3_smem_kernel(ConvArgs a, uint32_t in_bytes, uint32_t buf_stride, int nbuf, int xw, int nstrip,
                                                                          int rows_per_strip) {
     extern __shared__ __align__(128) uint8_t dsm[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(dsm);                 // nbuf mbarriers (<= 8)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(dsm);                 // nbuf "sample landed" mbarriers (<= 8) ...
+    uint32_t *done = reinterpret_cast<uint32_t *>(dsm + 64);            // ... and nbuf "warps finished with this slot" counters
     uint8_t *bufs = dsm + 128;
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
     const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(bufs);
     const int tid = threadIdx.x;
     const long long first = blockIdx.x, step = gridDim.x;
+    const int G = a.Cout >> 2;
+    const uint32_t row_bytes = (uint32_t)(a.W * G) * 4u;
     if (tid == 0) {
-        for (int k = 0; k < nbuf; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * k), "r"(1u) : "memory");
+        for (int k = 0; k < nbuf; ++k) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * k), "r"(1u) : "memory");
+            done[k] = 0;
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    {   // the zero-point rows above and below every slot's sample (the bulk copies never touch them)
+        const uint32_t izw = (uint32_t)(a.in_zp & 0xff) * 0x01010101u;
+        const int rw = (int)(row_bytes >> 2);
+        for (int k = 0; k < nbuf; ++k) {
+            uint32_t *top = reinterpret_cast<uint32_t *>(bufs + (size_t)k * buf_stride);
+            uint32_t *bot = reinterpret_cast<uint32_t *>(bufs + (size_t)k * buf_stride + row_bytes + in_bytes);
+            for (int i = tid; i < rw; i += kDwSmemThreads) { top[i] = izw; bot[i] = izw; }
+        }
+    }
     __syncthreads();
-    auto request = [&](long long b, int slot) {                         // thread 0 only
+    auto request = [&](long long b, int slot) {                         // one thread
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * slot), "r"(in_bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf0 + (uint32_t)slot * buf_stride),
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf0 + (uint32_t)slot * buf_stride + row_bytes),
                      "l"(a.in + (size_t)b * in_bytes), "r"(in_bytes), "r"(bar0 + 8u * slot)
                      : "memory");
     };
@@ -420,88 +447,105 @@ __global__ void __launch_bounds__(kDwSmemThreads, 3) dwconv3x3_smem_kernel(ConvA
         for (int k = 0; k < nbuf; ++k)
             if (first + (long long)k * step < a.batch) request(first + (long long)k * step, k);
 
-    const int G = a.Cout >> 2;
     const bool active = tid < xw * nstrip;
     const int strip = active ? tid / xw : 0;
     const int x = active ? tid - strip * xw : 0;
     const int j = x / G, g = x - j * G;
     const uint32_t *ww = reinterpret_cast<const uint32_t *>(a.w);
-    int wi[9][4];
+    float2 wf[9][2];                                                    // weights of channels (0,1) and (2,3) of this word, per tap
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         const uint32_t wv = __ldg(ww + (size_t)k * G + g);
-        wi[k][0] = sx8<0>(wv); wi[k][1] = sx8<1>(wv); wi[k][2] = sx8<2>(wv); wi[k][3] = sx8<3>(wv);
+        wf[k][0] = make_float2((float)sx8<0>(wv), (float)sx8<1>(wv));
+        wf[k][1] = make_float2((float)sx8<2>(wv), (float)sx8<3>(wv));
     }
     const int4 kc = __ldg(reinterpret_cast<const int4 *>(a.kcorr) + g);
     const float4 z = __ldg(reinterpret_cast<const float4 *>(a.c0z) + g);
     const float4 sc = __ldg(reinterpret_cast<const float4 *>(a.c1) + g);
-    const uint32_t izw = (uint32_t)(a.in_zp & 0xff) * 0x01010101u;
+    const float2 nk01 = make_float2(-(float)kc.x, -(float)kc.y), nk23 = make_float2(-(float)kc.z, -(float)kc.w);   // |kcorr| < 2^24: exact
+    const float2 z01 = make_float2(z.x, z.y), z23 = make_float2(z.z, z.w), s01 = make_float2(sc.x, sc.y), s23 = make_float2(sc.z, sc.w);
+    const float2 unbias = make_float2(-8388736.0f, -8388736.0f);        // -(2^23 + 128)
     const int c0 = S * j - a.off_c;
-    const bool cok0 = (unsigned)c0 < (unsigned)a.W, cok1 = (unsigned)(c0 + 1) < (unsigned)a.W, cok2 = (unsigned)(c0 + 2) < (unsigned)a.W;
     const int i0 = strip * rows_per_strip;
     const int i1 = active ? min(a.OH, i0 + rows_per_strip) : i0;
-    const int row_words = a.W * G, out_row_words = a.OW * G;
-    const int col_off = c0 * G + g;                                     // word offset of window column 0 inside an input row (may be < 0)
-    const float lo = a.lo, hi = a.hi;
-    const int H = a.H;
-    const int r_first = S * i0 - a.off_r;
+    const int out_row_words = a.OW * G;
+    const float lo = a.lo, hi = a.hi, nz = a.neg_zero;
+    // byte offset (inside a slot) of window column k at the first input row of this strip, and its per-row stride
+    uint32_t off[3], stride[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const bool ok = (unsigned)(c0 + k) < (unsigned)a.W;
+        off[k] = ok ? (uint32_t)((int)row_bytes * (1 + S * i0 - a.off_r) + ((c0 + k) * G + g) * 4) : 0u;
+        stride[k] = ok ? row_bytes : 0u;
+    }
 
     uint32_t it = 0;
     for (long long b = first; b < a.batch; b += step, ++it) {
         const int slot = (int)(it % (uint32_t)nbuf);
         sm_mbar_wait(bar0 + 8u * slot, (it / (uint32_t)nbuf) & 1u);
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(bufs + (size_t)slot * buf_stride);
         if (i1 > i0) {
+            const uint32_t base = buf0 + (uint32_t)slot * buf_stride;
+            uint32_t p0 = base + off[0], p1 = base + off[1], p2 = base + off[2];
             uint32_t *o = reinterpret_cast<uint32_t *>(a.out) + ((size_t)b * a.OH + i0) * out_row_words + x;
-            int r = r_first;
-            const uint32_t *p = src + r * row_words + col_off;           // only dereferenced where the predicates allow
-            auto take = [&](int (&d)[12]) {                             // d[n * 4 + k] = channel k of window column n of input row r
-                const bool rok = (unsigned)r < (unsigned)H;
-                const uint32_t v0 = (rok && cok0) ? p[0] : izw;
-                const uint32_t v1 = (rok && cok1) ? p[G] : izw;
-                const uint32_t v2 = (rok && cok2) ? p[2 * G] : izw;
-                d[0] = sx8<0>(v0); d[1] = sx8<1>(v0); d[2] = sx8<2>(v0); d[3] = sx8<3>(v0);
-                d[4] = sx8<0>(v1); d[5] = sx8<1>(v1); d[6] = sx8<2>(v1); d[7] = sx8<3>(v1);
-                d[8] = sx8<0>(v2); d[9] = sx8<1>(v2); d[10] = sx8<2>(v2); d[11] = sx8<3>(v2);
-                p += row_words;
-                ++r;
+            // d[n][h] = float2 of channels (2h, 2h+1) of window column n of the next input row
+            auto take = [&](float2 (&d)[3][2]) {
+                const uint32_t v0 = lds_u32(p0) ^ 0x80808080u, v1 = lds_u32(p1) ^ 0x80808080u, v2 = lds_u32(p2) ^ 0x80808080u;
+                p0 += stride[0]; p1 += stride[1]; p2 += stride[2];
+                d[0][0] = fadd2(make_float2(biased_f32_from_byte<0>(v0), biased_f32_from_byte<1>(v0)), unbias);
+                d[0][1] = fadd2(make_float2(biased_f32_from_byte<2>(v0), biased_f32_from_byte<3>(v0)), unbias);
+                d[1][0] = fadd2(make_float2(biased_f32_from_byte<0>(v1), biased_f32_from_byte<1>(v1)), unbias);
+                d[1][1] = fadd2(make_float2(biased_f32_from_byte<2>(v1), biased_f32_from_byte<3>(v1)), unbias);
+                d[2][0] = fadd2(make_float2(biased_f32_from_byte<0>(v2), biased_f32_from_byte<1>(v2)), unbias);
+                d[2][1] = fadd2(make_float2(biased_f32_from_byte<2>(v2), biased_f32_from_byte<3>(v2)), unbias);
             };
-            auto emit = [&](const int (&r0)[12], const int (&r1)[12], const int (&r2)[12]) {
-                int acc[4];
-                const int nk[4] = {-kc.x, -kc.y, -kc.z, -kc.w};          // the zero-point correction rides in the accumulator init
+            // Input-stationary: an unpacked input row is used at once for every output row it feeds (kernel row T of one,
+            // T-1 of the next ...), so no window of rows is kept, and the 2-3 output rows in flight are independent FFMA2 chains.
+            struct Acc { float2 c01, c23; };
+            const Acc fresh = {nk01, nk23};                             // the zero-point correction rides in the accumulator init
+            auto mac = [&](Acc &A, const float2 (&d)[3][2], int T) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    int s = r0[k] * wi[0][k] + nk[k];
-                    s += r0[4 + k] * wi[1][k]; s += r0[8 + k] * wi[2][k];
-                    s += r1[k] * wi[3][k]; s += r1[4 + k] * wi[4][k]; s += r1[8 + k] * wi[5][k];
-                    s += r2[k] * wi[6][k]; s += r2[4 + k] * wi[7][k]; s += r2[8 + k] * wi[8][k];
-                    acc[k] = s;
+                for (int n = 0; n < 3; ++n) {
+                    A.c01 = ffma2(d[n][0], wf[3 * T + n][0], A.c01);
+                    A.c23 = ffma2(d[n][1], wf[3 * T + n][1], A.c23);
                 }
-                *o = pack4(XU > 0 ? requant_xu<true>(acc[0], z.x, sc.x, lo, hi) : requant_nx<false>(acc[0], z.x, sc.x, lo, hi),
-                           XU > 1 ? requant_xu<true>(acc[1], z.y, sc.y, lo, hi) : requant_nx<false>(acc[1], z.y, sc.y, lo, hi),
-                           XU > 2 ? requant_xu<true>(acc[2], z.z, sc.z, lo, hi) : requant_nx<false>(acc[2], z.z, sc.z, lo, hi),
-                           XU > 3 ? requant_xu<true>(acc[3], z.w, sc.w, lo, hi) : requant_nx<false>(acc[3], z.w, sc.w, lo, hi));
+            };
+            auto store = [&](const Acc &A) {
+                int y0, y1, y2, y3;
+                requant_f2<FULL>(A.c01, z01, s01, lo, hi, nz, y0, y1);
+                requant_f2<FULL>(A.c23, z23, s23, lo, hi, nz, y2, y3);
+                *o = pack4(y0, y1, y2, y3);
                 o += out_row_words;
             };
-            int ra[12], rb[12], rc[12];
+            float2 d[3][2];
+            Acc A = fresh, B = fresh, C = fresh;
             int left = i1 - i0;
-            if (S == 1) {
-                take(ra); take(rb);
+            if (S == 1) {                                               // input row r is kernel row 0 of output r+off, 1 of the one before, 2 of the one before that
+                take(d); mac(A, d, 0);
+                take(d); mac(A, d, 1); mac(B, d, 0);
                 while (true) {
-                    take(rc); emit(ra, rb, rc); if (--left == 0) break;
-                    take(ra); emit(rb, rc, ra); if (--left == 0) break;
-                    take(rb); emit(rc, ra, rb); if (--left == 0) break;
+                    take(d); mac(A, d, 2); mac(B, d, 1); C = fresh; mac(C, d, 0); store(A); if (--left == 0) break;
+                    take(d); mac(B, d, 2); mac(C, d, 1); A = fresh; mac(A, d, 0); store(B); if (--left == 0) break;
+                    take(d); mac(C, d, 2); mac(A, d, 1); B = fresh; mac(B, d, 0); store(C); if (--left == 0) break;
                 }
-            } else {
-                take(ra);
+            } else {                                                    // stride 2: every second input row closes one output row and opens the next
+                take(d); mac(A, d, 0);
                 while (true) {
-                    take(rb); take(rc); emit(ra, rb, rc); if (--left == 0) break;
-                    take(rb); take(ra); emit(rc, rb, ra); if (--left == 0) break;
+                    take(d); mac(A, d, 1);
+                    take(d); mac(A, d, 2); B = fresh; mac(B, d, 0); store(A); if (--left == 0) break;
+                    take(d); mac(B, d, 1);
+                    take(d); mac(B, d, 2); A = fresh; mac(A, d, 0); store(B); if (--left == 0) break;
                 }
             }
         }
-        __syncthreads();                                                 // every thread is done reading this buffer
-        if (tid == 0 && b + (long long)nbuf * step < a.batch) request(b + (long long)nbuf * step, slot);
+        // No CTA-wide barrier per sample: warps run ahead into the slots that have already landed.  The last warp to finish
+        // with a slot (acq_rel counter: every warp's reads happen-before the refill) re-arms it for sample b + nbuf * step.
+        __syncwarp();
+        if ((tid & 31) == 0) {
+            uint32_t old;
+            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(bar0 + 64u + 4u * slot) : "memory");
+            if (old % (uint32_t)(kDwSmemThreads / 32) == (uint32_t)(kDwSmemThreads / 32 - 1))   // the counter is never reset
+                if (b + (long long)nbuf * step < a.batch) request(b + (long long)nbuf * step, slot);
+        }
     }
 }
 
@@ -510,11 +554,14 @@ bool dwconv3x3_smem_eligible(const ConvArgs &a) {
     if (!(dwconv_c4_eligible(a) && a.KH == 3 && a.KW == 3 && a.sh == a.sw && (a.sh == 1 || a.sh == 2))) return false;
     const long long in_bytes = (long long)a.H * a.W * a.Cin;
     const int xw = a.OW * (a.Cout / 4);
-    return in_bytes % 16 == 0 && in_bytes <= 48 * 1024 && xw <= kDwSmemThreads && a.batch >= 148 * 2 && ((uintptr_t)a.in % 16) == 0;
+    // rows read: -off_r .. sh*(OH-1) - off_r + 2; the slot holds rows -1 .. H
+    const bool rows_ok = a.off_r <= 1 && a.off_r >= 0 && a.sh * (a.OH - 1) - a.off_r + 2 <= a.H;
+    return in_bytes % 16 == 0 && ((long long)a.W * a.Cin) % 16 == 0 && in_bytes <= 48 * 1024 && xw <= kDwSmemThreads && rows_ok && a.batch >= 148 * 2 &&
+           ((uintptr_t)a.in % 16) == 0;
 }
 cudaError_t launch_dwconv3x3_smem(const ConvArgs &a, int num_sms, cudaStream_t s) {
     const uint32_t in_bytes = (uint32_t)(a.H * a.W * a.Cin);
-    const uint32_t buf_stride = (in_bytes + 127u) & ~127u;
+    const uint32_t buf_stride = (in_bytes + 2u * (uint32_t)(a.W * a.Cin) + 127u) & ~127u;   // sample + a zero-point row either side
     const int xw = a.OW * (a.Cout / 4);
     int nstrip = kDwSmemThreads / xw;
     if (nstrip > a.OH) nstrip = a.OH;
@@ -522,18 +569,20 @@ cudaError_t launch_dwconv3x3_smem(const ConvArgs &a, int num_sms, cudaStream_t s
     nstrip = (a.OH + rows - 1) / rows;
     int nbuf = in_bytes <= 12 * 1024 ? 4 : (in_bytes <= 24 * 1024 ? 3 : 2);
     const size_t smem = 128 + (size_t)nbuf * buf_stride;
-    static const int env_xu = [] { const char *e = std::getenv("MF_DW_XU"); return e ? std::atoi(e) : -1; }();
-    int xu = env_xu >= 0 ? env_xu : 4;
-    if (!(a.lo == -128.f && a.hi == 127.f)) xu = 0;
-    xu = xu >= 4 ? 4 : 0;
+    const bool full = a.lo == -128.f && a.hi == 127.f;          // F2I.S8 saturation doubles as the clamp
     using Fn = void (*)(ConvArgs, uint32_t, uint32_t, int, int, int, int);
-    Fn fn = a.sh == 1 ? (xu ? dwconv3x3_smem_kernel<1, 4> : dwconv3x3_smem_kernel<1, 0>) : (xu ? dwconv3x3_smem_kernel<2, 4> : dwconv3x3_smem_kernel<2, 0>);
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 + 4 * 48 * 1024));
+    static const int env_minb = [] { const char *e = std::getenv("MF_DW_MINB"); return e ? std::atoi(e) : 3; }();
+    const int minb = env_minb == 2 ? 2 : 3;
+    Fn fn = minb == 3 ? (a.sh == 1 ? (full ? dwconv3x3_smem_kernel<1, true, 3> : dwconv3x3_smem_kernel<1, false, 3>)
+                                   : (full ? dwconv3x3_smem_kernel<2, true, 3> : dwconv3x3_smem_kernel<2, false, 3>))
+                      : (a.sh == 1 ? (full ? dwconv3x3_smem_kernel<1, true, 2> : dwconv3x3_smem_kernel<1, false, 2>)
+                                   : (full ? dwconv3x3_smem_kernel<2, true, 2> : dwconv3x3_smem_kernel<2, false, 2>));
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
     // persistent CTAs: as many as fit an SM (3 by registers / launch bounds, fewer if the sample ring is large); samples are
     // taken grid-stride
     int per_sm = (int)((227 * 1024) / (smem + 1024));
-    if (per_sm > 3) per_sm = 3;
+    if (per_sm > minb) per_sm = minb;
     if (per_sm < 1) per_sm = 1;
     long long ctas = (long long)num_sms * per_sm;
     if (ctas > a.batch) ctas = a.batch;
