@@ -85,48 +85,6 @@ template <bool FULL> __device__ __forceinline__ int requant_xu(int acc, float c0
     return y;
 }
 
-// ---- packed f32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2 -- two IEEE-RN operations per issue slot) -------------------
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-    uint64_t d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<uint64_t *>(&a)), "l"(*reinterpret_cast<uint64_t *>(&b)), "l"(*reinterpret_cast<uint64_t *>(&c)));
-    return *reinterpret_cast<float2 *>(&d);
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-    uint64_t d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<uint64_t *>(&a)), "l"(*reinterpret_cast<uint64_t *>(&b)));
-    return *reinterpret_cast<float2 *>(&d);
-}
-// a * b rounded once, NOT contractible with a following add.  ptxas (12.9, even with --fmad false) fuses mul.rn.f32x2 +
-// add.rn.f32x2 into one FFMA2 and also folds fma(a, b, -0.0) back into a mul, which would change the reference's
-// two-rounding requantization.  So the multiply is an FFMA2 whose addend is a -0.0 the compiler cannot see (it arrives
-// as a kernel argument): fma(a, b, -0) == fl(a * b) for every input (x + -0 == x, including both zeros).
-__device__ __forceinline__ float2 fmul2_opaque(float2 a, float2 b, float neg_zero) { return ffma2(a, b, make_float2(neg_zero, neg_zero)); }
-// copysign(0x1.fffffep-2, t) in one LOP3: (t & 0x80000000) | 0x3EFFFFFF
-__device__ __forceinline__ float round_bias1(float t) {
-    uint32_t r;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(__float_as_uint(t)), "r"(0x80000000u), "r"(0x3EFFFFFFu));
-    return __uint_as_float(r);
-}
-// int8 byte K of a word whose bytes were XOR-ed with 0x80 -> the float 2^23 + 128 + b (exact); subtract 8388736.f to get b
-template <int K> __device__ __forceinline__ float biased_f32_from_byte(uint32_t w_xor80) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w_xor80), "r"(0x4B000000u), "r"((uint32_t)(0x7650 | K)));
-    return __uint_as_float(r);
-}
-// requantize a PAIR of exact integer-valued float accumulators (|acc| < 2^24): same f32 operations as the scalar path
-// (mul, add, roundf, saturate), issued as packed f32x2 instructions
-template <bool FULL> __device__ __forceinline__ void requant_f2(float2 acc, float2 c0z, float2 c1, float lo, float hi, float neg_zero, int &y0, int &y1) {
-    const float2 t = fadd2(c0z, fmul2_opaque(c1, acc, neg_zero));
-    if (FULL) {
-        const float2 s = fadd2(t, make_float2(round_bias1(t.x), round_bias1(t.y)));
-        asm("cvt.rzi.sat.s8.f32 %0, %1;" : "=r"(y0) : "f"(s.x));
-        asm("cvt.rzi.sat.s8.f32 %0, %1;" : "=r"(y1) : "f"(s.y));
-    } else {
-        y0 = round_clamp_nx(t.x, lo, hi);
-        y1 = round_clamp_nx(t.y, lo, hi);
-    }
-}
-
 // sign-extended byte k of a packed word: one PRMT (selector msb = replicate the sign of the selected byte)
 template <int K> __device__ __forceinline__ int sx8(uint32_t w) {
     int r;

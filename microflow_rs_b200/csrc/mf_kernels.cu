@@ -395,25 +395,39 @@ __device__ __forceinline__ void sm_mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
-// MACs run in fp32: an int8 x int8 product and a 9-term sum of them are exactly representable (|sum| < 2^24), so FFMA2
-// (two FMAs per issue slot) gives the same integers as IMAD at half the issue cost, the accumulator needs no I2F, and the
-// requantization arithmetic packs into FFMA2 / FADD2.  Unpacking a byte = XOR 0x80 per word, one PRMT that drops the byte
-// into the mantissa of 2^23, one (packed) subtract of 2^23 + 128.
+// Sample-resident depthwise 3x3.  Issue slots are what bound it (tools/ubench/pipes.cu: IMAD, IDP4A, PRMT, LOP3 and the
+// packed FFMA2 all cost 2 clk per warp on their pipe, FFMA 1), so the MACs are IDP.4A: the three columns of an input row
+// are transposed (6 PRMT, on the ALU pipe, overlapping the dot products) into one register per channel holding that
+// channel's (left, centre, right, -) bytes, and one dp4a against (w[T][0], w[T][1], w[T][2], 0) is a whole kernel row.
+// Input-stationary: a transposed row is used at once for every output row it feeds (kernel row 0 of one, 1 of the one
+// before, 2 of the one before that), so no window of rows is kept and the output rows in flight are independent chains.
 // Borders cost nothing in the row loop: each ring slot is [one row of in_zp][the sample][one row of in_zp], so rows -1 and
-// H are ordinary loads, and a window column that falls outside the image reads a zero-point word through a pointer whose
-// per-row stride is 0.
+// H are ordinary loads, a window column outside the image reads a zero-point word through a pointer whose per-row stride
+// is 0, and the accumulators start at -in_zp * sum(w).
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+template <uint32_t SEL> __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "n"(SEL));
+    return r;
+}
+// four words (one per column, 4 channels each; the 4th is ignored) -> per-channel (col0, col1, col2, don't-care) registers
+__device__ __forceinline__ void transpose_3x4(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t (&t)[4]) {
+    const uint32_t lo = prmt<0x5140>(v0, v1), hi = prmt<0x7362>(v0, v1);   // (v0.0 v1.0 v0.1 v1.1), (v0.2 v1.2 v0.3 v1.3)
+    t[0] = prmt<0x4410>(lo, v2);
+    t[1] = prmt<0x5532>(lo, v2);
+    t[2] = prmt<0x6610>(hi, v2);
+    t[3] = prmt<0x7732>(hi, v2);
+}
 template <int S, bool FULL, int MINB>
 __global__ void __launch_bounds__(kDwSmemThreads, MINB) dwconv3x3_smem_kernel(ConvArgs a, uint32_t in_bytes, uint32_t buf_stride, int nbuf, int xw, int nstrip,
-                                                                         int rows_per_strip) {
+                                                                            int rows_per_strip) {
     extern __shared__ __align__(128) uint8_t dsm[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(dsm);                 // nbuf "sample landed" mbarriers (<= 8) ...
-    uint32_t *done = reinterpret_cast<uint32_t *>(dsm + 64);            // ... and nbuf "warps finished with this slot" counters
-    uint8_t *bufs = dsm + 128;
+    uint8_t *bufs = dsm + 128;                                          // ... and, at dsm + 64, nbuf "warps finished with this slot" counters
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
     const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(bufs);
     const int tid = threadIdx.x;
@@ -423,7 +437,7 @@ __global__ void __launch_bounds__(kDwSmemThreads, MINB) dwconv3x3_smem_kernel(Co
     if (tid == 0) {
         for (int k = 0; k < nbuf; ++k) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * k), "r"(1u) : "memory");
-            done[k] = 0;
+            reinterpret_cast<uint32_t *>(dsm + 64)[k] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -451,25 +465,25 @@ __global__ void __launch_bounds__(kDwSmemThreads, MINB) dwconv3x3_smem_kernel(Co
     const int strip = active ? tid / xw : 0;
     const int x = active ? tid - strip * xw : 0;
     const int j = x / G, g = x - j * G;
-    const uint32_t *ww = reinterpret_cast<const uint32_t *>(a.w);
-    float2 wf[9][2];                                                    // weights of channels (0,1) and (2,3) of this word, per tap
+    // wq[T][c] = (w[T][0][c], w[T][1][c], w[T][2][c], 0): the three taps of kernel row T of channel 4g + c
+    uint32_t wq[3][4];
+    {
+        const uint32_t *ww = reinterpret_cast<const uint32_t *>(a.w);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const uint32_t wv = __ldg(ww + (size_t)k * G + g);
-        wf[k][0] = make_float2((float)sx8<0>(wv), (float)sx8<1>(wv));
-        wf[k][1] = make_float2((float)sx8<2>(wv), (float)sx8<3>(wv));
+        for (int T = 0; T < 3; ++T) {
+            transpose_3x4(__ldg(ww + (size_t)(3 * T) * G + g), __ldg(ww + (size_t)(3 * T + 1) * G + g), __ldg(ww + (size_t)(3 * T + 2) * G + g), wq[T]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) wq[T][c] &= 0x00ffffffu;
+        }
     }
     const int4 kc = __ldg(reinterpret_cast<const int4 *>(a.kcorr) + g);
     const float4 z = __ldg(reinterpret_cast<const float4 *>(a.c0z) + g);
     const float4 sc = __ldg(reinterpret_cast<const float4 *>(a.c1) + g);
-    const float2 nk01 = make_float2(-(float)kc.x, -(float)kc.y), nk23 = make_float2(-(float)kc.z, -(float)kc.w);   // |kcorr| < 2^24: exact
-    const float2 z01 = make_float2(z.x, z.y), z23 = make_float2(z.z, z.w), s01 = make_float2(sc.x, sc.y), s23 = make_float2(sc.z, sc.w);
-    const float2 unbias = make_float2(-8388736.0f, -8388736.0f);        // -(2^23 + 128)
     const int c0 = S * j - a.off_c;
     const int i0 = strip * rows_per_strip;
     const int i1 = active ? min(a.OH, i0 + rows_per_strip) : i0;
     const int out_row_words = a.OW * G;
-    const float lo = a.lo, hi = a.hi, nz = a.neg_zero;
+    const float lo = a.lo, hi = a.hi;
     // byte offset (inside a slot) of window column k at the first input row of this strip, and its per-row stride
     uint32_t off[3], stride[3];
 #pragma unroll
@@ -487,53 +501,40 @@ __global__ void __launch_bounds__(kDwSmemThreads, MINB) dwconv3x3_smem_kernel(Co
             const uint32_t base = buf0 + (uint32_t)slot * buf_stride;
             uint32_t p0 = base + off[0], p1 = base + off[1], p2 = base + off[2];
             uint32_t *o = reinterpret_cast<uint32_t *>(a.out) + ((size_t)b * a.OH + i0) * out_row_words + x;
-            // d[n][h] = float2 of channels (2h, 2h+1) of window column n of the next input row
-            auto take = [&](float2 (&d)[3][2]) {
-                const uint32_t v0 = lds_u32(p0) ^ 0x80808080u, v1 = lds_u32(p1) ^ 0x80808080u, v2 = lds_u32(p2) ^ 0x80808080u;
+            auto take = [&](uint32_t (&t)[4]) {                         // the next input row, transposed
+                const uint32_t v0 = lds_u32(p0), v1 = lds_u32(p1), v2 = lds_u32(p2);
                 p0 += stride[0]; p1 += stride[1]; p2 += stride[2];
-                d[0][0] = fadd2(make_float2(biased_f32_from_byte<0>(v0), biased_f32_from_byte<1>(v0)), unbias);
-                d[0][1] = fadd2(make_float2(biased_f32_from_byte<2>(v0), biased_f32_from_byte<3>(v0)), unbias);
-                d[1][0] = fadd2(make_float2(biased_f32_from_byte<0>(v1), biased_f32_from_byte<1>(v1)), unbias);
-                d[1][1] = fadd2(make_float2(biased_f32_from_byte<2>(v1), biased_f32_from_byte<3>(v1)), unbias);
-                d[2][0] = fadd2(make_float2(biased_f32_from_byte<0>(v2), biased_f32_from_byte<1>(v2)), unbias);
-                d[2][1] = fadd2(make_float2(biased_f32_from_byte<2>(v2), biased_f32_from_byte<3>(v2)), unbias);
+                transpose_3x4(v0, v1, v2, t);
             };
-            // Input-stationary: an unpacked input row is used at once for every output row it feeds (kernel row T of one,
-            // T-1 of the next ...), so no window of rows is kept, and the 2-3 output rows in flight are independent FFMA2 chains.
-            struct Acc { float2 c01, c23; };
-            const Acc fresh = {nk01, nk23};                             // the zero-point correction rides in the accumulator init
-            auto mac = [&](Acc &A, const float2 (&d)[3][2], int T) {
+            struct Acc { int c[4]; };
+            const Acc fresh = {{-kc.x, -kc.y, -kc.z, -kc.w}};           // the zero-point correction rides in the accumulator init
+            auto mac = [&](Acc &A, const uint32_t (&t)[4], int T) {
 #pragma unroll
-                for (int n = 0; n < 3; ++n) {
-                    A.c01 = ffma2(d[n][0], wf[3 * T + n][0], A.c01);
-                    A.c23 = ffma2(d[n][1], wf[3 * T + n][1], A.c23);
-                }
+                for (int c = 0; c < 4; ++c) A.c[c] = __dp4a((int)t[c], (int)wq[T][c], A.c[c]);
             };
             auto store = [&](const Acc &A) {
-                int y0, y1, y2, y3;
-                requant_f2<FULL>(A.c01, z01, s01, lo, hi, nz, y0, y1);
-                requant_f2<FULL>(A.c23, z23, s23, lo, hi, nz, y2, y3);
-                *o = pack4(y0, y1, y2, y3);
+                *o = pack4(requant_xu<FULL>(A.c[0], z.x, sc.x, lo, hi), requant_xu<FULL>(A.c[1], z.y, sc.y, lo, hi), requant_xu<FULL>(A.c[2], z.z, sc.z, lo, hi),
+                           requant_xu<FULL>(A.c[3], z.w, sc.w, lo, hi));
                 o += out_row_words;
             };
-            float2 d[3][2];
+            uint32_t t[4];
             Acc A = fresh, B = fresh, C = fresh;
             int left = i1 - i0;
-            if (S == 1) {                                               // input row r is kernel row 0 of output r+off, 1 of the one before, 2 of the one before that
-                take(d); mac(A, d, 0);
-                take(d); mac(A, d, 1); mac(B, d, 0);
+            if (S == 1) {
+                take(t); mac(A, t, 0);
+                take(t); mac(A, t, 1); mac(B, t, 0);
                 while (true) {
-                    take(d); mac(A, d, 2); mac(B, d, 1); C = fresh; mac(C, d, 0); store(A); if (--left == 0) break;
-                    take(d); mac(B, d, 2); mac(C, d, 1); A = fresh; mac(A, d, 0); store(B); if (--left == 0) break;
-                    take(d); mac(C, d, 2); mac(A, d, 1); B = fresh; mac(B, d, 0); store(C); if (--left == 0) break;
+                    take(t); mac(A, t, 2); mac(B, t, 1); C = fresh; mac(C, t, 0); store(A); if (--left == 0) break;
+                    take(t); mac(B, t, 2); mac(C, t, 1); A = fresh; mac(A, t, 0); store(B); if (--left == 0) break;
+                    take(t); mac(C, t, 2); mac(A, t, 1); B = fresh; mac(B, t, 0); store(C); if (--left == 0) break;
                 }
             } else {                                                    // stride 2: every second input row closes one output row and opens the next
-                take(d); mac(A, d, 0);
+                take(t); mac(A, t, 0);
                 while (true) {
-                    take(d); mac(A, d, 1);
-                    take(d); mac(A, d, 2); B = fresh; mac(B, d, 0); store(A); if (--left == 0) break;
-                    take(d); mac(B, d, 1);
-                    take(d); mac(B, d, 2); A = fresh; mac(A, d, 0); store(B); if (--left == 0) break;
+                    take(t); mac(A, t, 1);
+                    take(t); mac(A, t, 2); B = fresh; mac(B, t, 0); store(A); if (--left == 0) break;
+                    take(t); mac(B, t, 1);
+                    take(t); mac(B, t, 2); A = fresh; mac(A, t, 0); store(B); if (--left == 0) break;
                 }
             }
         }
@@ -567,23 +568,28 @@ cudaError_t launch_dwconv3x3_smem(const ConvArgs &a, int num_sms, cudaStream_t s
     if (nstrip > a.OH) nstrip = a.OH;
     const int rows = (a.OH + nstrip - 1) / nstrip;
     nstrip = (a.OH + rows - 1) / rows;
-    int nbuf = in_bytes <= 12 * 1024 ? 4 : (in_bytes <= 24 * 1024 ? 3 : 2);
+    static const int env_minb = [] { const char *e = std::getenv("MF_DW_MINB"); return e ? std::atoi(e) : 4; }();
+    const int minb = env_minb < 2 ? 2 : (env_minb > 4 ? 4 : env_minb);
+    // persistent CTAs, samples taken grid-stride: as many CTAs per SM as the launch bound allows while every CTA still has
+    // a ring of >= 2 sample slots (<= 4) in its share of the 227 KB
+    int per_sm = minb, nbuf = 0;
+    for (; per_sm >= 1; --per_sm) {
+        const long long share = (227ll * 1024) / per_sm - 1024 - 128;
+        nbuf = (int)(share / buf_stride);
+        if (nbuf > 4) nbuf = 4;
+        if (nbuf >= 2 || per_sm == 1) break;
+    }
+    if (nbuf < 1) return cudaErrorInvalidConfiguration;
     const size_t smem = 128 + (size_t)nbuf * buf_stride;
     const bool full = a.lo == -128.f && a.hi == 127.f;          // F2I.S8 saturation doubles as the clamp
     using Fn = void (*)(ConvArgs, uint32_t, uint32_t, int, int, int, int);
-    static const int env_minb = [] { const char *e = std::getenv("MF_DW_MINB"); return e ? std::atoi(e) : 3; }();
-    const int minb = env_minb == 2 ? 2 : 3;
-    Fn fn = minb == 3 ? (a.sh == 1 ? (full ? dwconv3x3_smem_kernel<1, true, 3> : dwconv3x3_smem_kernel<1, false, 3>)
-                                   : (full ? dwconv3x3_smem_kernel<2, true, 3> : dwconv3x3_smem_kernel<2, false, 3>))
-                      : (a.sh == 1 ? (full ? dwconv3x3_smem_kernel<1, true, 2> : dwconv3x3_smem_kernel<1, false, 2>)
-                                   : (full ? dwconv3x3_smem_kernel<2, true, 2> : dwconv3x3_smem_kernel<2, false, 2>));
+    Fn fn = nullptr;
+#define MF_DW_PICK(M) (a.sh == 1 ? (full ? dwconv3x3_smem_kernel<1, true, M> : dwconv3x3_smem_kernel<1, false, M>) \
+                                 : (full ? dwconv3x3_smem_kernel<2, true, M> : dwconv3x3_smem_kernel<2, false, M>))
+    fn = minb == 4 ? MF_DW_PICK(4) : (minb == 3 ? MF_DW_PICK(3) : MF_DW_PICK(2));
+#undef MF_DW_PICK
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
-    // persistent CTAs: as many as fit an SM (3 by registers / launch bounds, fewer if the sample ring is large); samples are
-    // taken grid-stride
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    if (per_sm > minb) per_sm = minb;
-    if (per_sm < 1) per_sm = 1;
     long long ctas = (long long)num_sms * per_sm;
     if (ctas > a.batch) ctas = a.batch;
     fn<<<(unsigned)ctas, kDwSmemThreads, smem, s>>>(a, in_bytes, buf_stride, nbuf, xw, nstrip, rows);

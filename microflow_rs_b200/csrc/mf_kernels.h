@@ -38,7 +38,6 @@ struct ConvArgs {
     float lo = -128.f, hi = 127.f;
     int is_u8 = 0, depthwise = 0;
     int big_acc = 0;                // 1 if |acc - kcorr| can exceed 2^22 (selects the general exact int->float)
-    float neg_zero = -0.0f;         // always -0.0; a value ptxas cannot see, used to keep a packed multiply un-contracted (mf_device.cuh)
     long long batch = 0;
 };
 
