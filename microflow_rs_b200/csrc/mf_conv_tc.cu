@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -43,9 +44,16 @@ constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr int kWarpAlloc = kEpiWarps, kWarpTma = kEpiWarps + 2, kWarpMma = kEpiWarps + 3;
 constexpr uint32_t kSmemLimit = 232448;  // 227 KB usable per CTA on sm_100
 
-// Per-channel epilogue tables, passed by value as a kernel parameter: they live in the constant bank, are read with
-// warp-uniform indices (every lane of a warp handles the same output column), and cost no shared memory -- which is
-// what lets the 3x3 configuration (147 KB of resident weights) afford a 4th TMA stage.
+// Per-channel epilogue tables, passed by value as a kernel parameter, i.e. they live in the constant bank.  How the
+// epilogue reads them is the kernel's TAB mode:
+//   kTabSmem    copied once per CTA into shared memory, read with broadcast LDS.128 (0.75 per output value; the MIO queue
+//               this fills is the top stall of the big pointwise layers, profiles/r01e)
+//   kTabPeriod  packed-pointwise layers with Cout | 32: every 32-column chunk sees the same 32 table entries, so ONE copy
+//               of the epilogue code has compile-time table indices and the values arrive as uniform-register / constant
+//               operands of the FMUL / FADD / IADD that use them -- no LDS at all
+//   kTabGroup   N <= 128: one code copy per column group (4 x 32 columns), same idea; with N = 256 the four copies (two
+//               chunks each) no longer fit the instruction cache of a sub-partition and this is slower than kTabSmem
+enum { kTabSmem = 0, kTabGroup = 1, kTabPeriod = 2 };
 struct ConvTcTables {
     float c0z[256];
     float c1[256];
@@ -60,7 +68,6 @@ struct ConvTcParams {
     long long num_tiles, OW, OH;
     float lo, hi;
     uint32_t idesc, stage_bytes, b_block_bytes, tmem_cols, nkb;
-    uint32_t out_stage_off;    // byte offset of the output staging buffers in dynamic smem (STAGE_OUT kernels)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -146,10 +153,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // the kernel
 // ------------------------------------------------------------------------------------------------
 // KH_T/KW_T/CB_T != 0: compile-time loop bounds, so the single MMA-issuing thread spends ~3 scalar instructions per MMA
-// (descriptor = base + constant); XUG = how many of the 8 four-value groups of each 32-column chunk take the XU epilogue.
-// STAGE_OUT: the int8 output tile goes through shared memory (padded rows, double buffered) and is written back with fully
-// coalesced 16-byte-per-lane stores (512 contiguous bytes per warp instruction) instead of one 32-byte piece per row.
-template <bool BIG, int XUG, int KH_T, int KW_T, int CB_T, bool STAGE_OUT>
+// (descriptor = base + constant); XU = F2I.S8 / I2F epilogue (needs the full int8 clamp range) instead of the XU-free one;
+// TAB = how the epilogue reads its per-channel tables (above).
+template <bool BIG, bool XU, int KH_T, int KW_T, int CB_T, int TAB>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ ConvTcTables tab,
                const ConvTcParams p) {
@@ -158,11 +164,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint8_t *sB = smem;
     uint8_t *sA = sB + (size_t)p.nkb * p.b_block_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(sA + (size_t)p.stages * p.stage_bytes);   // 256 bytes reserved
-    // epilogue tables: copied once per CTA from the parameter (constant) bank into shared memory -- register-indexed LDC in the
-    // hot loop stalls on the MIO queue (ncu, profiles/), broadcast LDS.128 does not
-    float *s_c0z = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(bars) + 256);
+    float *s_c0z = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(bars) + 256);          // kTabSmem only
     float *s_c1 = s_c0z + p.N;
-    int32_t *s_corr = reinterpret_cast<int32_t *>(s_c1 + p.N);
+    int32_t *s_corr = reinterpret_cast<int32_t *>(s_c1 + p.N);                                 // [ncls][N]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 5);
 
     const uint32_t bar0 = smem_u32(bars);
@@ -190,7 +194,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp < kEpiWarps) {
+    if (TAB == kTabSmem && warp < kEpiWarps) {
         for (int k = threadIdx.x; k < p.N; k += 32 * kEpiWarps) { s_c0z[k] = tab.c0z[k]; s_c1[k] = tab.c1[k]; }
         for (int k = threadIdx.x; k < p.ncls * p.N; k += 32 * kEpiWarps) s_corr[k] = tab.corr[k];
     }
@@ -261,71 +265,79 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else if (warp < kEpiWarps) {
         // ===== epilogue: warp e = (lane quarter q, column group cg); chunk c of 32 columns belongs to group c % 4 =====
-        const uint32_t q = (uint32_t)(warp & 3);               // == warp % 4: the TMEM lane quarter this warp may read
-        const int cg = warp >> 2;
-        const int row = (int)(q * 32 + lane);
-        const int rr = row >> p.tw_log2, rc = row & (p.TW - 1);
-        const float lo = p.lo, hi = p.hi;
-        uint32_t it = 0;
-        for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const uint32_t acc = it & 1, aph = (it >> 1) & 1;
-            uint32_t b, rem, ty, tx;
-            p.fd_img.divmod((uint32_t)tile, b, rem);
-            p.fd_tx.divmod(rem, ty, tx);
-            const long long oy = (long long)ty * p.TH + rr, ox = (long long)tx * p.TW + rc;
-            const bool valid = oy < p.OH && ox < p.OW;
-            int cls = 0;
-            if (p.ncls == 9) cls = 3 * (oy == 0 ? 0 : (oy == p.OH - 1 ? 2 : 1)) + (ox == 0 ? 0 : (ox == p.OW - 1 ? 2 : 1));
-            const int32_t *corr = s_corr + cls * p.N;
-            uint8_t *orow = p.out + (((long long)b * p.OH + oy) * p.OW + ox) * p.N;
-            const int out_pitch = p.N + 16;                                   // +16 B: conflict-free STS.128 across rows
-            uint8_t *s_out = smem + p.out_stage_off + (size_t)(it & 1) * (128u * (uint32_t)out_pitch);
+        // cg_tag: the column group as a compile-time constant (kTabGroup), else -1 and the group is warp >> 2.
+        auto epilogue = [&](auto cg_tag) {
+            constexpr int CG = decltype(cg_tag)::value;
+            const uint32_t q = (uint32_t)(warp & 3);               // == warp % 4: the TMEM lane quarter this warp may read
+            const int cg = CG >= 0 ? CG : (warp >> 2);
+            const int row = (int)(q * 32 + lane);
+            const int rr = row >> p.tw_log2, rc = row & (p.TW - 1);
+            const float lo = p.lo, hi = p.hi;
+            uint32_t it = 0;
+            for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+                uint32_t b, rem, ty, tx;
+                p.fd_img.divmod((uint32_t)tile, b, rem);
+                p.fd_tx.divmod(rem, ty, tx);
+                const long long oy = (long long)ty * p.TH + rr, ox = (long long)tx * p.TW + rc;
+                const bool valid = oy < p.OH && ox < p.OW;
+                int cls = 0;
+                if (TAB == kTabSmem && p.ncls == 9) cls = 3 * (oy == 0 ? 0 : (oy == p.OH - 1 ? 2 : 1)) + (ox == 0 ? 0 : (ox == p.OW - 1 ? 2 : 1));
+                const int32_t *corr = s_corr + cls * p.N;
+                uint8_t *orow = p.out + (((long long)b * p.OH + oy) * p.OW + ox) * p.N;
 
-            mbar_wait(tfull_bar(acc), aph);
-            tc_fence_after();
-            const uint32_t t_base = tmem_base + acc * (uint32_t)p.N + ((q * 32u) << 16);
-            for (int c0 = 32 * cg; c0 < p.N; c0 += 128) {
-                uint32_t r[32];
-                tmem_ld32(t_base + (uint32_t)c0, r);
-                uint32_t w[8];
+                mbar_wait(tfull_bar(acc), aph);
+                tc_fence_after();
+                const uint32_t t_base = tmem_base + acc * (uint32_t)p.N + ((q * 32u) << 16);
+                for (int c0 = 32 * cg; c0 < p.N; c0 += 128) {
+                    uint32_t r[32];
+                    tmem_ld32(t_base + (uint32_t)c0, r);
+                    uint32_t w[8];
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    const float4 z = *reinterpret_cast<const float4 *>(s_c0z + c0 + 4 * g);
-                    const float4 sc = *reinterpret_cast<const float4 *>(s_c1 + c0 + 4 * g);
-                    const int4 kc = *reinterpret_cast<const int4 *>(corr + c0 + 4 * g);
-                    const int y0 = (g < XUG ? requant_xu<true>((int)r[4 * g + 0] - kc.x, z.x, sc.x, lo, hi) : requant_nx<BIG>((int)r[4 * g + 0] - kc.x, z.x, sc.x, lo, hi));
-                    const int y1 = (g < XUG ? requant_xu<true>((int)r[4 * g + 1] - kc.y, z.y, sc.y, lo, hi) : requant_nx<BIG>((int)r[4 * g + 1] - kc.y, z.y, sc.y, lo, hi));
-                    const int y2 = (g < XUG ? requant_xu<true>((int)r[4 * g + 2] - kc.z, z.z, sc.z, lo, hi) : requant_nx<BIG>((int)r[4 * g + 2] - kc.z, z.z, sc.z, lo, hi));
-                    const int y3 = (g < XUG ? requant_xu<true>((int)r[4 * g + 3] - kc.w, z.w, sc.w, lo, hi) : requant_nx<BIG>((int)r[4 * g + 3] - kc.w, z.w, sc.w, lo, hi));
-                    w[g] = pack4(y0, y1, y2, y3);
+                    for (int g = 0; g < 8; ++g) {
+                        int y[4];
+                        if (TAB == kTabSmem) {
+                            const float4 z = *reinterpret_cast<const float4 *>(s_c0z + c0 + 4 * g);
+                            const float4 sc = *reinterpret_cast<const float4 *>(s_c1 + c0 + 4 * g);
+                            const int4 kc = *reinterpret_cast<const int4 *>(corr + c0 + 4 * g);
+                            const float zz[4] = {z.x, z.y, z.z, z.w}, ss[4] = {sc.x, sc.y, sc.z, sc.w};
+                            const int kk[4] = {kc.x, kc.y, kc.z, kc.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int a = (int)r[4 * g + u] - kk[u];
+                                y[u] = XU ? requant_xu<true>(a, zz[u], ss[u], lo, hi) : requant_nx<BIG>(a, zz[u], ss[u], lo, hi);
+                            }
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                // kTabPeriod: the tables repeat every 32 columns; kTabGroup: N <= 128, this warp's only chunk is 32 * CG
+                                const int n = (TAB == kTabPeriod ? 0 : 32 * CG) + 4 * g + u;
+                                const int a = (int)r[4 * g + u] - tab.corr[n];
+                                y[u] = XU ? requant_xu<true>(a, tab.c0z[n], tab.c1[n], lo, hi) : requant_nx<BIG>(a, tab.c0z[n], tab.c1[n], lo, hi);
+                            }
+                        }
+                        w[g] = pack4(y[0], y[1], y[2], y[3]);
+                    }
+                    if (valid) {
+                        uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
+                        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    }
                 }
-                if (STAGE_OUT) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(s_out + (size_t)row * out_pitch + c0);
-                    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                } else if (valid) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
-                    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
-            if (STAGE_OUT) {
-                // all 16 epilogue warps have filled this tile's staging buffer -> cooperative, coalesced write-back.
-                // (pointwise tiles only: TH == 1, so the tile's 128 output rows are contiguous in global memory.)
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-                const int vec_per_row = p.N >> 4;
-                const long long row0 = (long long)tx * p.TW;
-                uint8_t *gbase = p.out + row0 * p.N;
-                const int rows_valid = (int)((p.OW - row0) < 128 ? (p.OW - row0) : 128);
-                for (int v = threadIdx.x; v < 128 * vec_per_row; v += 32 * kEpiWarps) {
-                    const int r = v / vec_per_row, cv = v - r * vec_per_row;
-                    if (r < rows_valid)
-                        *reinterpret_cast<uint4 *>(gbase + (size_t)v * 16) = *reinterpret_cast<const uint4 *>(s_out + (size_t)r * out_pitch + cv * 16);
-                }
+        };
+        if (TAB == kTabGroup) {
+            switch (warp >> 2) {
+                case 0: epilogue(std::integral_constant<int, 0>{}); break;
+                case 1: epilogue(std::integral_constant<int, 1>{}); break;
+                case 2: epilogue(std::integral_constant<int, 2>{}); break;
+                default: epilogue(std::integral_constant<int, 3>{}); break;
             }
+        } else {
+            epilogue(std::integral_constant<int, -1>{});
         }
     }
 
@@ -375,16 +387,11 @@ bool encode_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *
     return true;
 }
 
-bool plan_stage_out(const ConvTcPlan &p) {
-    static const bool want_stage = std::getenv("MF_TC_STAGE") != nullptr;   // opt-in: measured slower than direct stores (session 10)
-    return want_stage && p.KH == 1 && p.KW == 1 && p.TH == 1;
-}
 size_t plan_smem(const ConvTcPlan &p, int stages) {
     const size_t b_bytes = (size_t)p.KH * p.KW * p.CB * p.N * 128;
     const size_t stage = (size_t)(p.TH + p.KH - 1) * p.TW * 128;
-    const size_t out_stage = plan_stage_out(p) ? 2 * 128 * (size_t)(p.N + 16) : 0;
     const size_t tables = (size_t)p.N * 8 + (size_t)p.ncls * p.N * 4;
-    return b_bytes + stage * stages + 256 + tables + out_stage;
+    return b_bytes + stage * stages + 256 + tables;
 }
 
 }  // namespace
@@ -510,35 +517,35 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     k.stage_bytes = (uint32_t)((p.TH + p.KH - 1) * p.TW * 128);
     k.b_block_bytes = (uint32_t)(p.N * 128);
     k.nkb = (uint32_t)(p.KH * p.KW * p.CB);
-    k.out_stage_off = (uint32_t)((size_t)p.KH * p.KW * p.CB * p.N * 128 + (size_t)p.stages * k.stage_bytes + 256 + (size_t)p.N * 8 + (size_t)p.ncls * p.N * 4);
     k.tmem_cols = 2 * p.N <= 32 ? 32 : (2 * p.N <= 64 ? 64 : (2 * p.N <= 128 ? 128 : (2 * p.N <= 256 ? 256 : 512)));
     if (k.num_tiles <= 0) return cudaSuccess;
 
-    // epilogue mix: XU path needs the full int8 clamp range (F2I.S8 saturation); MF_TC_XUG overrides the default group count
+    // the F2I.S8 / I2F epilogue needs the full int8 clamp range (F2I.S8 saturation is the clamp); MF_TC_XUG=0 forces the XU-free one
     static const int env_xug = [] { const char *e = std::getenv("MF_TC_XUG"); return e ? std::atoi(e) : -1; }();
-    const bool full = p.lo == -128.f && p.hi == 127.f;
-    int xug = env_xug >= 0 ? env_xug : 8;
-    if (!full) xug = 0;
-    xug = xug >= 8 ? 8 : (xug >= 5 ? 5 : 0);
+    const bool xu = p.lo == -128.f && p.hi == 127.f && env_xug != 0;
     const int shape = (p.KH == 3 && p.KW == 3 && p.CB == 1) ? 1 : ((p.KH == 1 && p.KW == 1 && p.CB == 1) ? 2 : ((p.KH == 1 && p.KW == 1 && p.CB == 2) ? 3 : 0));
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const ConvTcTables, const ConvTcParams);
     KernelFn fn = nullptr;
-    // measured on B200 (gpurun session 10): staging + one extra barrier per tile is SLOWER than the direct 32-byte-per-row stores
-    // (pointwise layers 0.91 vs 0.79 ms per 8192-sample step), so it is opt-in
-    const bool stage_out = plan_stage_out(p) && shape >= 2;
-#define MF_TC_PICK(BIGV, XUV)                                                                               \
-    switch (shape) {                                                                                        \
-        case 1: fn = conv_tc_kernel<BIGV, XUV, 3, 3, 1, false>; break;                                      \
-        case 2: fn = stage_out ? conv_tc_kernel<BIGV, XUV, 1, 1, 1, true> : conv_tc_kernel<BIGV, XUV, 1, 1, 1, false>; break; \
-        case 3: fn = stage_out ? conv_tc_kernel<BIGV, XUV, 1, 1, 2, true> : conv_tc_kernel<BIGV, XUV, 1, 1, 2, false>; break; \
-        default: fn = conv_tc_kernel<BIGV, XUV, 0, 0, 0, false>; break;                                     \
+#define MF_TC_PICK(BIGV, XUV)                                                       \
+    switch (shape) {                                                                \
+        case 1: fn = conv_tc_kernel<BIGV, XUV, 3, 3, 1, kTabSmem>; break;           \
+        case 2: fn = conv_tc_kernel<BIGV, XUV, 1, 1, 1, kTabSmem>; break;           \
+        case 3: fn = conv_tc_kernel<BIGV, XUV, 1, 1, 2, kTabSmem>; break;           \
+        default: fn = conv_tc_kernel<BIGV, XUV, 0, 0, 0, kTabSmem>; break;          \
     }
     if (p.big_acc) {
-        if (xug == 8) { MF_TC_PICK(true, 8) } else if (xug == 5) { MF_TC_PICK(true, 5) } else { MF_TC_PICK(true, 0) }
+        if (xu) { MF_TC_PICK(true, true) } else { MF_TC_PICK(true, false) }
     } else {
-        if (xug == 8) { MF_TC_PICK(false, 8) } else if (xug == 5) { MF_TC_PICK(false, 5) } else { MF_TC_PICK(false, 0) }
+        if (xu) { MF_TC_PICK(false, true) } else { MF_TC_PICK(false, false) }
     }
 #undef MF_TC_PICK
+    // constant-operand epilogues for the common pointwise case (one border class, one 128-byte channel block, XU epilogue)
+    static const int env_tab = [] { const char *e = std::getenv("MF_TC_TAB"); return e ? std::atoi(e) : -1; }();
+    if (shape == 2 && xu && !p.big_acc && p.ncls == 1 && env_tab != kTabSmem) {
+        const bool periodic = p.Cout > 0 && 32 % p.Cout == 0 && p.N % p.Cout == 0 && p.P * p.Cout == p.N;
+        if (periodic && env_tab != kTabGroup) fn = conv_tc_kernel<false, true, 1, 1, 1, kTabPeriod>;
+        else if (p.N <= 128) fn = conv_tc_kernel<false, true, 1, 1, 1, kTabGroup>;
+    }
     static std::mutex attr_mu;
     static std::vector<KernelFn> attr_done;
     {
