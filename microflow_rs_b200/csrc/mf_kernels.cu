@@ -679,28 +679,43 @@ __global__ void __launch_bounds__(128) dwconv_cin1_kernel(ConvArgs a, uint32_t p
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Cin == 1 depthwise 3x3 (person_detect layer 0), sample-resident variant: the 9 KB input image is brought into shared
-// memory by one cp.async.bulk per sample (ring of 4), one thread = one output column of a row strip, all COUT channels,
-// the 9 x COUT sign-extended weights live in registers, activations arrive sign-extended from LDS.S8.
-// ------------------------------------------------------------------------------------------------
-template <int COUT, int XU>
-__global__ void __launch_bounds__(kDwSmemThreads, 2) dwconv_cin1_smem_kernel(ConvArgs a, uint32_t in_bytes, uint32_t buf_stride, int nbuf, int nstrip, int rows_per_strip) {
+// Depth-multiplier first layer (Cin == 1 -> 8 channels, 3x3), sample-resident like dwconv3x3_smem_kernel and built from the
+// same parts: zero-point rows around the sample, per-slot warp counters, IDP.4A.  A thread owns one output column.  The
+// three input bytes of a kernel row are consecutive in memory: two aligned LDS words and one PRMT with a per-thread
+// selector give (left, centre, right, -), and one dp4a per channel against (w[T][0][c], w[T][1][c], w[T][2][c], 0) is that
+// channel's whole kernel row.  A word that lies entirely left / right of the image is read from a zero-point word instead
+// (pointer with stride 0), which needs W % 4 == 0.
+template <int S, bool FULL>
+__global__ void __launch_bounds__(kDwSmemThreads, 3) dwconv_cin1_smem_kernel(ConvArgs a, uint32_t in_bytes, uint32_t buf_stride, int nbuf, int nstrip, int rows_per_strip) {
+    constexpr int COUT = 8;
     extern __shared__ __align__(128) uint8_t dsm[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(dsm);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(dsm);                 // nbuf "sample landed" mbarriers; counters at dsm + 64
     uint8_t *bufs = dsm + 128;
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
     const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(bufs);
     const int tid = threadIdx.x;
     const long long first = blockIdx.x, step = gridDim.x;
+    const uint32_t row_bytes = (uint32_t)a.W;
     if (tid == 0) {
-        for (int k = 0; k < nbuf; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * k), "r"(1u) : "memory");
+        for (int k = 0; k < nbuf; ++k) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * k), "r"(1u) : "memory");
+            reinterpret_cast<uint32_t *>(dsm + 64)[k] = 0;
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const uint32_t izw = (uint32_t)(a.in_zp & 0xff) * 0x01010101u;
+        const int rw = (int)(row_bytes >> 2);
+        for (int k = 0; k < nbuf; ++k) {
+            uint32_t *top = reinterpret_cast<uint32_t *>(bufs + (size_t)k * buf_stride);
+            uint32_t *bot = reinterpret_cast<uint32_t *>(bufs + (size_t)k * buf_stride + row_bytes + in_bytes);
+            for (int i = tid; i < rw; i += kDwSmemThreads) { top[i] = izw; bot[i] = izw; }
+        }
     }
     __syncthreads();
     auto request = [&](long long b, int slot) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * slot), "r"(in_bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf0 + (uint32_t)slot * buf_stride),
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf0 + (uint32_t)slot * buf_stride + row_bytes),
                      "l"(a.in + (size_t)b * in_bytes), "r"(in_bytes), "r"(bar0 + 8u * slot)
                      : "memory");
     };
@@ -708,82 +723,120 @@ __global__ void __launch_bounds__(kDwSmemThreads, 2) dwconv_cin1_smem_kernel(Con
         for (int k = 0; k < nbuf; ++k)
             if (first + (long long)k * step < a.batch) request(first + (long long)k * step, k);
 
-    constexpr int Q = COUT / 4;
     const bool active = tid < a.OW * nstrip;
     const int strip = active ? tid / a.OW : 0;
     const int j = active ? tid - strip * a.OW : 0;
-    int wr[9][COUT];
+    // wq[T][c] = (w[T][0][c], w[T][1][c], w[T][2][c], 0)
+    uint32_t wq[3][COUT];
 #pragma unroll
-    for (int t = 0; t < 9; ++t)
+    for (int T = 0; T < 3; ++T)
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) wr[t][c] = (int)(int8_t)__ldg(a.w + t * COUT + c);
+        for (int c = 0; c < COUT; ++c)
+            wq[T][c] = (uint32_t)__ldg(a.w + (3 * T) * COUT + c) | ((uint32_t)__ldg(a.w + (3 * T + 1) * COUT + c) << 8) | ((uint32_t)__ldg(a.w + (3 * T + 2) * COUT + c) << 16);
     int kcr[COUT];
     float zr[COUT], sr[COUT];
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) { kcr[c] = __ldg(a.kcorr + c); zr[c] = __ldg(a.c0z + c); sr[c] = __ldg(a.c1 + c); }
-    const int c0 = a.sw * j - a.off_c;
-    const bool cok0 = (unsigned)c0 < (unsigned)a.W, cok1 = (unsigned)(c0 + 1) < (unsigned)a.W, cok2 = (unsigned)(c0 + 2) < (unsigned)a.W;
+    for (int c = 0; c < COUT; ++c) { kcr[c] = -__ldg(a.kcorr + c); zr[c] = __ldg(a.c0z + c); sr[c] = __ldg(a.c1 + c); }
+    const int c0 = S * j - a.off_c;                                     // leftmost window column, >= -1
+    const int w0 = (c0 >= 0 ? c0 : c0 - 3) / 4;                         // floor(c0 / 4): the aligned word holding it
+    const uint32_t kk = (uint32_t)(c0 - 4 * w0);                        // its byte inside that word
+    const uint32_t sel = kk | ((kk + 1) << 4) | ((kk + 2) << 8) | ((kk + 2) << 12);
+    const bool lo_ok = w0 >= 0, hi_ok = 4 * (w0 + 1) < a.W;
     const int i0 = strip * rows_per_strip;
     const int i1 = active ? min(a.OH, i0 + rows_per_strip) : i0;
     const float lo = a.lo, hi = a.hi;
-    const int H = a.H, W = a.W, iz = a.in_zp;
+    const uint32_t first_row_off = (uint32_t)((int)row_bytes * (1 + S * i0 - a.off_r));
+    const uint32_t off_lo = lo_ok ? first_row_off + 4u * (uint32_t)w0 : 0u, off_hi = hi_ok ? first_row_off + 4u * (uint32_t)(w0 + 1) : 0u;
+    const uint32_t st_lo = lo_ok ? row_bytes : 0u, st_hi = hi_ok ? row_bytes : 0u;
 
     uint32_t it = 0;
     for (long long b = first; b < a.batch; b += step, ++it) {
         const int slot = (int)(it % (uint32_t)nbuf);
         sm_mbar_wait(bar0 + 8u * slot, (it / (uint32_t)nbuf) & 1u);
-        const int8_t *src = reinterpret_cast<const int8_t *>(bufs + (size_t)slot * buf_stride);
-        uint32_t *o = reinterpret_cast<uint32_t *>(a.out) + (((size_t)b * a.OH + i0) * a.OW + j) * Q;
-        for (int i = i0; i < i1; ++i) {
-            int acc[COUT];
+        if (i1 > i0) {
+            const uint32_t base = buf0 + (uint32_t)slot * buf_stride;
+            uint32_t plo = base + off_lo, phi = base + off_hi;
+            uint2 *o = reinterpret_cast<uint2 *>(a.out) + ((size_t)b * a.OH + i0) * a.OW + j;
+            auto take = [&]() {                                         // (left, centre, right, -) of the next input row
+                const uint32_t vlo = lds_u32(plo), vhi = lds_u32(phi);
+                plo += st_lo; phi += st_hi;
+                uint32_t t;
+                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(vlo), "r"(vhi), "r"(sel));
+                return t;
+            };
+            struct Acc { int c[COUT]; };
+            Acc fresh;
 #pragma unroll
-            for (int c = 0; c < COUT; ++c) acc[c] = 0;
+            for (int c = 0; c < COUT; ++c) fresh.c[c] = kcr[c];
+            auto mac = [&](Acc &A, uint32_t t, int T) {
 #pragma unroll
-            for (int m = 0; m < 3; ++m) {
-                const int r = a.sh * i + m - a.off_r;
-                const bool rok = (unsigned)r < (unsigned)H;
-                const int8_t *p = src + r * W + c0;
-                const int v0 = (rok && cok0) ? (int)p[0] : iz, v1 = (rok && cok1) ? (int)p[1] : iz, v2 = (rok && cok2) ? (int)p[2] : iz;
+                for (int c = 0; c < COUT; ++c) A.c[c] = __dp4a((int)t, (int)wq[T][c], A.c[c]);
+            };
+            auto store = [&](const Acc &A) {
+                int y[COUT];
 #pragma unroll
-                for (int c = 0; c < COUT; ++c) acc[c] += v0 * wr[3 * m][c] + v1 * wr[3 * m + 1][c] + v2 * wr[3 * m + 2][c];
-            }
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                int y[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int c = 4 * q + u;
-                    y[u] = XU ? requant_xu<true>(acc[c] - kcr[c], zr[c], sr[c], lo, hi) : requant_nx<false>(acc[c] - kcr[c], zr[c], sr[c], lo, hi);
+                for (int c = 0; c < COUT; ++c) y[c] = requant_xu<FULL>(A.c[c], zr[c], sr[c], lo, hi);
+                *o = make_uint2(pack4(y[0], y[1], y[2], y[3]), pack4(y[4], y[5], y[6], y[7]));
+                o += a.OW;
+            };
+            Acc A = fresh, B = fresh, C = fresh;
+            int left = i1 - i0;
+            uint32_t t;
+            if (S == 1) {
+                t = take(); mac(A, t, 0);
+                t = take(); mac(A, t, 1); mac(B, t, 0);
+                while (true) {
+                    t = take(); mac(A, t, 2); mac(B, t, 1); C = fresh; mac(C, t, 0); store(A); if (--left == 0) break;
+                    t = take(); mac(B, t, 2); mac(C, t, 1); A = fresh; mac(A, t, 0); store(B); if (--left == 0) break;
+                    t = take(); mac(C, t, 2); mac(A, t, 1); B = fresh; mac(B, t, 0); store(C); if (--left == 0) break;
                 }
-                o[q] = pack4(y[0], y[1], y[2], y[3]);
+            } else {
+                t = take(); mac(A, t, 0);
+                while (true) {
+                    t = take(); mac(A, t, 1);
+                    t = take(); mac(A, t, 2); B = fresh; mac(B, t, 0); store(A); if (--left == 0) break;
+                    t = take(); mac(B, t, 1);
+                    t = take(); mac(B, t, 2); A = fresh; mac(A, t, 0); store(B); if (--left == 0) break;
+                }
             }
-            o += (size_t)a.OW * Q;
         }
-        __syncthreads();
-        if (tid == 0 && b + (long long)nbuf * step < a.batch) request(b + (long long)nbuf * step, slot);
+        __syncwarp();
+        if ((tid & 31) == 0) {
+            uint32_t old;
+            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(bar0 + 64u + 4u * slot) : "memory");
+            if (old % (uint32_t)(kDwSmemThreads / 32) == (uint32_t)(kDwSmemThreads / 32 - 1))
+                if (b + (long long)nbuf * step < a.batch) request(b + (long long)nbuf * step, slot);
+        }
     }
 }
 
 bool dwconv_cin1_smem_eligible(const ConvArgs &a) {
     const long long in_bytes = (long long)a.H * a.W;
-    return a.depthwise && !a.is_u8 && a.Cin == 1 && a.Cout == 8 && a.KH == 3 && a.KW == 3 && a.kcorr != nullptr && !a.big_acc && in_bytes % 16 == 0 &&
-           in_bytes <= 32 * 1024 && a.OW <= kDwSmemThreads && a.batch >= 148 * 2 && ((uintptr_t)a.in % 16) == 0;
+    const bool rows_ok = a.off_r >= 0 && a.off_r <= 1 && a.sh * (a.OH - 1) - a.off_r + 2 <= a.H;
+    const bool cols_ok = a.off_c >= 0 && a.off_c <= 1 && a.sw * (a.OW - 1) - a.off_c + 2 <= a.W;   // at most one column outside, on either side
+    return a.depthwise && !a.is_u8 && a.Cin == 1 && a.Cout == 8 && a.KH == 3 && a.KW == 3 && a.sh == a.sw && (a.sh == 1 || a.sh == 2) && a.kcorr != nullptr &&
+           !a.big_acc && a.W % 16 == 0 && in_bytes <= 32 * 1024 && a.OW <= kDwSmemThreads && rows_ok && cols_ok && a.batch >= 148 * 2 && ((uintptr_t)a.in % 16) == 0 &&
+           ((uintptr_t)a.out % 8) == 0;
 }
 cudaError_t launch_dwconv_cin1_smem(const ConvArgs &a, int num_sms, cudaStream_t s) {
     const uint32_t in_bytes = (uint32_t)(a.H * a.W);
-    const uint32_t buf_stride = (in_bytes + 127u) & ~127u;
+    const uint32_t buf_stride = (in_bytes + 2u * (uint32_t)a.W + 127u) & ~127u;
     int nstrip = kDwSmemThreads / a.OW;
     if (nstrip > a.OH) nstrip = a.OH;
     const int rows = (a.OH + nstrip - 1) / nstrip;
     nstrip = (a.OH + rows - 1) / rows;
-    const int nbuf = 4;
+    const int per_sm = 3;
+    int nbuf = (int)(((227ll * 1024) / per_sm - 1024 - 128) / buf_stride);
+    if (nbuf > 4) nbuf = 4;
+    if (nbuf < 2) return cudaErrorInvalidConfiguration;       // cannot happen: in_bytes <= 32 KB
     const size_t smem = 128 + (size_t)nbuf * buf_stride;
     const bool full = a.lo == -128.f && a.hi == 127.f;
     using Fn = void (*)(ConvArgs, uint32_t, uint32_t, int, int, int);
-    Fn fn = full ? dwconv_cin1_smem_kernel<8, 1> : dwconv_cin1_smem_kernel<8, 0>;
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 + 4 * 32 * 1024));
+    Fn fn = a.sh == 1 ? (full ? dwconv_cin1_smem_kernel<1, true> : dwconv_cin1_smem_kernel<1, false>)
+                      : (full ? dwconv_cin1_smem_kernel<2, true> : dwconv_cin1_smem_kernel<2, false>);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
-    long long ctas = (long long)num_sms * 2;
+    long long ctas = (long long)num_sms * per_sm;
     if (ctas > a.batch) ctas = a.batch;
     fn<<<(unsigned)ctas, kDwSmemThreads, smem, s>>>(a, in_bytes, buf_stride, nbuf, nstrip, rows);
     return cudaGetLastError();

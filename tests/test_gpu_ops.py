@@ -164,7 +164,11 @@ FAST_SIMT_CASES = [
     (300, 11, 13, 8, 8, 3, 3, 2, 2, "valid", "relu6", True, "dwconv3x3_rows"),
     (300, 3, 3, 256, 256, 3, 3, 1, 1, "same", "relu6", True, "dwconv3x3_rows"),
     (300, 32, 32, 1, 8, 3, 3, 2, 2, "same", "relu6", True, "dwconv_cin1"),        # sample-resident Cin=1 kernel (layer-0 shape, scaled down)
-    (300, 20, 16, 1, 8, 3, 3, 1, 1, "valid", "relu", True, "dwconv_cin1"),                 # mixed strides stay on the generic-shape fast kernel
+    (300, 20, 16, 1, 8, 3, 3, 1, 1, "valid", "relu", True, "dwconv_cin1"),                 # same kernel, stride 1, no padding, partial clamp
+    (300, 10, 32, 1, 8, 3, 3, 1, 1, "same", "none", True, "dwconv_cin1"),                  # stride 1: a column outside on both sides
+    (300, 96, 96, 1, 8, 3, 3, 2, 2, "same", "relu6", True, "dwconv_cin1"),                 # person_detect layer 0 at full extent
+    (300, 15, 48, 1, 8, 3, 3, 2, 2, "valid", "relu6", True, "dwconv_cin1"),
+    (300, 20, 16, 1, 8, 3, 3, 2, 1, "same", "relu", True, "dwconv_cin1"),                  # mixed strides stay on the generic-shape fast kernel
     (3, 1, 1, 256, 2, 1, 1, 1, 1, "same", "none", False, "pwconv_dp4a"),            # person_detect's last conv (Cout = 2)
     (2, 4, 4, 16, 7, 1, 1, 1, 1, "same", "relu", False, "pwconv_dp4a"),
     (3, 12, 12, 8, 16, 1, 1, 1, 1, "same", "relu6", False, "pwconv_dp4a|conv_tc"),   # person_detect layer 2 shape
