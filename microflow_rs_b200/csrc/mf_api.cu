@@ -59,6 +59,10 @@ struct mf_model {
     size_t prof_chunks = 0;
     uint64_t launches = 0;
     int softmax_tail = -1;                  // index of a trailing softmax layer (its input = "logits")
+    // classifier tail run as one launch (tail_fused_kernel): layers [tail_first .. tail_last] = global average pool, 1x1 conv,
+    // reshapes, softmax.  Per-layer tracing runs the layers one by one instead.
+    int tail_first = -1, tail_conv = -1, tail_last = -1;
+    TailArgs tail;
     size_t slot_rr = 0;                     // round-robin position of the host-path stream slots
     std::mutex mu;
 };
@@ -107,6 +111,19 @@ int run_chunk(mf_model *m, Slot &s, const uint8_t *d_in, size_t n, float *d_out_
     if (prof) MF_CUDA(cudaEventRecord(prof[0], st));
     for (size_t i = 0; i < m->layers.size(); ++i) {
         const LayerExec &L = m->layers[i];
+        if ((int)i == m->tail_first && !layer_outs_host) {      // pool + conv + softmax in one launch
+            TailArgs t = m->tail;
+            t.in = cur; t.out = s.act[flip]; t.logits = d_logits; t.batch = (long long)n;
+            cudaError_t e = launch_tail_fused(t, st);
+            if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("tail_fused_kernel launch failed: ") + cudaGetErrorString(e));
+            m->launches += 1;
+            cur = t.out;
+            flip ^= 1;
+            if (prof)
+                for (size_t k = i; k <= (size_t)m->tail_last; ++k) MF_CUDA(cudaEventRecord(prof[k + 1], st));
+            i = (size_t)m->tail_last;
+            continue;
+        }
         if (d_logits && (int)i == m->softmax_tail)
             MF_CUDA(cudaMemcpyAsync(d_logits, cur, n * L.spec.in_elems, cudaMemcpyDeviceToDevice, st));
         if (L.kernel != Kernel::None) {
@@ -130,6 +147,36 @@ int run_chunk(mf_model *m, Slot &s, const uint8_t *d_in, size_t n, float *d_out_
     }
     if (d_out_q) MF_CUDA(cudaMemcpyAsync(d_out_q, cur, total, cudaMemcpyDeviceToDevice, st));
     return MF_OK;
+}
+
+// Recognises [average_pool_2d over the whole image] -> [1x1 conv_2d, <= 8 outputs, dp4a kernel] -> reshape* -> softmax (last
+// layer) and prepares the single-launch tail.  Anything else keeps the layer-by-layer path.
+void plan_tail(mf_model *m) {
+    const int n = (int)m->layers.size();
+    if (m->softmax_tail < 0) return;
+    for (int i = 0; i + 2 < n; ++i) {
+        const LayerExec &P = m->layers[(size_t)i], &C = m->layers[(size_t)i + 1];
+        if (P.kernel != Kernel::PoolGeneric || C.kernel != Kernel::PwConvDp4a) continue;
+        const LayerSpec &p = P.spec, &c = C.spec;
+        const PoolArgs &pa = P.pool;
+        // the pool window must cover the whole image from a single output position
+        if (p.is_u8 || p.OH != 1 || p.OW != 1 || -pa.off_r > 0 || -pa.off_c > 0 || -pa.off_r + p.KH < p.H || -pa.off_c + p.KW < p.W) continue;
+        if (p.Cin % 128 != 0 || p.Cin > 512 || c.H != 1 || c.W != 1 || c.Cin != p.Cin || c.Cout > 8 || c.is_u8) continue;
+        int j = i + 2;
+        while (j < n && m->layers[(size_t)j].kernel == Kernel::None) ++j;
+        if (j != m->softmax_tail || j != n - 1 || m->layers[(size_t)j].kernel != Kernel::Softmax) continue;
+        const SoftmaxArgs &sa = m->layers[(size_t)j].sm;
+        if (sa.rows * sa.cols != c.Cout) continue;
+        TailArgs &t = m->tail;
+        t = TailArgs{};
+        t.HW = p.H * p.W; t.C = p.Cin; t.N = c.Cout;
+        t.inv_len = 1.0f / (float)(p.H * p.W);      // pool_generic_kernel: __fdiv_rn(1.0f, float(len)), len = every pixel
+        t.pool_c0 = pa.c0; t.pool_c1 = pa.c1; t.pool_lo = pa.lo; t.pool_hi = pa.hi;
+        t.w = C.conv.w; t.c0z = C.conv.c0z; t.c1 = C.conv.c1; t.kcorr = C.conv.kcorr; t.conv_lo = C.conv.lo; t.conv_hi = C.conv.hi;
+        t.exp_lut = sa.exp_lut; t.sm_rows = sa.rows; t.sm_cols = sa.cols; t.out_scale = sa.out_scale; t.out_zp = sa.out_zp; t.sm_lo = sa.lo; t.sm_hi = sa.hi;
+        m->tail_first = i; m->tail_conv = i + 1; m->tail_last = j;
+        return;
+    }
 }
 
 int need_device(const mf_model *m) {
@@ -232,6 +279,7 @@ int create_model(const uint8_t *buf, size_t len, const mf_options *opt, mf_model
         }
         for (auto &L : m->layers)
             if (!L.resolve(m->d_blob, &err)) return fail(MF_ERR_CUDA, err);
+        if (impl != 1 && !std::getenv("MF_NO_TAIL_FUSE")) plan_tail(m.get());
         for (int k = 0; k < 2; ++k) {
             rc = alloc_slot(m.get(), m->slot[k]);
             if (rc) return rc;
@@ -324,7 +372,10 @@ int mf_model_layer_info(const mf_model *m, int i, mf_layer_info *o) {
     o->act_lo = L.act_lo; o->act_hi = L.act_hi;
     o->n_c0 = (int)L.c0.size(); o->n_c1 = (int)L.c1.size();
     o->macs = L.macs; o->bytes = E.alg_bytes; o->weight_bytes = E.weight_bytes;
-    std::snprintf(o->kernel, sizeof o->kernel, "%s", m->host_only ? "" : kernel_name(E.kernel));
+    const char *kn = m->host_only ? "" : kernel_name(E.kernel);
+    if (m->tail_first >= 0 && i >= m->tail_first && i <= m->tail_last && E.kernel != Kernel::None)
+        kn = i == m->tail_first ? "tail_fused_kernel" : "(in tail_fused_kernel)";
+    std::snprintf(o->kernel, sizeof o->kernel, "%s", kn);
     return MF_OK;
 }
 int mf_model_layer_constants(const mf_model *m, int i, float *c0, float *c1, int32_t *c2, int32_t *c3, int cap) {

@@ -953,6 +953,78 @@ __global__ void __launch_bounds__(256) fc_warp_kernel(FcArgs a) {
     }
 }
 
+// ================================================================================================
+// FAST: classifier tail.  One warp per sample runs average_pool_2d (whole image -> 1x1), the 1x1 conv_2d with a handful of
+// outputs and the softmax, each with exactly the arithmetic of its stand-alone kernel (pool_generic_kernel,
+// pwconv_dp4a_kernel, softmax_kernel): three launches that each move a few bytes per sample become one.
+// Lane l owns channel words l, l + 32, ... of every pixel, so the loads are fully coalesced.
+// ================================================================================================
+template <int WPL>   // channel words (4 channels) per lane: C == 128 * WPL
+__global__ void __launch_bounds__(256) tail_fused_kernel(TailArgs a) {
+    const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= a.batch) return;
+    const int CW = a.C >> 2;
+    const uint32_t *x = reinterpret_cast<const uint32_t *>(a.in + (size_t)b * a.HW * a.C);
+    int sum[WPL][4];
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) sum[k][0] = sum[k][1] = sum[k][2] = sum[k][3] = 0;
+    for (int p = 0; p < a.HW; ++p) {
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) {
+            const uint32_t v = __ldg(x + (size_t)p * CW + lane + 32 * k);
+            sum[k][0] += sx8<0>(v); sum[k][1] += sx8<1>(v); sum[k][2] += sx8<2>(v); sum[k][3] += sx8<3>(v);
+        }
+    }
+    int acc[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[o] = 0;
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) {
+        int q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float xm = __fmul_rn(a.inv_len, __int2float_rn(sum[k][u]));
+            q[u] = round_clamp(__fadd_rn(__fmul_rn(a.pool_c0, xm), a.pool_c1), a.pool_lo, a.pool_hi);
+        }
+        const int pv = (int)pack4(q[0], q[1], q[2], q[3]);
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+            if (o < a.N) acc[o] = __dp4a(pv, (int)__ldg(reinterpret_cast<const uint32_t *>(a.w) + (size_t)o * CW + lane + 32 * k), acc[o]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], off);
+    if (lane != 0) return;
+    int q[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+        q[o] = o < a.N ? (requant_nx<true>(acc[o] - __ldg(a.kcorr + o), __ldg(a.c0z + o), __ldg(a.c1 + o), a.conv_lo, a.conv_hi) & 0xff) : 0;
+    if (a.logits)
+        for (int o = 0; o < a.N; ++o) a.logits[(size_t)b * a.N + o] = (uint8_t)q[o];
+    float sumexp = 0.0f;                                            // softmax_kernel's summation order
+    for (int j = 0; j < a.sm_cols; ++j)
+        for (int i = 0; i < a.sm_rows; ++i) sumexp = __fadd_rn(sumexp, __ldg(a.exp_lut + q[i * a.sm_cols + j]));
+    for (int k = 0; k < a.N; ++k) {
+        const float t = __fadd_rn(__fdiv_rn(__fdiv_rn(__ldg(a.exp_lut + q[k]), sumexp), a.out_scale), a.out_zp);
+        a.out[(size_t)b * a.N + k] = (uint8_t)round_clamp(t, a.sm_lo, a.sm_hi);
+    }
+}
+
+cudaError_t launch_tail_fused(const TailArgs &a, cudaStream_t s) {
+    if (a.batch <= 0) return cudaSuccess;
+    if (a.C % 128 != 0 || a.C > 512 || a.N < 1 || a.N > 8 || a.sm_rows * a.sm_cols != a.N) return cudaErrorInvalidValue;
+    const unsigned grid = grid_for(a.batch * 32, 256);
+    switch (a.C / 128) {
+        case 1: tail_fused_kernel<1><<<grid, 256, 0, s>>>(a); break;
+        case 2: tail_fused_kernel<2><<<grid, 256, 0, s>>>(a); break;
+        case 3: tail_fused_kernel<3><<<grid, 256, 0, s>>>(a); break;
+        default: tail_fused_kernel<4><<<grid, 256, 0, s>>>(a); break;
+    }
+    return cudaGetLastError();
+}
+
 bool fc_warp_eligible(const FcArgs &a) { return !a.is_u8 && (a.K % 16) == 0 && a.N >= 1 && a.N <= 8; }
 cudaError_t launch_fc_warp(const FcArgs &a, cudaStream_t s) {
     if (a.batch <= 0) return cudaSuccess;

@@ -73,6 +73,24 @@ struct SoftmaxArgs {
     long long batch = 0;
 };
 
+// Classifier tail in one launch: global average pool -> 1x1 conv with <= 8 outputs -> (reshape) -> softmax.
+struct TailArgs {
+    const uint8_t *in = nullptr;     // [batch][HW][C] int8
+    uint8_t *out = nullptr;          // [batch][N] softmax output
+    uint8_t *logits = nullptr;       // optional [batch][N]: the conv output (= the softmax input)
+    int HW = 1, C = 128, N = 2;      // C % 128 == 0, N <= 8
+    float inv_len = 1.f, pool_c0 = 0.f, pool_c1 = 0.f, pool_lo = -128.f, pool_hi = 127.f;   // average_pool_2d.rs:52-56
+    const uint8_t *w = nullptr;      // conv weights [N][C]
+    const float *c0z = nullptr, *c1 = nullptr;
+    const int32_t *kcorr = nullptr;
+    float conv_lo = -128.f, conv_hi = 127.f;
+    const float *exp_lut = nullptr;
+    int sm_rows = 1, sm_cols = 1;
+    float out_scale = 1.f, out_zp = 0.f, sm_lo = -128.f, sm_hi = 127.f;
+    long long batch = 0;
+};
+cudaError_t launch_tail_fused(const TailArgs &a, cudaStream_t s);
+
 // ---- generic direct kernels: any shape / zero point / dtype; the cross-check path --------------------
 cudaError_t launch_conv_generic(const ConvArgs &a, cudaStream_t s);
 cudaError_t launch_fc_generic(const FcArgs &a, cudaStream_t s);
