@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <memory>
@@ -108,15 +109,21 @@ int run_chunk(mf_model *m, Slot &s, const uint8_t *d_in, size_t n, float *d_out_
               cudaEvent_t *prof, void *const *layer_outs_host, size_t sample_offset) {
     const uint8_t *cur = d_in;
     int flip = 0;
+    // Programmatic dependent launch between consecutive layers (mf_kernels.h): off while per-layer events or trace copies sit
+    // between the kernels, and for the first kernel of a chunk (its predecessor in the stream is a copy or another call).
+    static const bool env_pdl = [] { const char *e = std::getenv("MF_PDL"); return !e || std::atoi(e) != 0; }();
+    const bool use_pdl = env_pdl && !prof && !layer_outs_host;
+    int pdl = 0;
     if (prof) MF_CUDA(cudaEventRecord(prof[0], st));
     for (size_t i = 0; i < m->layers.size(); ++i) {
         const LayerExec &L = m->layers[i];
         if ((int)i == m->tail_first && !layer_outs_host) {      // pool + conv + softmax in one launch
             TailArgs t = m->tail;
-            t.in = cur; t.out = s.act[flip]; t.logits = d_logits; t.batch = (long long)n;
+            t.in = cur; t.out = s.act[flip]; t.logits = d_logits; t.batch = (long long)n; t.pdl = pdl;
             cudaError_t e = launch_tail_fused(t, st);
             if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("tail_fused_kernel launch failed: ") + cudaGetErrorString(e));
             m->launches += 1;
+            pdl = use_pdl;
             cur = t.out;
             flip ^= 1;
             if (prof)
@@ -124,14 +131,17 @@ int run_chunk(mf_model *m, Slot &s, const uint8_t *d_in, size_t n, float *d_out_
             i = (size_t)m->tail_last;
             continue;
         }
-        if (d_logits && (int)i == m->softmax_tail)
+        if (d_logits && (int)i == m->softmax_tail) {
             MF_CUDA(cudaMemcpyAsync(d_logits, cur, n * L.spec.in_elems, cudaMemcpyDeviceToDevice, st));
+            pdl = 0;
+        }
         if (L.kernel != Kernel::None) {
             uint8_t *dst = s.act[flip];
             std::string err;
-            cudaError_t e = L.run(cur, dst, (long long)n, m->num_sms, st, &err);
+            cudaError_t e = L.run(cur, dst, (long long)n, m->num_sms, st, &err, pdl);
             if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string(kernel_name(L.kernel)) + " launch failed: " + cudaGetErrorString(e) + " " + err);
             m->launches += 1;
+            pdl = use_pdl;
             cur = dst;
             flip ^= 1;
         }
@@ -141,7 +151,7 @@ int run_chunk(mf_model *m, Slot &s, const uint8_t *d_in, size_t n, float *d_out_
     }
     const size_t total = n * m->spec.out_elems;
     if (d_out_f32) {
-        cudaError_t e = launch_dequantize(cur, d_out_f32, total, m->spec.out_scale, (float)m->spec.out_zp, m->spec.is_u8_out, st);   // src/tensor.rs:89-92
+        cudaError_t e = launch_dequantize(cur, d_out_f32, total, m->spec.out_scale, (float)m->spec.out_zp, m->spec.is_u8_out, st, pdl);   // src/tensor.rs:89-92
         if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("dequantize launch failed: ") + cudaGetErrorString(e));
         m->launches += 1;
     }
@@ -373,6 +383,7 @@ int mf_model_layer_info(const mf_model *m, int i, mf_layer_info *o) {
     o->n_c0 = (int)L.c0.size(); o->n_c1 = (int)L.c1.size();
     o->macs = L.macs; o->bytes = E.alg_bytes; o->weight_bytes = E.weight_bytes;
     const char *kn = m->host_only ? "" : kernel_name(E.kernel);
+    if (!m->host_only) kn = E.launched_name(m->slot[0].act[0], m->slot[0].act[1], 1 << 20);   // the variant large batches run on
     if (m->tail_first >= 0 && i >= m->tail_first && i <= m->tail_last && E.kernel != Kernel::None)
         kn = i == m->tail_first ? "tail_fused_kernel" : "(in tail_fused_kernel)";
     std::snprintf(o->kernel, sizeof o->kernel, "%s", kn);
@@ -400,7 +411,7 @@ int mf_model_dump(const mf_model *m, const char *path) {
         std::fprintf(f, "layer %zu: op %d in [%d,%d,%d,%d] out [%d,%d,%d,%d] k %dx%d s %dx%d pad %d act %d izp %d ozp %d is %.9g os %.9g clamp [%d,%d] kernel %s%s%s\n", i,
                      L.op, L.in_dims[0], L.in_dims[1], L.in_dims[2], L.in_dims[3], L.out_dims[0], L.out_dims[1], L.out_dims[2], L.out_dims[3], L.KH, L.KW, L.sh,
                      L.sw, L.pad, L.act, L.in_zp, L.out_zp, L.in_scale, L.out_scale, L.act_lo, L.act_hi, m->host_only ? "-" : kernel_name(E.kernel),
-                     E.why_not_fast.empty() ? "" : "  # ", E.why_not_fast.c_str());
+                     E.why_not_fast.empty() ? (E.big_acc ? "  # accumulator range beyond 2^22" : "") : "  # ", E.why_not_fast.c_str());
         std::fprintf(f, "  c0:");
         for (float v : L.c0) std::fprintf(f, " %.9g", v);
         std::fprintf(f, "\n  c1:");
@@ -569,9 +580,11 @@ static int run_single_layer(LayerSpec &L, int impl, const void *in, void *out, s
         if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
         e = cudaMemcpy(out, d_out, batch * L.out_elems, cudaMemcpyDeviceToHost);
     } while (false);
+    const uint8_t *d_in_tag = d_in;   // only their alignment is inspected after the buffers are freed
+    uint8_t *d_out_tag = d_out;
     cleanup();
     if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string(kernel_name(E.kernel)) + ": " + cudaGetErrorString(e) + " " + err);
-    g_err = kernel_name(E.kernel);   // lets tests see which kernel ran
+    g_err = E.launched_name(d_in_tag, d_out_tag, (long long)batch);   // lets tests see which kernel ran
     return MF_OK;
 }
 

@@ -202,12 +202,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
 
     if (warp == kWarpTma) {
         if (lane == 0) {
             // ===== TMA producer =====
             mbar_expect_tx(bfull_bar, p.nkb * p.b_block_bytes);
             for (uint32_t kb = 0; kb < p.nkb; ++kb) tma_load_2d(smem_u32(sB + (size_t)kb * p.b_block_bytes), &tmap_b, bfull_bar, (int)(kb * 128), 0);
+            pdl_wait();       // the weights above are static; the activations below are the previous kernel's output
             uint32_t s = 0, ph = 0;
             for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 uint32_t b, rem, ty, tx;
@@ -273,6 +275,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int row = (int)(q * 32 + lane);
             const int rr = row >> p.tw_log2, rc = row & (p.TW - 1);
             const float lo = p.lo, hi = p.hi;
+            pdl_wait();       // stores must not overtake the previous kernel's reads of the ping-pong buffer
             uint32_t it = 0;
             for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const uint32_t acc = it & 1, aph = (it >> 1) & 1;
@@ -295,28 +298,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     uint32_t w[8];
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
-                        int y[4];
+                        // PACKED (XU && !BIG): the correction table holds kAccBias - corr, so acc + table is the pre-biased
+                        // accumulator of requant4_biased (packed FADD2 epilogue, no I2F); otherwise table = corr
+                        constexpr bool PACKED = XU && !BIG;
+                        float zz[4], ss[4];
+                        int kk[4];
                         if (TAB == kTabSmem) {
                             const float4 z = *reinterpret_cast<const float4 *>(s_c0z + c0 + 4 * g);
                             const float4 sc = *reinterpret_cast<const float4 *>(s_c1 + c0 + 4 * g);
                             const int4 kc = *reinterpret_cast<const int4 *>(corr + c0 + 4 * g);
-                            const float zz[4] = {z.x, z.y, z.z, z.w}, ss[4] = {sc.x, sc.y, sc.z, sc.w};
-                            const int kk[4] = {kc.x, kc.y, kc.z, kc.w};
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int a = (int)r[4 * g + u] - kk[u];
-                                y[u] = XU ? requant_xu<true>(a, zz[u], ss[u], lo, hi) : requant_nx<BIG>(a, zz[u], ss[u], lo, hi);
-                            }
+                            zz[0] = z.x; zz[1] = z.y; zz[2] = z.z; zz[3] = z.w;
+                            ss[0] = sc.x; ss[1] = sc.y; ss[2] = sc.z; ss[3] = sc.w;
+                            kk[0] = kc.x; kk[1] = kc.y; kk[2] = kc.z; kk[3] = kc.w;
                         } else {
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 // kTabPeriod: the tables repeat every 32 columns; kTabGroup: N <= 128, this warp's only chunk is 32 * CG
                                 const int n = (TAB == kTabPeriod ? 0 : 32 * CG) + 4 * g + u;
-                                const int a = (int)r[4 * g + u] - tab.corr[n];
-                                y[u] = XU ? requant_xu<true>(a, tab.c0z[n], tab.c1[n], lo, hi) : requant_nx<BIG>(a, tab.c0z[n], tab.c1[n], lo, hi);
+                                zz[u] = tab.c0z[n]; ss[u] = tab.c1[n]; kk[u] = tab.corr[n];
                             }
                         }
-                        w[g] = pack4(y[0], y[1], y[2], y[3]);
+                        if (PACKED) {
+                            w[g] = requant4_biased<true>((int)r[4 * g] + kk[0], (int)r[4 * g + 1] + kk[1], (int)r[4 * g + 2] + kk[2], (int)r[4 * g + 3] + kk[3],
+                                                         make_float4(zz[0], zz[1], zz[2], zz[3]), make_float4(ss[0], ss[1], ss[2], ss[3]), lo, hi);
+                        } else {
+                            int y[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int a = (int)r[4 * g + u] - kk[u];
+                                y[u] = XU ? requant_xu<true>(a, zz[u], ss[u], lo, hi) : requant_nx<BIG>(a, zz[u], ss[u], lo, hi);
+                            }
+                            w[g] = pack4(y[0], y[1], y[2], y[3]);
+                        }
                     }
                     if (valid) {
                         uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
@@ -498,6 +511,7 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     ConvTcTables tab;
     std::memcpy(tab.c0z, p.h_c0z.data(), (size_t)p.N * 4);
     std::memcpy(tab.c1, p.h_c1.data(), (size_t)p.N * 4);
+    const bool packed_epilogue = p.lo == -128.f && p.hi == 127.f && !p.big_acc;   // == the kernel's XU && !BIG (MF_TC_XUG=0 clears it below)
     std::memcpy(tab.corr, p.h_corr.data(), (size_t)p.ncls * p.N * 4);
     k.N = p.N; k.CB = p.CB; k.KH = p.KH; k.KW = p.KW; k.TW = p.TW; k.TH = p.TH;
     k.tw_log2 = 0;
@@ -523,6 +537,8 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     // the F2I.S8 / I2F epilogue needs the full int8 clamp range (F2I.S8 saturation is the clamp); MF_TC_XUG=0 forces the XU-free one
     static const int env_xug = [] { const char *e = std::getenv("MF_TC_XUG"); return e ? std::atoi(e) : -1; }();
     const bool xu = p.lo == -128.f && p.hi == 127.f && env_xug != 0;
+    if (xu && packed_epilogue)   // pre-biased accumulators: the table entry is added, not subtracted (conv_tc_kernel, PACKED)
+        for (int k = 0; k < p.ncls * p.N; ++k) tab.corr[k] = kAccBias - tab.corr[k];
     const int shape = (p.KH == 3 && p.KW == 3 && p.CB == 1) ? 1 : ((p.KH == 1 && p.KW == 1 && p.CB == 1) ? 2 : ((p.KH == 1 && p.KW == 1 && p.CB == 2) ? 3 : 0));
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const ConvTcTables, const ConvTcParams);
     KernelFn fn = nullptr;
@@ -559,8 +575,7 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
         }
     }
     const unsigned grid = (unsigned)(k.num_tiles < num_sms ? k.num_tiles : num_sms);
-    fn<<<grid, kThreads, p.smem_bytes, s>>>(ta, tb, tab, k);
-    return cudaGetLastError();
+    return launch_pdl(fn, dim3(grid), dim3(kThreads), p.smem_bytes, s, l.pdl, ta, tb, tab, k);
 }
 
 }  // namespace mf

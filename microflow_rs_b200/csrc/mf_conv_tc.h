@@ -49,6 +49,7 @@ struct ConvTcLaunch {
     uint8_t *out = nullptr;
     long long W = 0, H = 1, B = 1;  // tensor-map extents of the activations (in packed rows for pointwise)
     long long OW = 0, OH = 1;       // output extents (== W, H for stride-1 SAME)
+    int pdl = 0;                    // programmatic dependent launch (mf_kernels.h)
 };
 
 // Host-side packing helpers (pure functions, tested on CPU)

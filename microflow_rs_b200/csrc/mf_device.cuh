@@ -85,6 +85,46 @@ template <bool FULL> __device__ __forceinline__ int requant_xu(int acc, float c0
     return y;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Four values per call, fewest issue slots (the hot kernels are bound by issue slots, profiles/r01h_*):
+//   * the accumulators arrive PRE-BIASED: a = 0x4B400000 + acc (the bias rides in the dp4a accumulator init or in the
+//     correction term that is added anyway), |acc| <= 2^22, so as_float(a) - 1.5*2^23 == float(acc) exactly -- one packed
+//     FADD2 per two values instead of one I2F (XU pipe) each;
+//   * the two epilogue adds are packed FADD2 (add.rn.f32x2: two independent IEEE RN adds, one issue slot).  The multiply
+//     stays scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false (checked in SASS),
+//     which would round once instead of twice and break bit-exactness; FMUL + FADD2 is never contracted.
+//   4 values: 2 FADD2 + 4 FMUL + 2 FADD2 + 4 LOP3 + 2 FADD2 + 4 F2I.S8 + 3 PRMT = 21 issue slots (was 27).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kAccBias = 0x4B400000;   // bits of 1.5 * 2^23 = 12582912.0f
+
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+template <bool FULL> __device__ __forceinline__ int round_sat_s8(float s, float lo, float hi) {
+    if (!FULL) s = fminf(fmaxf(s, lo), hi);
+    int y;
+    asm("cvt.rzi.sat.s8.f32 %0, %1;" : "=r"(y) : "f"(s));      // trunc, saturate to int8, NaN -> 0 (Rust's `as i8`)
+    return y;
+}
+// two pre-biased accumulators -> two values in [lo, hi]
+template <bool FULL> __device__ __forceinline__ void requant2_biased(int a0, int a1, float z0, float z1, float s0, float s1, float lo, float hi, int &y0, int &y1) {
+    const float2 f = fadd2(make_float2(__int_as_float(a0), __int_as_float(a1)), make_float2(-12582912.0f, -12582912.0f));
+    const float2 t = fadd2(make_float2(z0, z1), make_float2(__fmul_rn(s0, f.x), __fmul_rn(s1, f.y)));
+    const float2 r = fadd2(t, make_float2(round_bias(t.x), round_bias(t.y)));
+    y0 = round_sat_s8<FULL>(r.x, lo, hi);
+    y1 = round_sat_s8<FULL>(r.y, lo, hi);
+}
+template <bool FULL> __device__ __forceinline__ uint32_t requant4_biased(int a0, int a1, int a2, int a3, float4 z, float4 s, float lo, float hi) {
+    int y0, y1, y2, y3;
+    requant2_biased<FULL>(a0, a1, z.x, z.y, s.x, s.y, lo, hi, y0, y1);
+    requant2_biased<FULL>(a2, a3, z.z, z.w, s.z, s.w, lo, hi, y2, y3);
+    return pack4(y0, y1, y2, y3);
+}
+
 // sign-extended byte k of a packed word: one PRMT (selector msb = replicate the sign of the selected byte)
 template <int K> __device__ __forceinline__ int sx8(uint32_t w) {
     int r;

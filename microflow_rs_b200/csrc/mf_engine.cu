@@ -66,13 +66,15 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
             else for (size_t k = 0; k < (size_t)taps * L.Cin; ++k) s += elem_i(L.w[(size_t)co * taps * L.Cin + k], L.is_u8);
             kcorr[(size_t)co] = L.in_zp * s;
         }
-        // can |acc - kcorr| exceed 2^22 ?  (bound: sum |w| * 128 + |kcorr|)  -> selects the general exact int->float
+        // can the corrected accumulator exceed 2^22 ?  It equals sum_valid (v - in_zp) * w whatever the kernel does with borders
+        // (zero-point padding, zero fill + border-class table, masked weights), and |v - in_zp| <= 255, so 255 * sum |w| bounds
+        // it rigorously.  Beyond 2^22 the kernels take the general exact int -> float conversion instead of the biased one.
         big_acc = false;
         for (int co = 0; co < Cout; ++co) {
             long long sa = 0;
             if (dw) for (int t = 0; t < taps; ++t) sa += std::abs(elem_i(L.w[(size_t)t * Cout + co], L.is_u8));
             else for (size_t k = 0; k < (size_t)taps * L.Cin; ++k) sa += std::abs(elem_i(L.w[(size_t)co * taps * L.Cin + k], L.is_u8));
-            if (sa * 128 + std::llabs((long long)kcorr[(size_t)co]) > (1ll << 22)) big_acc = true;
+            if (sa * 255 > (1ll << 22)) big_acc = true;
         }
         o_w = bb.add(L.w.data(), L.w.size());
         o_wzp = bb.add(wzp.data(), wzp.size() * 4);
@@ -160,7 +162,7 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
             for (int j = 0; j < L.Cout; ++j) {
                 long long sa = 0;
                 for (int k = 0; k < L.Cin; ++k) sa += std::abs(elem_i(L.w[(size_t)j * L.Cin + k], false));
-                big = std::max(big, sa * 128 + std::llabs((long long)L.c2[(size_t)j]));
+                big = std::max(big, sa * 255);     // acc - c2[j] = sum (x - in_zp) * w  (w_zp == 0)
             }
             big_acc = big > (1ll << 22);
             tc = ConvTcPlan{};
@@ -241,12 +243,23 @@ bool LayerExec::resolve(const uint8_t *d, std::string *err) {
     return true;
 }
 
-cudaError_t LayerExec::run(const uint8_t *in, uint8_t *out, long long batch, int num_sms, cudaStream_t s, std::string *err) const {
+const char *LayerExec::launched_name(const uint8_t *in, uint8_t *out, long long batch) const {
+    if (kernel == Kernel::DwConv3x3Rows || kernel == Kernel::DwConvCin1) {
+        static const bool no_smem = std::getenv("MF_DW_NO_SMEM") != nullptr;
+        ConvArgs a = conv;
+        a.in = in; a.out = out; a.batch = batch;
+        if (!no_smem && kernel == Kernel::DwConv3x3Rows && dwconv3x3_smem_eligible(a)) return "dwconv3x3_smem_kernel";
+        if (!no_smem && kernel == Kernel::DwConvCin1 && dwconv_cin1_smem_eligible(a)) return "dwconv_cin1_smem_kernel";
+    }
+    return kernel_name(kernel);
+}
+
+cudaError_t LayerExec::run(const uint8_t *in, uint8_t *out, long long batch, int num_sms, cudaStream_t s, std::string *err, int pdl) const {
     switch (kernel) {
         case Kernel::None: return cudaSuccess;
         case Kernel::ConvGeneric: case Kernel::PwConvDp4a: case Kernel::DwConvC4: case Kernel::DwConv3x3Rows: case Kernel::DwConvCin1: {
             ConvArgs a = conv;
-            a.in = in; a.out = out; a.batch = batch;
+            a.in = in; a.out = out; a.batch = batch; a.pdl = pdl;
             if (kernel == Kernel::ConvGeneric) return launch_conv_generic(a, s);
             if (kernel == Kernel::PwConvDp4a) return launch_pwconv_dp4a(a, s);
             if (kernel == Kernel::DwConvC4) return launch_dwconv_c4(a, s);
@@ -263,20 +276,20 @@ cudaError_t LayerExec::run(const uint8_t *in, uint8_t *out, long long batch, int
         }
         case Kernel::ConvTcPointwise: {
             ConvTcLaunch l;
-            l.in = in; l.out = out;
+            l.in = in; l.out = out; l.pdl = pdl;
             l.W = l.OW = batch * spec.OH * spec.OW / tc_P;
             l.H = l.OH = 1; l.B = 1;
             return conv_tc_launch(tc, l, num_sms, s, err);
         }
         case Kernel::ConvTc3x3: {
             ConvTcLaunch l;
-            l.in = in; l.out = out;
+            l.in = in; l.out = out; l.pdl = pdl;
             l.W = l.OW = spec.W; l.H = l.OH = spec.H; l.B = batch;
             return conv_tc_launch(tc, l, num_sms, s, err);
         }
         case Kernel::FcTc: {
             ConvTcLaunch l;
-            l.in = in; l.out = out;
+            l.in = in; l.out = out; l.pdl = pdl;
             l.W = l.OW = batch; l.H = l.OH = 1; l.B = 1;
             return conv_tc_launch(tc, l, num_sms, s, err);
         }

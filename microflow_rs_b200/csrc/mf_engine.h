@@ -57,7 +57,9 @@ struct LayerExec {
     // impl: 0 auto, 1 generic only, 2 auto without tensor cores
     void plan(BlobBuilder &bb, int impl, bool have_device);
     bool resolve(const uint8_t *d_blob, std::string *err);
-    cudaError_t run(const uint8_t *in, uint8_t *out, long long batch, int num_sms, cudaStream_t s, std::string *err) const;
+    cudaError_t run(const uint8_t *in, uint8_t *out, long long batch, int num_sms, cudaStream_t s, std::string *err, int pdl = 0) const;
+    // name of the kernel run() launches for these buffers / this batch (two depthwise kernels pick a sample-resident variant at run time)
+    const char *launched_name(const uint8_t *in, uint8_t *out, long long batch) const;
 };
 
 }  // namespace mf

@@ -176,6 +176,8 @@ __global__ void __launch_bounds__(256) quantize_kernel(const float *in, uint8_t 
 template <bool U8>
 __global__ void __launch_bounds__(256) dequantize_kernel(const uint8_t *in, float *out, size_t n, float scale, float zp) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (idx >= n) return;
     out[idx] = __fmul_rn(scale, __fsub_rn(__int2float_rn(ld_elem<U8>(in + idx)), zp));
 }
@@ -184,11 +186,11 @@ cudaError_t launch_quantize(const float *in, uint8_t *out, size_t n, float scale
     quantize_kernel<<<grid_for((long long)n, 256), 256, 0, s>>>(in, out, n, scale, zp, is_u8 ? 0.f : -128.f, is_u8 ? 255.f : 127.f);
     return cudaGetLastError();
 }
-cudaError_t launch_dequantize(const uint8_t *in, float *out, size_t n, float scale, float zp, int is_u8, cudaStream_t s) {
+cudaError_t launch_dequantize(const uint8_t *in, float *out, size_t n, float scale, float zp, int is_u8, cudaStream_t s, int pdl) {
     if (!n) return cudaSuccess;
-    if (is_u8) dequantize_kernel<true><<<grid_for((long long)n, 256), 256, 0, s>>>(in, out, n, scale, zp);
-    else dequantize_kernel<false><<<grid_for((long long)n, 256), 256, 0, s>>>(in, out, n, scale, zp);
-    return cudaGetLastError();
+    const dim3 grid(grid_for((long long)n, 256));
+    if (is_u8) return launch_pdl(dequantize_kernel<true>, grid, dim3(256), 0, s, pdl, in, out, n, scale, zp);
+    return launch_pdl(dequantize_kernel<false>, grid, dim3(256), 0, s, pdl, in, out, n, scale, zp);
 }
 
 // ================================================================================================
@@ -422,12 +424,22 @@ __device__ __forceinline__ void transpose_3x4(uint32_t v0, uint32_t v1, uint32_t
     t[2] = prmt<0x6610>(hi, v2);
     t[3] = prmt<0x7732>(hi, v2);
 }
+// Slot layout (kDwHead bytes of header, then nbuf slots of buf_stride bytes, then kDwTail bytes):
+//   header: nbuf "sample landed" mbarriers at +0, nbuf "warps finished with this slot" counters at +64
+//   slot:   [one row of in_zp][the sample, filled by one cp.async.bulk][one row of in_zp]
+// A thread addresses its window with ONE pointer: the three columns are at p, p + 4G and p + 8G bytes (G = channel words per
+// pixel, a uniform offset) and a new input row is one pointer add.  A window column outside the image therefore reads
+// whatever lies one pixel left / right in memory (the neighbouring row, the header or the tail padding): its three weight
+// bytes are zeroed in that thread's registers, so the garbage is multiplied by 0, and the thread's correction term only sums
+// the weights that remain -- exactly the reference's masked filter sum (conv_2d.rs:83-89 / depthwise_conv_2d.rs:80-86).
+constexpr uint32_t kDwHead = 512, kDwTail = 256;     // >= 4 * (C / 4) bytes for C <= 256 on either side
+
 template <int S, bool FULL, int MINB>
 __global__ void __launch_bounds__(kDwSmemThreads, MINB) dwconv3x3_smem_kernel(ConvArgs a, uint32_t in_bytes, uint32_t buf_stride, int nbuf, int xw, int nstrip,
                                                                             int rows_per_strip) {
     extern __shared__ __align__(128) uint8_t dsm[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(dsm);                 // nbuf "sample landed" mbarriers (<= 8) ...
-    uint8_t *bufs = dsm + 128;                                          // ... and, at dsm + 64, nbuf "warps finished with this slot" counters
+    uint64_t *bars = reinterpret_cast<uint64_t *>(dsm);
+    uint8_t *bufs = dsm + kDwHead;
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
     const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(bufs);
     const int tid = threadIdx.x;
@@ -457,84 +469,92 @@ __global__ void __launch_bounds__(kDwSmemThreads, MINB) dwconv3x3_smem_kernel(Co
                      "l"(a.in + (size_t)b * in_bytes), "r"(in_bytes), "r"(bar0 + 8u * slot)
                      : "memory");
     };
-    if (tid == 0)
+    pdl_trigger();
+    if (tid == 0) {                                                     // the input is the previous kernel's output: first access after pdl_wait
+        pdl_wait();
         for (int k = 0; k < nbuf; ++k)
             if (first + (long long)k * step < a.batch) request(first + (long long)k * step, k);
+    }
 
     const bool active = tid < xw * nstrip;
     const int strip = active ? tid / xw : 0;
     const int x = active ? tid - strip * xw : 0;
     const int j = x / G, g = x - j * G;
-    // wq[T][c] = (w[T][0][c], w[T][1][c], w[T][2][c], 0): the three taps of kernel row T of channel 4g + c
+    const int c0 = S * j - a.off_c;
+    // wq[T][c] = (w[T][0][c], w[T][1][c], w[T][2][c], 0): the three taps of kernel row T of channel 4g + c, with the taps of
+    // window columns outside the image zeroed
     uint32_t wq[3][4];
+    int fresh[4];                                                       // accumulator init: float-conversion bias - in_zp * (sum of the remaining weights)
     {
         const uint32_t *ww = reinterpret_cast<const uint32_t *>(a.w);
+        uint32_t keep = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if ((unsigned)(c0 + k) < (unsigned)a.W) keep |= 0xffu << (8 * k);
+        int wsum[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int T = 0; T < 3; ++T) {
             transpose_3x4(__ldg(ww + (size_t)(3 * T) * G + g), __ldg(ww + (size_t)(3 * T + 1) * G + g), __ldg(ww + (size_t)(3 * T + 2) * G + g), wq[T]);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) wq[T][c] &= 0x00ffffffu;
+            for (int c = 0; c < 4; ++c) {
+                wq[T][c] &= keep;
+                wsum[c] = __dp4a((int)wq[T][c], 0x01010101, wsum[c]);
+            }
         }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) fresh[c] = kAccBias - a.in_zp * wsum[c];
     }
-    const int4 kc = __ldg(reinterpret_cast<const int4 *>(a.kcorr) + g);
     const float4 z = __ldg(reinterpret_cast<const float4 *>(a.c0z) + g);
     const float4 sc = __ldg(reinterpret_cast<const float4 *>(a.c1) + g);
-    const int c0 = S * j - a.off_c;
     const int i0 = strip * rows_per_strip;
     const int i1 = active ? min(a.OH, i0 + rows_per_strip) : i0;
     const int out_row_words = a.OW * G;
     const float lo = a.lo, hi = a.hi;
-    // byte offset (inside a slot) of window column k at the first input row of this strip, and its per-row stride
-    uint32_t off[3], stride[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const bool ok = (unsigned)(c0 + k) < (unsigned)a.W;
-        off[k] = ok ? (uint32_t)((int)row_bytes * (1 + S * i0 - a.off_r) + ((c0 + k) * G + g) * 4) : 0u;
-        stride[k] = ok ? row_bytes : 0u;
-    }
+    // word offset (inside a slot) of window column 0 at the first input row of this strip; may be negative by up to G words
+    const int poff = (int)(row_bytes >> 2) * (1 + S * i0 - a.off_r) + c0 * G + g;
+    const int row_words = (int)(row_bytes >> 2);
 
+    pdl_wait();                                                         // every thread: its stores must not overtake the previous kernel's reads
     uint32_t it = 0;
     for (long long b = first; b < a.batch; b += step, ++it) {
         const int slot = (int)(it % (uint32_t)nbuf);
         sm_mbar_wait(bar0 + 8u * slot, (it / (uint32_t)nbuf) & 1u);
         if (i1 > i0) {
-            const uint32_t base = buf0 + (uint32_t)slot * buf_stride;
-            uint32_t p0 = base + off[0], p1 = base + off[1], p2 = base + off[2];
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(bufs + (size_t)slot * buf_stride) + poff;
             uint32_t *o = reinterpret_cast<uint32_t *>(a.out) + ((size_t)b * a.OH + i0) * out_row_words + x;
             auto take = [&](uint32_t (&t)[4]) {                         // the next input row, transposed
-                const uint32_t v0 = lds_u32(p0), v1 = lds_u32(p1), v2 = lds_u32(p2);
-                p0 += stride[0]; p1 += stride[1]; p2 += stride[2];
+                const uint32_t v0 = p[0], v1 = p[G], v2 = p[2 * G];
+                p += row_words;
                 transpose_3x4(v0, v1, v2, t);
             };
             struct Acc { int c[4]; };
-            const Acc fresh = {{-kc.x, -kc.y, -kc.z, -kc.w}};           // the zero-point correction rides in the accumulator init
+            const Acc init = {{fresh[0], fresh[1], fresh[2], fresh[3]}};
             auto mac = [&](Acc &A, const uint32_t (&t)[4], int T) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) A.c[c] = __dp4a((int)t[c], (int)wq[T][c], A.c[c]);
             };
             auto store = [&](const Acc &A) {
-                *o = pack4(requant_xu<FULL>(A.c[0], z.x, sc.x, lo, hi), requant_xu<FULL>(A.c[1], z.y, sc.y, lo, hi), requant_xu<FULL>(A.c[2], z.z, sc.z, lo, hi),
-                           requant_xu<FULL>(A.c[3], z.w, sc.w, lo, hi));
+                *o = requant4_biased<FULL>(A.c[0], A.c[1], A.c[2], A.c[3], z, sc, lo, hi);
                 o += out_row_words;
             };
             uint32_t t[4];
-            Acc A = fresh, B = fresh, C = fresh;
+            Acc A = init, B = init, C = init;
             int left = i1 - i0;
             if (S == 1) {
                 take(t); mac(A, t, 0);
                 take(t); mac(A, t, 1); mac(B, t, 0);
                 while (true) {
-                    take(t); mac(A, t, 2); mac(B, t, 1); C = fresh; mac(C, t, 0); store(A); if (--left == 0) break;
-                    take(t); mac(B, t, 2); mac(C, t, 1); A = fresh; mac(A, t, 0); store(B); if (--left == 0) break;
-                    take(t); mac(C, t, 2); mac(A, t, 1); B = fresh; mac(B, t, 0); store(C); if (--left == 0) break;
+                    take(t); mac(A, t, 2); mac(B, t, 1); C = init; mac(C, t, 0); store(A); if (--left == 0) break;
+                    take(t); mac(B, t, 2); mac(C, t, 1); A = init; mac(A, t, 0); store(B); if (--left == 0) break;
+                    take(t); mac(C, t, 2); mac(A, t, 1); B = init; mac(B, t, 0); store(C); if (--left == 0) break;
                 }
             } else {                                                    // stride 2: every second input row closes one output row and opens the next
                 take(t); mac(A, t, 0);
                 while (true) {
                     take(t); mac(A, t, 1);
-                    take(t); mac(A, t, 2); B = fresh; mac(B, t, 0); store(A); if (--left == 0) break;
+                    take(t); mac(A, t, 2); B = init; mac(B, t, 0); store(A); if (--left == 0) break;
                     take(t); mac(B, t, 1);
-                    take(t); mac(B, t, 2); A = fresh; mac(A, t, 0); store(B); if (--left == 0) break;
+                    take(t); mac(B, t, 2); A = init; mac(A, t, 0); store(B); if (--left == 0) break;
                 }
             }
         }
@@ -557,7 +577,9 @@ bool dwconv3x3_smem_eligible(const ConvArgs &a) {
     const int xw = a.OW * (a.Cout / 4);
     // rows read: -off_r .. sh*(OH-1) - off_r + 2; the slot holds rows -1 .. H
     const bool rows_ok = a.off_r <= 1 && a.off_r >= 0 && a.sh * (a.OH - 1) - a.off_r + 2 <= a.H;
-    return in_bytes % 16 == 0 && ((long long)a.W * a.Cin) % 16 == 0 && in_bytes <= 48 * 1024 && xw <= kDwSmemThreads && rows_ok && a.batch >= 148 * 2 &&
+    return in_bytes % 16 == 0 && ((long long)a.W * a.Cin) % 16 == 0 && in_bytes <= 48 * 1024 && xw <= kDwSmemThreads && rows_ok && a.batch >= 148 * 2 && a.Cout <= 256 &&
+           a.off_c >= 0 && a.off_c <= 1 &&   // a window column outside the image is at most one pixel (<= kDwTail bytes) away
+          
            ((uintptr_t)a.in % 16) == 0;
 }
 cudaError_t launch_dwconv3x3_smem(const ConvArgs &a, int num_sms, cudaStream_t s) {
@@ -574,13 +596,13 @@ cudaError_t launch_dwconv3x3_smem(const ConvArgs &a, int num_sms, cudaStream_t s
     // a ring of >= 2 sample slots (<= 4) in its share of the 227 KB
     int per_sm = minb, nbuf = 0;
     for (; per_sm >= 1; --per_sm) {
-        const long long share = (227ll * 1024) / per_sm - 1024 - 128;
+        const long long share = (227ll * 1024) / per_sm - 1024 - (long long)(kDwHead + kDwTail);
         nbuf = (int)(share / buf_stride);
         if (nbuf > 4) nbuf = 4;
         if (nbuf >= 2 || per_sm == 1) break;
     }
     if (nbuf < 1) return cudaErrorInvalidConfiguration;
-    const size_t smem = 128 + (size_t)nbuf * buf_stride;
+    const size_t smem = kDwHead + (size_t)nbuf * buf_stride + kDwTail;
     const bool full = a.lo == -128.f && a.hi == 127.f;          // F2I.S8 saturation doubles as the clamp
     using Fn = void (*)(ConvArgs, uint32_t, uint32_t, int, int, int, int);
     Fn fn = nullptr;
@@ -592,8 +614,7 @@ cudaError_t launch_dwconv3x3_smem(const ConvArgs &a, int num_sms, cudaStream_t s
     if (e != cudaSuccess) return e;
     long long ctas = (long long)num_sms * per_sm;
     if (ctas > a.batch) ctas = a.batch;
-    fn<<<(unsigned)ctas, kDwSmemThreads, smem, s>>>(a, in_bytes, buf_stride, nbuf, xw, nstrip, rows);
-    return cudaGetLastError();
+    return launch_pdl(fn, dim3((unsigned)ctas), dim3(kDwSmemThreads), smem, s, a.pdl, a, in_bytes, buf_stride, nbuf, xw, nstrip, rows);
 }
 
 bool dwconv3x3_rows_eligible(const ConvArgs &a) {
@@ -719,9 +740,12 @@ __global__ void __launch_bounds__(kDwSmemThreads, 3) dwconv_cin1_smem_kernel(Con
                      "l"(a.in + (size_t)b * in_bytes), "r"(in_bytes), "r"(bar0 + 8u * slot)
                      : "memory");
     };
-    if (tid == 0)
+    pdl_trigger();
+    if (tid == 0) {
+        pdl_wait();
         for (int k = 0; k < nbuf; ++k)
             if (first + (long long)k * step < a.batch) request(first + (long long)k * step, k);
+    }
 
     const bool active = tid < a.OW * nstrip;
     const int strip = active ? tid / a.OW : 0;
@@ -736,7 +760,7 @@ __global__ void __launch_bounds__(kDwSmemThreads, 3) dwconv_cin1_smem_kernel(Con
     int kcr[COUT];
     float zr[COUT], sr[COUT];
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) { kcr[c] = -__ldg(a.kcorr + c); zr[c] = __ldg(a.c0z + c); sr[c] = __ldg(a.c1 + c); }
+    for (int c = 0; c < COUT; ++c) { kcr[c] = kAccBias - __ldg(a.kcorr + c); zr[c] = __ldg(a.c0z + c); sr[c] = __ldg(a.c1 + c); }   // pre-biased accumulators (mf_device.cuh)
     const int c0 = S * j - a.off_c;                                     // leftmost window column, >= -1
     const int w0 = (c0 >= 0 ? c0 : c0 - 3) / 4;                         // floor(c0 / 4): the aligned word holding it
     const uint32_t kk = (uint32_t)(c0 - 4 * w0);                        // its byte inside that word
@@ -749,6 +773,7 @@ __global__ void __launch_bounds__(kDwSmemThreads, 3) dwconv_cin1_smem_kernel(Con
     const uint32_t off_lo = lo_ok ? first_row_off + 4u * (uint32_t)w0 : 0u, off_hi = hi_ok ? first_row_off + 4u * (uint32_t)(w0 + 1) : 0u;
     const uint32_t st_lo = lo_ok ? row_bytes : 0u, st_hi = hi_ok ? row_bytes : 0u;
 
+    pdl_wait();
     uint32_t it = 0;
     for (long long b = first; b < a.batch; b += step, ++it) {
         const int slot = (int)(it % (uint32_t)nbuf);
@@ -773,10 +798,8 @@ __global__ void __launch_bounds__(kDwSmemThreads, 3) dwconv_cin1_smem_kernel(Con
                 for (int c = 0; c < COUT; ++c) A.c[c] = __dp4a((int)t, (int)wq[T][c], A.c[c]);
             };
             auto store = [&](const Acc &A) {
-                int y[COUT];
-#pragma unroll
-                for (int c = 0; c < COUT; ++c) y[c] = requant_xu<FULL>(A.c[c], zr[c], sr[c], lo, hi);
-                *o = make_uint2(pack4(y[0], y[1], y[2], y[3]), pack4(y[4], y[5], y[6], y[7]));
+                *o = make_uint2(requant4_biased<FULL>(A.c[0], A.c[1], A.c[2], A.c[3], make_float4(zr[0], zr[1], zr[2], zr[3]), make_float4(sr[0], sr[1], sr[2], sr[3]), lo, hi),
+                                requant4_biased<FULL>(A.c[4], A.c[5], A.c[6], A.c[7], make_float4(zr[4], zr[5], zr[6], zr[7]), make_float4(sr[4], sr[5], sr[6], sr[7]), lo, hi));
                 o += a.OW;
             };
             Acc A = fresh, B = fresh, C = fresh;
@@ -838,8 +861,7 @@ cudaError_t launch_dwconv_cin1_smem(const ConvArgs &a, int num_sms, cudaStream_t
     if (e != cudaSuccess) return e;
     long long ctas = (long long)num_sms * per_sm;
     if (ctas > a.batch) ctas = a.batch;
-    fn<<<(unsigned)ctas, kDwSmemThreads, smem, s>>>(a, in_bytes, buf_stride, nbuf, nstrip, rows);
-    return cudaGetLastError();
+    return launch_pdl(fn, dim3((unsigned)ctas), dim3(kDwSmemThreads), smem, s, a.pdl, a, in_bytes, buf_stride, nbuf, nstrip, rows);
 }
 
 bool dwconv_cin1_eligible(const ConvArgs &a) {
@@ -963,6 +985,8 @@ template <int WPL>   // channel words (4 channels) per lane: C == 128 * WPL
 __global__ void __launch_bounds__(256) tail_fused_kernel(TailArgs a) {
     const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();
     if (b >= a.batch) return;
     const int CW = a.C >> 2;
     const uint32_t *x = reinterpret_cast<const uint32_t *>(a.in + (size_t)b * a.HW * a.C);
@@ -1017,12 +1041,11 @@ cudaError_t launch_tail_fused(const TailArgs &a, cudaStream_t s) {
     if (a.C % 128 != 0 || a.C > 512 || a.N < 1 || a.N > 8 || a.sm_rows * a.sm_cols != a.N) return cudaErrorInvalidValue;
     const unsigned grid = grid_for(a.batch * 32, 256);
     switch (a.C / 128) {
-        case 1: tail_fused_kernel<1><<<grid, 256, 0, s>>>(a); break;
-        case 2: tail_fused_kernel<2><<<grid, 256, 0, s>>>(a); break;
-        case 3: tail_fused_kernel<3><<<grid, 256, 0, s>>>(a); break;
-        default: tail_fused_kernel<4><<<grid, 256, 0, s>>>(a); break;
+        case 1: return launch_pdl(tail_fused_kernel<1>, dim3(grid), dim3(256), 0, s, a.pdl, a);
+        case 2: return launch_pdl(tail_fused_kernel<2>, dim3(grid), dim3(256), 0, s, a.pdl, a);
+        case 3: return launch_pdl(tail_fused_kernel<3>, dim3(grid), dim3(256), 0, s, a.pdl, a);
+        default: return launch_pdl(tail_fused_kernel<4>, dim3(grid), dim3(256), 0, s, a.pdl, a);
     }
-    return cudaGetLastError();
 }
 
 bool fc_warp_eligible(const FcArgs &a) { return !a.is_u8 && (a.K % 16) == 0 && a.N >= 1 && a.N <= 8; }

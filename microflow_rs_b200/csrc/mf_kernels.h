@@ -23,6 +23,27 @@ struct FastDiv {
 #endif
 };
 
+// Programmatic dependent launch (PDL).  A kernel launched with pdl != 0 may become resident while the previous kernel of the
+// stream is still running: its prologue (barrier init, TMEM allocation, weights and constants) overlaps the predecessor's
+// tail, and it executes pdl_wait() before its first access to activation memory -- that returns only when the predecessor
+// grid has completed and its writes are visible, so both the RAW on this layer's input and the WAR on the ping-pong output
+// buffer are ordered.  Every kernel that can be a predecessor calls pdl_trigger() at its start so the dependent may be
+// scheduled as SM resources free up.  Without the launch attribute both instructions are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*fn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int pdl, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, fn, KArgs(args)...);
+}
+#endif
+
 // One quantized conv / depthwise-conv layer on `batch` independent NHWC samples.
 struct ConvArgs {
     const uint8_t *in = nullptr;
@@ -39,6 +60,7 @@ struct ConvArgs {
     int is_u8 = 0, depthwise = 0;
     int big_acc = 0;                // 1 if |acc - kcorr| can exceed 2^22 (selects the general exact int->float)
     long long batch = 0;
+    int pdl = 0;                    // launch with programmatic stream serialization (see launch_pdl); smem / tcgen05 kernels only
 };
 
 struct FcArgs {
@@ -88,6 +110,7 @@ struct TailArgs {
     int sm_rows = 1, sm_cols = 1;
     float out_scale = 1.f, out_zp = 0.f, sm_lo = -128.f, sm_hi = 127.f;
     long long batch = 0;
+    int pdl = 0;
 };
 cudaError_t launch_tail_fused(const TailArgs &a, cudaStream_t s);
 
@@ -97,7 +120,7 @@ cudaError_t launch_fc_generic(const FcArgs &a, cudaStream_t s);
 cudaError_t launch_pool_generic(const PoolArgs &a, cudaStream_t s);
 cudaError_t launch_softmax(const SoftmaxArgs &a, cudaStream_t s);
 cudaError_t launch_quantize(const float *in, uint8_t *out, size_t n, float scale, float zp, int is_u8, cudaStream_t s);
-cudaError_t launch_dequantize(const uint8_t *in, float *out, size_t n, float scale, float zp, int is_u8, cudaStream_t s);
+cudaError_t launch_dequantize(const uint8_t *in, float *out, size_t n, float scale, float zp, int is_u8, cudaStream_t s, int pdl = 0);
 
 // ---- SIMT fast kernels (int8, weight zero-point 0): coalesced NHWC, dp4a -------------------------------
 bool dwconv_c4_eligible(const ConvArgs &a);      // depthwise, Cin == Cout, C % 4 == 0
