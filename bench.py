@@ -316,6 +316,17 @@ def main():
     e2e_val = world * batch * args.steps / float(t[0].item())
     e2e_block_val = world * batch * args.steps / float(t[1].item())
 
+    # ---- latency of the reference's own call shape: ONE sample through mf_predict_quantized (host buffers, blocking)
+    one = np.ascontiguousarray(host_in[0].array[0])
+    for _ in range(20):
+        m.predict_quantized(one)
+    lat = []
+    for _ in range(200):
+        t0 = time.perf_counter()
+        m.predict_quantized(one)
+        lat.append(time.perf_counter() - t0)
+    lat_us = 1e6 * float(np.median(lat))
+
     if rank == 0:
         # ---- roofline of the dominant kernel: group layers by kernel, take the largest share of the step
         groups = {}
@@ -355,6 +366,8 @@ def main():
                        "l2": f"inputs rotate over {R} device batches ({R * batch * ie / 1e6:.0f} MB > 126 MB L2)", "chunk": args.chunk or 8192},
             "e2e": {"value": e2e_val, "unit": "inferences/s", "h2d_bytes_per_step": world * batch * ie, "d2h_bytes_per_step": world * batch * oe * 4,
                     "api": "mf_predict_many_quantized_async x K + mf_model_synchronize (pinned host buffers)", "blocking": e2e_block_val},
+            "single_sample_latency_us": {"value": lat_us, "api": "mf_predict_quantized (one sample, host buffers, blocking; CUDA-graph replay)",
+                                         "note": "median of 200 calls incl. the Python/ctypes call overhead"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
             "layers": [{"i": i, "op": L["op"], "kernel": L["kernel"], "us_per_step": round(1e3 * float(t) / args.steps, 2),
                         "GBps": round((L["bytes"] - L["weight_bytes"]) * batch * args.steps / (float(t) * 1e-3) / 1e9, 1) if t > 0 else None}

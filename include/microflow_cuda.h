@@ -11,8 +11,10 @@
  *
  * Tensor layout: NHWC, row-major, one byte per element (int8 or uint8 -- `T: Quantized`,
  * src/quantize.rs:6-7).  Sample s of a batched call starts at byte s * in_elems.  The reference's
- * nalgebra buffers are column-major ([batch][col][row][chan], src/buffer.rs:10-16); the Rust shim
- * transposes or passes MF_LAYOUT_NALGEBRA (not implemented in this round: NHWC only).
+ * nalgebra buffers are column-major ([batch][col][row][chan], src/buffer.rs:10-16): a model created
+ * with mf_options.layout = MF_LAYOUT_NALGEBRA takes and returns HOST buffers in exactly that memory
+ * order (the Rust shim then passes `input.as_ptr()` with no copy); the transposition runs on the
+ * device.  Device-resident entry points (mf_predict_many_device, mf_op_run_device) are NHWC only.
  *
  * Errors: the reference reports every error at Rust compile time (abort_call_site!) and is infallible
  * at run time.  Here every function returns an mf_status; mf_last_error() gives the text a shim would
@@ -31,7 +33,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
 #endif
 
-#define MF_ABI_VERSION 1
+#define MF_ABI_VERSION 2
 
 typedef enum mf_status {
     MF_OK = 0,
@@ -73,11 +75,17 @@ typedef enum mf_status {
 #define MF_FLAG_FORCE_GENERIC 2u  /* run every layer on the generic direct kernels (cross-check path) */
 #define MF_FLAG_NO_TENSOR_CORE 4u /* keep SIMT fast kernels but never pick a tcgen05 kernel */
 
+/* mf_options.layout: memory order of the HOST input / output buffers of predict* */
+#define MF_LAYOUT_NHWC 0u     /* [sample][row][col][chan], row-major (default) */
+#define MF_LAYOUT_NALGEBRA 1u /* the reference's own buffers: Buffer4D = [SMatrix<[T; CH], R, C>; B] and Buffer2D = SMatrix<T, R, C>,
+                                 both column-major (src/buffer.rs:5-16): [sample][col][row][chan] */
+
 typedef struct mf_options {
-    uint32_t struct_size; /* = sizeof(mf_options) */
+    uint32_t struct_size; /* = sizeof(mf_options) of the caller; a shorter (older) struct leaves the missing fields at 0 */
     int32_t device;       /* CUDA device ordinal; -1 = current device */
     uint32_t chunk;       /* samples per internal chunk of predict_many (0 = default) */
     uint32_t flags;       /* MF_FLAG_* */
+    uint32_t layout;      /* MF_LAYOUT_* (ABI version 2) */
 } mf_options;
 
 typedef struct mf_tensor_info {

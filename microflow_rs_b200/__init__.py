@@ -42,8 +42,11 @@ class MicroflowError(RuntimeError):
         self.text = text
 
 
+LAYOUT_NHWC, LAYOUT_NALGEBRA = 0, 1   # mf_options.layout: host buffers row-major NHWC, or the reference's column-major nalgebra buffers
+
+
 class _Options(C.Structure):
-    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("chunk", C.c_uint32), ("flags", C.c_uint32)]
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("chunk", C.c_uint32), ("flags", C.c_uint32), ("layout", C.c_uint32)]
 
 
 class _TensorInfo(C.Structure):
@@ -199,9 +202,9 @@ def _dtype_code(a):
 class Model:
     """What `#[model("path.tflite")]` generates in the reference: predict / predict_quantized (+ predict_many)."""
 
-    def __init__(self, path_or_bytes, device=-1, chunk=0, flags=0):
+    def __init__(self, path_or_bytes, device=-1, chunk=0, flags=0, layout=LAYOUT_NHWC):
         self._h = C.c_void_p()
-        opt = _Options(C.sizeof(_Options), device, chunk, flags)
+        opt = _Options(C.sizeof(_Options), device, chunk, flags, layout)
         if isinstance(path_or_bytes, (str, os.PathLike)):
             _check(lib().mf_model_create_from_file(str(path_or_bytes).encode(), C.byref(opt), C.byref(self._h)))
         else:

@@ -41,6 +41,8 @@ struct Slot {
     float *out_f32 = nullptr;
     uint8_t *out_q = nullptr;
     uint8_t *logits = nullptr;
+    uint8_t *in_t = nullptr;      // MF_LAYOUT_NALGEBRA only: transposed copies of the input / outputs
+    uint8_t *out_t = nullptr;
 };
 
 }  // namespace
@@ -49,6 +51,9 @@ struct mf_model {
     ModelSpec spec;
     std::vector<LayerExec> layers;
     uint32_t flags = 0;
+    uint32_t layout = MF_LAYOUT_NHWC;
+    // MF_LAYOUT_NALGEBRA: per sample the host tensors are `mats` column-major R x C matrices of `ch`-element cells
+    struct Geo { int mats = 1, R = 1, C = 1, ch = 1; bool transpose = false; } geo_in, geo_out;
     bool host_only = false;
     int device = 0, num_sms = 148;
     uint8_t *d_blob = nullptr;
@@ -65,6 +70,20 @@ struct mf_model {
     int tail_first = -1, tail_conv = -1, tail_last = -1;
     TailArgs tail;
     size_t slot_rr = 0;                     // round-robin position of the host-path stream slots
+    // Small host-path calls (n <= kGraphMaxN, the reference's one-sample predict() above all) replay a captured CUDA graph:
+    // H2D from a pinned staging buffer, every layer, D2H into pinned staging -- one graph launch instead of ~30 stream
+    // operations.  One executable graph per (n, input kind, outputs wanted); capture happens on first use.
+    struct SmallGraph {
+        size_t n = 0;
+        int kind = 0;                       // bit 0: f32 input, bit 1: f32 output, bit 2: quantized output, bit 3: logits
+        cudaGraphExec_t exec = nullptr;
+        uint64_t kernels = 0;               // kernel nodes per replay (for mf_model_launch_count)
+    };
+    std::vector<SmallGraph> graphs;
+    bool graphs_disabled = false;           // set when capture / instantiation fails once: the stream path is used from then on
+    uint8_t *h_stage_in = nullptr;          // pinned staging, kGraphMaxN samples each
+    float *h_stage_out_f32 = nullptr;
+    uint8_t *h_stage_out_q = nullptr, *h_stage_logits = nullptr;
     std::mutex mu;
 };
 
@@ -85,7 +104,8 @@ int check_device(int *count) {
 
 void free_slot(Slot &s) {
     if (s.stream) cudaStreamDestroy(s.stream);
-    for (auto *p : {(void *)s.act[0], (void *)s.act[1], (void *)s.in_q, (void *)s.in_f32, (void *)s.out_f32, (void *)s.out_q, (void *)s.logits})
+    for (auto *p : {(void *)s.act[0], (void *)s.act[1], (void *)s.in_q, (void *)s.in_f32, (void *)s.out_f32, (void *)s.out_q, (void *)s.logits, (void *)s.in_t,
+                    (void *)s.out_t})
         if (p) cudaFree(p);
     s = Slot{};
 }
@@ -100,6 +120,31 @@ int alloc_slot(mf_model *m, Slot &s) {
     MF_CUDA(cudaMalloc(&s.out_f32, c * m->spec.out_elems * sizeof(float)));
     MF_CUDA(cudaMalloc(&s.out_q, c * m->spec.out_elems));
     MF_CUDA(cudaMalloc(&s.logits, c * m->spec.max_elems));
+    if (m->geo_in.transpose) MF_CUDA(cudaMalloc(&s.in_t, c * m->spec.in_elems));
+    if (m->geo_out.transpose) MF_CUDA(cudaMalloc(&s.out_t, c * m->spec.out_elems * sizeof(float)));
+    return MF_OK;
+}
+
+// MF_LAYOUT_NALGEBRA, input side: s.in_q holds the quantized input in the reference's column-major order -> NHWC in s.in_t
+int stage_input_layout(mf_model *m, Slot &s, size_t n, cudaStream_t st, const uint8_t **d_in) {
+    *d_in = s.in_q;
+    if (!m->geo_in.transpose) return MF_OK;
+    const auto &g = m->geo_in;
+    cudaError_t e = launch_layout_transpose(s.in_q, s.in_t, (long long)n * g.mats, g.R, g.C, g.ch, st);
+    if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("layout_transpose_kernel launch failed: ") + cudaGetErrorString(e));
+    m->launches += 1;
+    *d_in = s.in_t;
+    return MF_OK;
+}
+// output side: NHWC result in `src` (elements of `esz` bytes) -> column-major copy in s.out_t; *d_out is what the D2H copy reads
+int stage_output_layout(mf_model *m, Slot &s, size_t n, const void *src, size_t esz, cudaStream_t st, const void **d_out) {
+    *d_out = src;
+    if (!m->geo_out.transpose) return MF_OK;
+    const auto &g = m->geo_out;
+    cudaError_t e = launch_layout_transpose((const uint8_t *)src, s.out_t, (long long)n * g.mats, g.C, g.R, g.ch * (int)esz, st);   // roles of R and C swapped
+    if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("layout_transpose_kernel launch failed: ") + cudaGetErrorString(e));
+    m->launches += 1;
+    *d_out = s.out_t;
     return MF_OK;
 }
 
@@ -195,6 +240,87 @@ int need_device(const mf_model *m) {
     return MF_OK;
 }
 
+constexpr size_t kGraphMaxN = 64;
+
+// Returns MF_OK after serving the call from a graph, or -1 when the caller should take the stream path (never a CPU path).
+int predict_small_graph(mf_model *m, const void *in_q, const float *in_f32, size_t n, float *out_f32, void *out_q, void *logits) {
+    static const bool env_graph = [] { const char *e = std::getenv("MF_GRAPH"); return !e || std::atoi(e) != 0; }();
+    if (!env_graph || m->graphs_disabled || n == 0 || n > kGraphMaxN || n > m->chunk) return -1;
+    const size_t ie = m->spec.in_elems, oe = m->spec.out_elems;
+    const size_t le = m->softmax_tail >= 0 ? m->layers[(size_t)m->softmax_tail].spec.in_elems : 0;
+    const int kind = (in_f32 ? 1 : 0) | (out_f32 ? 2 : 0) | (out_q ? 4 : 0) | (logits ? 8 : 0);
+    Slot &s = m->slot[0];
+    if (!m->h_stage_in) {
+        if (cudaMallocHost(&m->h_stage_in, kGraphMaxN * ie * sizeof(float)) != cudaSuccess ||
+            cudaMallocHost(&m->h_stage_out_f32, kGraphMaxN * oe * sizeof(float)) != cudaSuccess ||
+            cudaMallocHost(&m->h_stage_out_q, kGraphMaxN * oe) != cudaSuccess ||
+            cudaMallocHost(&m->h_stage_logits, kGraphMaxN * (le ? le : 1)) != cudaSuccess) {
+            (void)cudaGetLastError();
+            m->graphs_disabled = true;
+            return -1;
+        }
+    }
+    mf_model::SmallGraph *g = nullptr;
+    for (auto &e : m->graphs)
+        if (e.n == n && e.kind == kind) g = &e;
+    if (!g) {
+        // both slots' streams may still hold work of earlier asynchronous calls that uses the same device buffers
+        if (cudaStreamSynchronize(m->slot[0].stream) != cudaSuccess || cudaStreamSynchronize(m->slot[1].stream) != cudaSuccess) return -1;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        const uint64_t launches0 = m->launches;
+        bool ok = cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            if (in_f32) {
+                ok = cudaMemcpyAsync(s.in_f32, m->h_stage_in, n * ie * sizeof(float), cudaMemcpyHostToDevice, s.stream) == cudaSuccess &&
+                     launch_quantize(s.in_f32, s.in_q, n * ie, m->spec.in_scale, (float)m->spec.in_zp, m->spec.is_u8_in, s.stream) == cudaSuccess;
+                m->launches += 1;
+            } else {
+                ok = cudaMemcpyAsync(s.in_q, m->h_stage_in, n * ie, cudaMemcpyHostToDevice, s.stream) == cudaSuccess;
+            }
+            const uint8_t *d_in = s.in_q;
+            ok = ok && stage_input_layout(m, s, n, s.stream, &d_in) == MF_OK;
+            ok = ok && run_chunk(m, s, d_in, n, out_f32 ? s.out_f32 : nullptr, out_q ? s.out_q : nullptr, logits ? s.logits : nullptr, s.stream, nullptr, nullptr, 0) == MF_OK;
+            const void *d_o = nullptr;   // the transposed copy (if any) is consumed by the D2H right behind it, so one buffer serves both outputs
+            if (ok && out_f32)
+                ok = stage_output_layout(m, s, n, s.out_f32, sizeof(float), s.stream, &d_o) == MF_OK &&
+                     cudaMemcpyAsync(m->h_stage_out_f32, d_o, n * oe * sizeof(float), cudaMemcpyDeviceToHost, s.stream) == cudaSuccess;
+            if (ok && out_q)
+                ok = stage_output_layout(m, s, n, s.out_q, 1, s.stream, &d_o) == MF_OK &&
+                     cudaMemcpyAsync(m->h_stage_out_q, d_o, n * oe, cudaMemcpyDeviceToHost, s.stream) == cudaSuccess;
+            if (ok && logits) ok = cudaMemcpyAsync(m->h_stage_logits, s.logits, n * le, cudaMemcpyDeviceToHost, s.stream) == cudaSuccess;
+            const bool ended = cudaStreamEndCapture(s.stream, &graph) == cudaSuccess;   // always end the capture, even after a failure
+            ok = ok && ended && graph != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        const uint64_t per_replay = m->launches - launches0;
+        m->launches = launches0;                          // capturing launched nothing; replays are counted below
+        if (!ok) {
+            (void)cudaGetLastError();
+            m->graphs_disabled = true;
+            return -1;
+        }
+        if (m->graphs.size() >= 32) {                     // bounded cache: drop the oldest
+            cudaGraphExecDestroy(m->graphs.front().exec);
+            m->graphs.erase(m->graphs.begin());
+        }
+        mf_model::SmallGraph e;
+        e.n = n; e.kind = kind; e.exec = exec; e.kernels = per_replay;
+        m->graphs.push_back(e);
+        g = &m->graphs.back();
+    }
+    std::memcpy(m->h_stage_in, in_f32 ? (const void *)in_f32 : in_q, n * ie * (in_f32 ? sizeof(float) : 1));
+    // slot 0's stream orders the replay after any earlier asynchronous call that used slot 0's device buffers
+    MF_CUDA(cudaGraphLaunch(g->exec, s.stream));
+    MF_CUDA(cudaStreamSynchronize(s.stream));
+    if (out_f32) std::memcpy(out_f32, m->h_stage_out_f32, n * oe * sizeof(float));
+    if (out_q) std::memcpy(out_q, m->h_stage_out_q, n * oe);
+    if (logits) std::memcpy(logits, m->h_stage_logits, n * le);
+    m->launches += g->kernels;
+    return MF_OK;
+}
+
 // host-buffer batched path: chunks alternate between two streams so H2D(c+1) overlaps compute(c) and D2H(c-1)
 int predict_many_host(mf_model *m, const void *in_q, const float *in_f32, size_t n, float *out_f32, void *out_q, void *logits, bool wait = true) {
     int rc = need_device(m);
@@ -205,6 +331,10 @@ int predict_many_host(mf_model *m, const void *in_q, const float *in_f32, size_t
     MF_CUDA(cudaSetDevice(m->device));
     const size_t ie = m->spec.in_elems, oe = m->spec.out_elems;
     const size_t le = m->softmax_tail >= 0 ? m->layers[(size_t)m->softmax_tail].spec.in_elems : 0;
+    if (wait && n <= kGraphMaxN) {
+        rc = predict_small_graph(m, in_q, in_f32, n, out_f32, out_q, logits);
+        if (rc >= 0) return rc;
+    }
     // host path: pieces small enough that the H2D of piece c+1 overlaps the compute of piece c (two streams), large enough
     // to keep the per-launch fixed costs amortised
     size_t piece = std::min(m->chunk, std::max<size_t>(1024, (n + 1) / 2));
@@ -221,10 +351,22 @@ int predict_many_host(mf_model *m, const void *in_q, const float *in_f32, size_t
         } else {
             MF_CUDA(cudaMemcpyAsync(s.in_q, (const uint8_t *)in_q + off * ie, cn * ie, cudaMemcpyHostToDevice, s.stream));
         }
-        rc = run_chunk(m, s, s.in_q, cn, out_f32 ? s.out_f32 : nullptr, out_q ? s.out_q : nullptr, logits ? s.logits : nullptr, s.stream, nullptr, nullptr, 0);
+        const uint8_t *d_in = s.in_q;
+        rc = stage_input_layout(m, s, cn, s.stream, &d_in);
         if (rc) return rc;
-        if (out_f32) MF_CUDA(cudaMemcpyAsync(out_f32 + off * oe, s.out_f32, cn * oe * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-        if (out_q) MF_CUDA(cudaMemcpyAsync((uint8_t *)out_q + off * oe, s.out_q, cn * oe, cudaMemcpyDeviceToHost, s.stream));
+        rc = run_chunk(m, s, d_in, cn, out_f32 ? s.out_f32 : nullptr, out_q ? s.out_q : nullptr, logits ? s.logits : nullptr, s.stream, nullptr, nullptr, 0);
+        if (rc) return rc;
+        const void *d_o = nullptr;
+        if (out_f32) {
+            rc = stage_output_layout(m, s, cn, s.out_f32, sizeof(float), s.stream, &d_o);
+            if (rc) return rc;
+            MF_CUDA(cudaMemcpyAsync(out_f32 + off * oe, d_o, cn * oe * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        }
+        if (out_q) {
+            rc = stage_output_layout(m, s, cn, s.out_q, 1, s.stream, &d_o);
+            if (rc) return rc;
+            MF_CUDA(cudaMemcpyAsync((uint8_t *)out_q + off * oe, d_o, cn * oe, cudaMemcpyDeviceToHost, s.stream));
+        }
         if (logits) MF_CUDA(cudaMemcpyAsync((uint8_t *)logits + off * le, s.logits, cn * le, cudaMemcpyDeviceToHost, s.stream));
     }
     m->slot_rr = ci;                                   // the next call continues the slot rotation (pipelining across async calls)
@@ -241,15 +383,29 @@ int create_model(const uint8_t *buf, size_t len, const mf_options *opt, mf_model
     mf_options o{};
     o.struct_size = sizeof(mf_options);
     o.device = -1;
-    if (opt) {
-        if (opt->struct_size < sizeof(mf_options)) return fail(MF_ERR_INVALID_ARG, "mf_options.struct_size too small");
-        o = *opt;
+    if (opt) {   // struct_size versions the struct: an ABI-1 caller (16 bytes, no `layout`) is accepted, unknown trailing bytes are ignored
+        if (opt->struct_size < 16) return fail(MF_ERR_INVALID_ARG, "mf_options.struct_size too small");
+        std::memcpy(&o, opt, std::min<size_t>(opt->struct_size, sizeof(mf_options)));
+        o.struct_size = sizeof(mf_options);
     }
+    if (o.layout != MF_LAYOUT_NHWC && o.layout != MF_LAYOUT_NALGEBRA) return fail(MF_ERR_INVALID_ARG, "mf_options.layout must be MF_LAYOUT_NHWC or MF_LAYOUT_NALGEBRA");
     std::unique_ptr<mf_model, void (*)(mf_model *)> m(new mf_model(), mf_model_destroy);
     std::string err;
     int rc = parse_tflite(buf, len, m->spec, err);
     if (rc != MF_OK) return fail(rc, err);
     m->flags = o.flags;
+    m->layout = o.layout;
+    if (o.layout == MF_LAYOUT_NALGEBRA) {
+        auto geo = [](int rank, const int *d) {
+            mf_model::Geo g;
+            if (rank == 4) { g.mats = d[0]; g.R = d[1]; g.C = d[2]; g.ch = d[3]; }   // Buffer4D = [SMatrix<[T; CH], R, C>; B]
+            else { g.mats = 1; g.R = d[0]; g.C = d[1]; g.ch = 1; }                   // Buffer2D = SMatrix<T, R, C>
+            g.transpose = g.R > 1 && g.C > 1;                                        // a single row or column is the same bytes either way
+            return g;
+        };
+        m->geo_in = geo(m->spec.in_rank, m->spec.in_dims);
+        m->geo_out = geo(m->spec.out_rank, m->spec.out_dims);
+    }
     m->host_only = (o.flags & MF_FLAG_HOST_ONLY) != 0;
     bool have_device = false;
     if (!m->host_only) {
@@ -343,6 +499,9 @@ void mf_model_destroy(mf_model *m) {
         cudaSetDevice(m->device);
         cudaDeviceSynchronize();
         for (auto e : m->prof_events) cudaEventDestroy(e);
+        for (auto &g : m->graphs) cudaGraphExecDestroy(g.exec);
+        for (void *hp : {(void *)m->h_stage_in, (void *)m->h_stage_out_f32, (void *)m->h_stage_out_q, (void *)m->h_stage_logits})
+            if (hp) cudaFreeHost(hp);
         free_slot(m->slot[0]);
         free_slot(m->slot[1]);
         if (m->d_blob) cudaFree(m->d_blob);

@@ -178,6 +178,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KH = KH_T ? KH_T : p.KH, KW = KW_T ? KW_T : p.KW, CB = CB_T ? CB_T : p.CB;
+    // the 1x1 instantiations are only launched on a single row of (packed) pixels (TW = 128, H = B = 1; conv_tc_launch checks):
+    // a tile index is its x coordinate and there are no border classes
+    constexpr bool LINEAR = KH_T == 1 && KW_T == 1;
 
     if (warp == kWarpTma && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
@@ -212,9 +215,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             pdl_wait();       // the weights above are static; the activations below are the previous kernel's output
             uint32_t s = 0, ph = 0;
             for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                uint32_t b, rem, ty, tx;
-                p.fd_img.divmod((uint32_t)tile, b, rem);
-                p.fd_tx.divmod(rem, ty, tx);
+                uint32_t b = 0, rem, ty = 0, tx = (uint32_t)tile;
+                if (!LINEAR) {
+                    p.fd_img.divmod((uint32_t)tile, b, rem);
+                    p.fd_tx.divmod(rem, ty, tx);
+                }
                 for (int n = 0; n < KW; ++n)
                     for (int cb = 0; cb < CB; ++cb) {
                         mbar_wait(empty_bar(s), ph ^ 1);
@@ -279,15 +284,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             uint32_t it = 0;
             for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const uint32_t acc = it & 1, aph = (it >> 1) & 1;
-                uint32_t b, rem, ty, tx;
-                p.fd_img.divmod((uint32_t)tile, b, rem);
-                p.fd_tx.divmod(rem, ty, tx);
-                const long long oy = (long long)ty * p.TH + rr, ox = (long long)tx * p.TW + rc;
-                const bool valid = oy < p.OH && ox < p.OW;
-                int cls = 0;
-                if (TAB == kTabSmem && p.ncls == 9) cls = 3 * (oy == 0 ? 0 : (oy == p.OH - 1 ? 2 : 1)) + (ox == 0 ? 0 : (ox == p.OW - 1 ? 2 : 1));
-                const int32_t *corr = s_corr + cls * p.N;
-                uint8_t *orow = p.out + (((long long)b * p.OH + oy) * p.OW + ox) * p.N;
+                bool valid;
+                const int32_t *corr = s_corr;
+                uint8_t *orow;
+                if (LINEAR) {                                       // one row of 128-byte (packed) pixels: tile t covers rows [128 t, 128 t + 128)
+                    const long long ox = tile * 128 + row;
+                    valid = ox < p.OW;
+                    orow = p.out + ox * p.N;
+                } else {
+                    uint32_t b, rem, ty, tx;
+                    p.fd_img.divmod((uint32_t)tile, b, rem);
+                    p.fd_tx.divmod(rem, ty, tx);
+                    const long long oy = (long long)ty * p.TH + rr, ox = (long long)tx * p.TW + rc;
+                    valid = oy < p.OH && ox < p.OW;
+                    int cls = 0;
+                    if (TAB == kTabSmem && p.ncls == 9) cls = 3 * (oy == 0 ? 0 : (oy == p.OH - 1 ? 2 : 1)) + (ox == 0 ? 0 : (ox == p.OW - 1 ? 2 : 1));
+                    corr = s_corr + cls * p.N;
+                    orow = p.out + (((long long)b * p.OH + oy) * p.OW + ox) * p.N;
+                }
 
                 mbar_wait(tfull_bar(acc), aph);
                 tc_fence_after();
@@ -539,7 +553,8 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     const bool xu = p.lo == -128.f && p.hi == 127.f && env_xug != 0;
     if (xu && packed_epilogue)   // pre-biased accumulators: the table entry is added, not subtracted (conv_tc_kernel, PACKED)
         for (int k = 0; k < p.ncls * p.N; ++k) tab.corr[k] = kAccBias - tab.corr[k];
-    const int shape = (p.KH == 3 && p.KW == 3 && p.CB == 1) ? 1 : ((p.KH == 1 && p.KW == 1 && p.CB == 1) ? 2 : ((p.KH == 1 && p.KW == 1 && p.CB == 2) ? 3 : 0));
+    const bool linear = p.KH == 1 && p.KW == 1 && p.TW == 128 && p.TH == 1 && l.H == 1 && l.B == 1 && l.OH == 1 && p.ncls == 1;
+    const int shape = (p.KH == 3 && p.KW == 3 && p.CB == 1) ? 1 : ((linear && p.CB == 1) ? 2 : ((linear && p.CB == 2) ? 3 : 0));
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const ConvTcTables, const ConvTcParams);
     KernelFn fn = nullptr;
 #define MF_TC_PICK(BIGV, XUV)                                                       \

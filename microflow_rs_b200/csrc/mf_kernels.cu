@@ -194,6 +194,33 @@ cudaError_t launch_dequantize(const uint8_t *in, float *out, size_t n, float sca
 }
 
 // ================================================================================================
+// host-buffer layout conversion (MF_LAYOUT_NALGEBRA): dst[b][r][c][e] = src[b][c][r][e].  One thread per destination byte
+// (writes coalesced; an input image is a few KB, so the strided reads stay in L1/L2).
+// ================================================================================================
+__global__ void __launch_bounds__(256) layout_transpose_kernel(const uint8_t *src, uint8_t *dst, uint32_t per_sample, FastDiv fd_ce, FastDiv fd_e, int R, int C,
+                                                               int elem, long long batch) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per_sample) return;
+    uint32_t r, rem, c, e;
+    fd_ce.divmod(idx, r, rem);
+    fd_e.divmod(rem, c, e);
+    const uint32_t sidx = (c * (uint32_t)R + r) * (uint32_t)elem + e;
+    for (long long b = blockIdx.y; b < batch; b += gridDim.y) dst[(size_t)b * per_sample + idx] = src[(size_t)b * per_sample + sidx];
+}
+cudaError_t launch_layout_transpose(const uint8_t *src, uint8_t *dst, long long batch, int R, int C, int elem, cudaStream_t s) {
+    const long long per = (long long)R * C * elem;
+    if (per <= 0 || batch <= 0) return cudaSuccess;
+    if (per >= (1ll << 31)) return cudaErrorInvalidValue;
+    const long long gx = (per + 255) / 256;
+    long long gy = (148ll * 16 + gx - 1) / gx;
+    if (gy > batch) gy = batch;
+    if (gy > 65535) gy = 65535;
+    layout_transpose_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, s>>>(src, dst, (uint32_t)per, FastDiv((uint32_t)(C * elem)), FastDiv((uint32_t)elem), R, C, elem,
+                                                                            batch);
+    return cudaGetLastError();
+}
+
+// ================================================================================================
 // FAST kernels.  Grid: blockIdx.y = sample (grid-stride), blockIdx.x * blockDim.x + threadIdx.x = 32-bit index inside
 // the sample, decoded with FastDiv (no 64-bit div/mod on the device).
 // ================================================================================================
@@ -515,13 +542,19 @@ __global__ void __launch_bounds__(kDwSmemThreads, MINB) dwconv3x3_smem_kernel(Co
     const int row_words = (int)(row_bytes >> 2);
 
     pdl_wait();                                                         // every thread: its stores must not overtake the previous kernel's reads
-    uint32_t it = 0;
-    for (long long b = first; b < a.batch; b += step, ++it) {
-        const int slot = (int)(it % (uint32_t)nbuf);
-        sm_mbar_wait(bar0 + 8u * slot, (it / (uint32_t)nbuf) & 1u);
+    // per-sample state is carried incrementally (ring slot, mbarrier phase, slot base, output pointer): the small feature
+    // maps spend only a few hundred instructions per sample, so divisions and 64-bit multiplies per sample would show
+    int slot = 0;
+    uint32_t phase = 0;
+    const uint32_t *pslot = reinterpret_cast<const uint32_t *>(bufs) + poff;
+    uint32_t *osample = reinterpret_cast<uint32_t *>(a.out) + ((size_t)first * a.OH + i0) * out_row_words + x;
+    const size_t ostep = (size_t)step * a.OH * out_row_words;
+    const uint32_t slot_words = buf_stride >> 2;
+    for (long long b = first; b < a.batch; b += step) {
+        sm_mbar_wait(bar0 + 8u * slot, phase);
         if (i1 > i0) {
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(bufs + (size_t)slot * buf_stride) + poff;
-            uint32_t *o = reinterpret_cast<uint32_t *>(a.out) + ((size_t)b * a.OH + i0) * out_row_words + x;
+            const uint32_t *p = pslot;
+            uint32_t *o = osample;
             auto take = [&](uint32_t (&t)[4]) {                         // the next input row, transposed
                 const uint32_t v0 = p[0], v1 = p[G], v2 = p[2 * G];
                 p += row_words;
@@ -564,9 +597,14 @@ __global__ void __launch_bounds__(kDwSmemThreads, MINB) dwconv3x3_smem_kernel(Co
         if ((tid & 31) == 0) {
             uint32_t old;
             asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(bar0 + 64u + 4u * slot) : "memory");
-            if (old % (uint32_t)(kDwSmemThreads / 32) == (uint32_t)(kDwSmemThreads / 32 - 1))   // the counter is never reset
+            if (old == (uint32_t)(kDwSmemThreads / 32 - 1)) {           // last warp out: reset the counter, refill the slot
+                reinterpret_cast<volatile uint32_t *>(dsm + 64)[slot] = 0;
                 if (b + (long long)nbuf * step < a.batch) request(b + (long long)nbuf * step, slot);
+            }
         }
+        osample += ostep;
+        pslot += slot_words;
+        if (++slot == nbuf) { slot = 0; phase ^= 1u; pslot -= (size_t)nbuf * slot_words; }
     }
 }
 
@@ -591,7 +629,7 @@ cudaError_t launch_dwconv3x3_smem(const ConvArgs &a, int num_sms, cudaStream_t s
     const int rows = (a.OH + nstrip - 1) / nstrip;
     nstrip = (a.OH + rows - 1) / rows;
     static const int env_minb = [] { const char *e = std::getenv("MF_DW_MINB"); return e ? std::atoi(e) : 4; }();
-    const int minb = env_minb < 2 ? 2 : (env_minb > 4 ? 4 : env_minb);
+    const int minb = env_minb < 2 ? 2 : (env_minb > 6 ? 6 : env_minb);
     // persistent CTAs, samples taken grid-stride: as many CTAs per SM as the launch bound allows while every CTA still has
     // a ring of >= 2 sample slots (<= 4) in its share of the 227 KB
     int per_sm = minb, nbuf = 0;
@@ -608,7 +646,7 @@ cudaError_t launch_dwconv3x3_smem(const ConvArgs &a, int num_sms, cudaStream_t s
     Fn fn = nullptr;
 #define MF_DW_PICK(M) (a.sh == 1 ? (full ? dwconv3x3_smem_kernel<1, true, M> : dwconv3x3_smem_kernel<1, false, M>) \
                                  : (full ? dwconv3x3_smem_kernel<2, true, M> : dwconv3x3_smem_kernel<2, false, M>))
-    fn = minb == 4 ? MF_DW_PICK(4) : (minb == 3 ? MF_DW_PICK(3) : MF_DW_PICK(2));
+    fn = minb == 6 ? MF_DW_PICK(6) : (minb == 5 ? MF_DW_PICK(5) : (minb == 4 ? MF_DW_PICK(4) : (minb == 3 ? MF_DW_PICK(3) : MF_DW_PICK(2))));
 #undef MF_DW_PICK
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
     if (e != cudaSuccess) return e;
@@ -774,14 +812,15 @@ __global__ void __launch_bounds__(kDwSmemThreads, 3) dwconv_cin1_smem_kernel(Con
     const uint32_t st_lo = lo_ok ? row_bytes : 0u, st_hi = hi_ok ? row_bytes : 0u;
 
     pdl_wait();
-    uint32_t it = 0;
-    for (long long b = first; b < a.batch; b += step, ++it) {
-        const int slot = (int)(it % (uint32_t)nbuf);
-        sm_mbar_wait(bar0 + 8u * slot, (it / (uint32_t)nbuf) & 1u);
+    int slot = 0;                                                       // per-sample state carried incrementally (see dwconv3x3_smem_kernel)
+    uint32_t phase = 0, base = buf0;
+    uint2 *osample = reinterpret_cast<uint2 *>(a.out) + ((size_t)first * a.OH + i0) * a.OW + j;
+    const size_t ostep = (size_t)step * a.OH * a.OW;
+    for (long long b = first; b < a.batch; b += step) {
+        sm_mbar_wait(bar0 + 8u * slot, phase);
         if (i1 > i0) {
-            const uint32_t base = buf0 + (uint32_t)slot * buf_stride;
             uint32_t plo = base + off_lo, phi = base + off_hi;
-            uint2 *o = reinterpret_cast<uint2 *>(a.out) + ((size_t)b * a.OH + i0) * a.OW + j;
+            uint2 *o = osample;
             auto take = [&]() {                                         // (left, centre, right, -) of the next input row
                 const uint32_t vlo = lds_u32(plo), vhi = lds_u32(phi);
                 plo += st_lo; phi += st_hi;
@@ -827,9 +866,14 @@ __global__ void __launch_bounds__(kDwSmemThreads, 3) dwconv_cin1_smem_kernel(Con
         if ((tid & 31) == 0) {
             uint32_t old;
             asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(bar0 + 64u + 4u * slot) : "memory");
-            if (old % (uint32_t)(kDwSmemThreads / 32) == (uint32_t)(kDwSmemThreads / 32 - 1))
+            if (old == (uint32_t)(kDwSmemThreads / 32 - 1)) {           // last warp out: reset the counter, refill the slot
+                reinterpret_cast<volatile uint32_t *>(dsm + 64)[slot] = 0;
                 if (b + (long long)nbuf * step < a.batch) request(b + (long long)nbuf * step, slot);
+            }
         }
+        osample += ostep;
+        base += buf_stride;
+        if (++slot == nbuf) { slot = 0; phase ^= 1u; base = buf0; }
     }
 }
 

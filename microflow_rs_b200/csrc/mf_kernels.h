@@ -122,6 +122,10 @@ cudaError_t launch_softmax(const SoftmaxArgs &a, cudaStream_t s);
 cudaError_t launch_quantize(const float *in, uint8_t *out, size_t n, float scale, float zp, int is_u8, cudaStream_t s);
 cudaError_t launch_dequantize(const uint8_t *in, float *out, size_t n, float scale, float zp, int is_u8, cudaStream_t s, int pdl = 0);
 
+// MF_LAYOUT_NALGEBRA <-> NHWC: per sample, elements of `elem` bytes, src [C][R][elem] -> dst [R][C][elem] (pass R and C
+// swapped for the opposite direction).  Buffer4D / Buffer2D of the reference are column-major (src/buffer.rs:5-16).
+cudaError_t launch_layout_transpose(const uint8_t *src, uint8_t *dst, long long batch, int R, int C, int elem, cudaStream_t s);
+
 // ---- SIMT fast kernels (int8, weight zero-point 0): coalesced NHWC, dp4a -------------------------------
 bool dwconv_c4_eligible(const ConvArgs &a);      // depthwise, Cin == Cout, C % 4 == 0
 cudaError_t launch_dwconv_c4(const ConvArgs &a, cudaStream_t s);

@@ -141,3 +141,24 @@ def test_async_predict_many_pipelines_and_matches_blocking(gpu_models, ora):
         np.testing.assert_array_equal(outs[k].array, m.predict_many_quantized(ins[k].array))
     want, _ = o.predict_many_quantized(ins[1].array[:64], threads=oracle.max_threads())
     np.testing.assert_array_equal(outs[1].array[:64], want)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_small_calls_replay_a_cuda_graph_and_match_the_oracle(gpu_models, ora, name):
+    """Host-path calls of <= 64 samples (the reference's one-sample predict() above all) replay a captured CUDA graph: the same
+    graph must serve changing inputs, sizes either side of the limit must agree, and every variant (f32 in, logits out) is checked."""
+    m, o = gpu_models[name], ora[name]
+    xs = splitmix_bytes(SEEDS[name] + 11, 70 * o.in_elems).reshape(70, -1)
+    want_f, want_q = o.predict_many_quantized(xs, threads=oracle.max_threads())
+    for rep in range(3):                                   # capture on the first pass, replays afterwards
+        for s in (0, 1, 69):
+            np.testing.assert_array_equal(m.predict_quantized(xs[s]).reshape(-1), want_f[s])
+    for n in (1, 2, 17, 64, 65, 70):                       # 65 and 70 take the stream path
+        np.testing.assert_array_equal(m.predict_many_quantized(xs[:n]), want_f[:n])
+        q, _ = m.predict_many_logits(xs[:n])
+        np.testing.assert_array_equal(q, want_q[:n])
+    xf = np.random.default_rng(3).uniform(-2, 2, (5, o.in_elems)).astype(np.float32)
+    want = np.stack([o.predict(xf[s]).reshape(-1) for s in range(5)])
+    for rep in range(2):
+        np.testing.assert_array_equal(m.predict_many(xf), want)
+        np.testing.assert_array_equal(m.predict(xf[3]).reshape(-1), want[3])

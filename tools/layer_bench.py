@@ -16,6 +16,9 @@ LAYERS = {  # name: (H, W, Cin, Cout, K, stride, depthwise)
     "L3_dw16_s2": (48, 48, 16, 16, 3, 2, True), "L4_pw16_32": (24, 24, 16, 32, 1, 1, False), "L5_dw32": (24, 24, 32, 32, 3, 1, True),
     "L6_pw32_32": (24, 24, 32, 32, 1, 1, False), "L13_dw128": (6, 6, 128, 128, 3, 1, True), "L14_pw128": (6, 6, 128, 128, 1, 1, False),
     "L26_pw256": (3, 3, 256, 256, 1, 1, False),
+    "L7_dw32_s2": (24, 24, 32, 32, 3, 2, True), "L9_dw64": (12, 12, 64, 64, 3, 1, True), "L11_dw64_s2": (12, 12, 64, 64, 3, 2, True),
+    "L23_dw128_s2": (6, 6, 128, 128, 3, 2, True), "L25_dw256": (3, 3, 256, 256, 3, 1, True), "L8_pw32_64": (12, 12, 32, 64, 1, 1, False),
+    "L10_pw64_64": (12, 12, 64, 64, 1, 1, False), "L12_pw64_128": (6, 6, 64, 128, 1, 1, False), "L24_pw128_256": (3, 3, 128, 256, 1, 1, False),
 }
 
 

@@ -5,10 +5,10 @@
 #include <cuda_runtime.h>
 
 enum { FFMA2, FFMA, FADD2, PRMT, LOP3, IMAD, IADD, DP4A, I2F, F2I, FMNMX, SHF, ISETP_SEL, FADD, LDS,
-       FFMA2_FFMA, FFMA2_LOP3, PRMT_FFMA, DP4A_PRMT, DP4A_FFMA, DP4A_IMAD, I2F_F2I, F2I_FFMA, I2F_PRMT, PRMT_IADD, DP4A_LOP3, FFMA_IMAD, DP4A_F2I, NMODES };
+       FFMA2_FFMA, FFMA2_LOP3, PRMT_FFMA, DP4A_PRMT, DP4A_FFMA, DP4A_IMAD, I2F_F2I, F2I_FFMA, I2F_PRMT, PRMT_IADD, DP4A_LOP3, FFMA_IMAD, DP4A_F2I, F2I32, I2IP, F2I32_I2IP, FADD2_DP4A, FADD2_PRMT, FADD2_FADD, F2I_DP4A_PRMT, NMODES };
 static const char *names[NMODES] = {"FFMA2", "FFMA", "FADD2", "PRMT", "LOP3", "IMAD", "IADD3", "IDP4A", "I2F.S32", "F2I.S8", "FMNMX", "SHF", "ISETP+SEL", "FADD", "LDS",
-       "FFMA2+FFMA", "FFMA2+LOP3", "PRMT+FFMA", "IDP4A+PRMT", "IDP4A+FFMA", "IDP4A+IMAD", "I2F+F2I", "F2I+FFMA", "I2F+PRMT", "PRMT+IADD3", "IDP4A+LOP3", "FFMA+IMAD", "IDP4A+F2I"};
-static const int group[NMODES] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2};
+       "FFMA2+FFMA", "FFMA2+LOP3", "PRMT+FFMA", "IDP4A+PRMT", "IDP4A+FFMA", "IDP4A+IMAD", "I2F+F2I", "F2I+FFMA", "I2F+PRMT", "PRMT+IADD3", "IDP4A+LOP3", "FFMA+IMAD", "IDP4A+F2I", "F2I.S32", "I2IP", "F2I.S32+I2IP", "FADD2+IDP4A", "FADD2+PRMT", "FADD2+FADD", "F2I.S8+IDP4A+PRMT"};
+static const int group[NMODES] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 1, 1, 2, 2, 2, 2, 3};
 
 template <int MODE> __global__ void k(uint64_t *out, long long *cyc, int iters, float seed) {
     __shared__ uint32_t sm[1024];
@@ -28,15 +28,18 @@ template <int MODE> __global__ void k(uint64_t *out, long long *cyc, int iters, 
 #define IS(m) (MODE == (m))
                 if (IS(FFMA2) || IS(FFMA2_FFMA) || IS(FFMA2_LOP3)) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(M), "l"(C));
                 if (IS(FFMA) || IS(FFMA2_FFMA) || IS(PRMT_FFMA) || IS(DP4A_FFMA) || IS(F2I_FFMA) || IS(FFMA_IMAD)) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(m2.x), "f"(c2.x));
-                if (IS(FADD2)) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(C));
-                if (IS(FADD)) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c2.x));
-                if (IS(PRMT) || IS(PRMT_FFMA) || IS(DP4A_PRMT) || IS(I2F_PRMT) || IS(PRMT_IADD)) asm volatile("prmt.b32 %0, %0, %1, 0x7650;" : "+r"(u[i]) : "r"(0x4B000000u + i));
+                if (IS(FADD2) || IS(FADD2_DP4A) || IS(FADD2_PRMT) || IS(FADD2_FADD)) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(a[i]) : "l"(C));
+                if (IS(FADD) || IS(FADD2_FADD)) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c2.x));
+                if (IS(PRMT) || IS(FADD2_PRMT) || IS(F2I_DP4A_PRMT) || IS(PRMT_FFMA) || IS(DP4A_PRMT) || IS(I2F_PRMT) || IS(PRMT_IADD)) asm volatile("prmt.b32 %0, %0, %1, 0x7650;" : "+r"(u[i]) : "r"(0x4B000000u + i));
                 if (IS(LOP3) || IS(FFMA2_LOP3) || IS(DP4A_LOP3)) asm volatile("lop3.b32 %0, %0, %1, %2, 0xEA;" : "+r"(u[i]) : "r"(0x80000000u), "r"(0x3EFFFFFFu + it));
                 if (IS(IMAD) || IS(DP4A_IMAD) || IS(FFMA_IMAD)) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(u[i]) : "r"(it | 3), "r"(i));
                 if (IS(IADD) || IS(PRMT_IADD)) asm volatile("add.s32 %0, %0, %1;" : "+r"(v[i]) : "r"(it));
-                if (IS(DP4A) || IS(DP4A_PRMT) || IS(DP4A_FFMA) || IS(DP4A_IMAD) || IS(DP4A_LOP3) || IS(DP4A_F2I)) asm volatile("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(v[i]) : "r"(u[(i + 1) & 7]), "r"(0x01020304 + it));
+                if (IS(DP4A) || IS(FADD2_DP4A) || IS(F2I_DP4A_PRMT) || IS(DP4A_PRMT) || IS(DP4A_FFMA) || IS(DP4A_IMAD) || IS(DP4A_LOP3) || IS(DP4A_F2I)) asm volatile("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(v[i]) : "r"(u[(i + 1) & 7]), "r"(0x01020304 + it));
                 if (IS(I2F) || IS(I2F_F2I) || IS(I2F_PRMT)) { float t; asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(t) : "r"(v[i])); f[i] = t; if (IS(I2F)) v[i] = __float_as_int(t) >> 1; }
                 if (IS(F2I) || IS(I2F_F2I) || IS(F2I_FFMA) || IS(DP4A_F2I)) { int t; asm volatile("cvt.rzi.sat.s8.f32 %0, %1;" : "=r"(t) : "f"(f[i])); v[i] = IS(DP4A_F2I) ? v[i] : t; if (IS(F2I)) f[i] = __int_as_float(t + 0x3f800000); if (IS(DP4A_F2I)) u[i] = t; }
+                if (IS(F2I_DP4A_PRMT)) { int t; asm volatile("cvt.rzi.sat.s8.f32 %0, %1;" : "=r"(t) : "f"(f[i])); f[i] = __int_as_float(t + 0x3f800000); }
+                if (IS(F2I32) || IS(F2I32_I2IP)) { int t; asm volatile("cvt.rzi.s32.f32 %0, %1;" : "=r"(t) : "f"(f[i])); if (IS(F2I32)) f[i] = __int_as_float(t + 0x3f800000); else v[i] = t; }
+                if (IS(I2IP) || IS(F2I32_I2IP)) asm volatile("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %0;" : "+r"(u[i]) : "r"(v[i]), "r"(v[(i + 1) & 7]));
                 if (IS(FMNMX)) asm volatile("max.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(c2.x + it));
                 if (IS(SHF)) asm volatile("shf.r.wrap.b32 %0, %0, %1, 3;" : "+r"(u[i]) : "r"(u[(i + 1) & 7]));
                 if (IS(ISETP_SEL)) { asm volatile("{.reg .pred p; setp.lt.u32 p, %0, %1; selp.u32 %0, %2, %0, p;}" : "+r"(u[i]) : "r"(0x7fffffffu - it), "r"(i + it)); }
