@@ -221,6 +221,10 @@ int mf_op_average_pool_2d(const mf_pool_desc *d, const void *in, void *out, size
 /* microflow::ops::softmax (src/ops/softmax.rs:15-27): over the whole rows x cols buffer of each sample */
 int mf_op_softmax(int32_t dtype, int32_t rows, int32_t cols, float in_scale, float out_scale, int32_t out_zero_point,
                   const void *in, void *out, size_t batch);
+/* MF_LAYOUT_NALGEBRA <-> MF_LAYOUT_NHWC conversion of `batch` matrices of rows x cols cells of elem_bytes each (host buffers; the
+ * device kernel predict* runs when a model is created with mf_options.layout = MF_LAYOUT_NALGEBRA).  Column-major storage is
+ * nalgebra's (src/buffer.rs:5-16).  to_nalgebra = 0: [cols][rows][cell] -> [rows][cols][cell]; 1: the opposite direction. */
+int mf_op_layout_transpose(const void *in, void *out, size_t batch, int32_t rows, int32_t cols, int32_t elem_bytes, int32_t to_nalgebra);
 /* Tensor::quantize / dequantize (src/tensor.rs:80-92, :246-262; src/quantize.rs:16-29) */
 int mf_op_quantize(int32_t dtype, float scale, int32_t zero_point, const float *in, void *out, size_t n);
 int mf_op_dequantize(int32_t dtype, float scale, int32_t zero_point, const void *in, float *out, size_t n);

@@ -91,7 +91,7 @@ ABI_SYMBOLS = [
     "mf_predict", "mf_predict_quantized", "mf_predict_many", "mf_predict_many_quantized", "mf_predict_many_quantized_async", "mf_predict_many_logits", "mf_predict_many_device",
     "mf_predict_trace", "mf_model_synchronize", "mf_model_set_profiling", "mf_model_layer_times_ms", "mf_model_launch_count", "mf_model_blob",
     "mf_host_alloc", "mf_host_free", "mf_op_conv_2d", "mf_op_conv_2d_create", "mf_op_run_device", "mf_op_kernel_name", "mf_op_destroy", "mf_op_fully_connected", "mf_op_average_pool_2d", "mf_op_softmax", "mf_op_quantize",
-    "mf_op_dequantize",
+    "mf_op_dequantize", "mf_op_layout_transpose",
 ]
 
 _lib = None
@@ -131,6 +131,7 @@ def lib():
         L.mf_predict_many_logits.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.mf_predict_many_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mf_predict_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.mf_op_layout_transpose.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         L.mf_model_synchronize.argtypes = [C.c_void_p]
         L.mf_model_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.mf_model_layer_times_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -458,6 +459,16 @@ class _Ops:
         out = np.zeros(x.shape, dtype)
         _check(lib().mf_op_quantize(DTYPE_U8 if np.dtype(dtype) == np.uint8 else DTYPE_I8, np.float32(scale), int(zp), x.ctypes.data, out.ctypes.data,
                                     x.size))
+        return out
+
+    def layout_transpose(self, x, to_nalgebra):
+        """x: [batch, rows, cols, cell...] (to_nalgebra) or [batch, cols, rows, cell...]; returns the other memory order."""
+        x = np.ascontiguousarray(x)
+        b, d1, d2 = x.shape[:3]
+        elem = int(np.prod(x.shape[3:], dtype=np.int64)) * x.itemsize
+        rows, cols = (d1, d2) if to_nalgebra else (d2, d1)
+        out = np.zeros((b, d2, d1) + x.shape[3:], x.dtype)
+        _check(lib().mf_op_layout_transpose(x.ctypes.data, out.ctypes.data, b, rows, cols, elem, 1 if to_nalgebra else 0))
         return out
 
     def dequantize(self, q, scale, zp):

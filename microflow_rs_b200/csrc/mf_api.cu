@@ -880,6 +880,27 @@ int mf_op_softmax(int32_t dtype, int32_t rows, int32_t cols, float in_scale, flo
     return run_single_layer(L, 0, in, out, batch);
 }
 
+int mf_op_layout_transpose(const void *in, void *out, size_t batch, int32_t rows, int32_t cols, int32_t elem_bytes, int32_t to_nalgebra) {
+    int rc = check_device(nullptr);
+    if (rc) return rc;
+    if (!in || !out || rows < 1 || cols < 1 || elem_bytes < 1) return fail(MF_ERR_INVALID_ARG, "bad argument");
+    const size_t bytes = batch * (size_t)rows * cols * elem_bytes;
+    if (!bytes) return MF_OK;
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    cudaError_t e = cudaSuccess;
+    do {
+        if ((e = cudaMalloc(&d_in, bytes)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_out, bytes)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(d_in, in, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        // the kernel writes dst[r][c] = src[c][r] for its (R, C): towards column-major the destination's outer index is the column
+        if ((e = launch_layout_transpose(d_in, d_out, (long long)batch, to_nalgebra ? cols : rows, to_nalgebra ? rows : cols, elem_bytes, nullptr)) != cudaSuccess) break;
+        if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
+        e = cudaMemcpy(out, d_out, bytes, cudaMemcpyDeviceToHost);
+    } while (false);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("layout_transpose_kernel: ") + cudaGetErrorString(e));
+    return MF_OK;
+}
 int mf_op_quantize(int32_t dtype, float scale, int32_t zero_point, const float *in, void *out, size_t n) {
     int rc = check_device(nullptr);
     if (rc) return rc;

@@ -1,4 +1,4 @@
-//! Raw bindings to `include/microflow_cuda.h` (ABI version 1).  UNBUILT here: no Rust toolchain in the image.
+//! Raw bindings to `include/microflow_cuda.h` (ABI version 2).  UNBUILT here: no Rust toolchain in the image.
 #![allow(non_camel_case_types)]
 use core::ffi::{c_char, c_int, c_void};
 
@@ -8,6 +8,9 @@ pub const MF_DTYPE_I8: i32 = 9;
 pub const MF_FLAG_HOST_ONLY: u32 = 1;
 pub const MF_FLAG_FORCE_GENERIC: u32 = 2;
 pub const MF_FLAG_NO_TENSOR_CORE: u32 = 4;
+pub const MF_LAYOUT_NHWC: u32 = 0;
+/// host buffers in nalgebra's column-major order: `Buffer4D` / `Buffer2D` memory is passed as it is
+pub const MF_LAYOUT_NALGEBRA: u32 = 1;
 
 #[repr(C)]
 pub struct mf_model {
@@ -21,6 +24,7 @@ pub struct mf_options {
     pub device: i32,
     pub chunk: u32,
     pub flags: u32,
+    pub layout: u32,
 }
 
 #[repr(C)]

@@ -1,7 +1,8 @@
 //! Drop-in for the functions `#[model("x.tflite")]` generates (microflow-macros/src/lib.rs:188-196), backed by the
 //! CUDA library.  UNBUILT here (no Rust toolchain).  Buffer types are the reference's: `Buffer2D = SMatrix<T, R, C>`
-//! (column-major) and `Buffer4D = [SMatrix<[T; CH], R, C>; B]` (src/buffer.rs:5-16), so inputs are transposed into the
-//! NHWC row-major layout the C ABI takes.
+//! (column-major) and `Buffer4D = [SMatrix<[T; CH], R, C>; B]` (src/buffer.rs:5-16); handles are created with
+//! `MF_LAYOUT_NALGEBRA`, so those buffers cross the C ABI as they lie in memory (the transposition to NHWC runs on the GPU).
+//! `nhwc_from_buffer4d` / `rowmajor_from_buffer2d` remain for callers that want NHWC handles.
 use core::ffi::c_void;
 use std::ffi::CStr;
 use std::sync::OnceLock;
@@ -27,8 +28,17 @@ fn check(rc: i32) {
 impl Handle {
     /// `include_bytes!("model.tflite")` -> parsed, pre-processed, uploaded once.
     pub fn from_bytes(bytes: &[u8]) -> Self {
+        // MF_LAYOUT_NALGEBRA: the library takes and returns the reference's column-major buffers as they lie in memory,
+        // so `predict*` below hands over `input.as_ptr()` without a host-side transposition.
+        let opt = sys::mf_options {
+            struct_size: core::mem::size_of::<sys::mf_options>() as u32,
+            device: -1,
+            chunk: 0,
+            flags: 0,
+            layout: sys::MF_LAYOUT_NALGEBRA,
+        };
         let mut h = core::ptr::null_mut();
-        check(unsafe { sys::mf_model_create_from_tflite(bytes.as_ptr() as *const c_void, bytes.len(), core::ptr::null(), &mut h) });
+        check(unsafe { sys::mf_model_create_from_tflite(bytes.as_ptr() as *const c_void, bytes.len(), &opt, &mut h) });
         Handle(h)
     }
 }
@@ -66,15 +76,16 @@ pub fn predict_quantized_4d<const B: usize, const R: usize, const C: usize, cons
     model: &Handle,
     input: &Buffer4D<i8, B, R, C, CH>,
 ) -> Buffer2D<f32, OR, OC> {
-    let x = nhwc_from_buffer4d(input);
-    let mut out = vec![0f32; OR * OC];
-    check(unsafe { sys::mf_predict_quantized(model.0, x.as_ptr() as *const c_void, out.as_mut_ptr()) });
-    Buffer2D::<f32, OR, OC>::from_row_slice(&out)
+    // `[SMatrix<[i8; CH], R, C>; B]` is B contiguous column-major matrices of CH-byte cells: exactly MF_LAYOUT_NALGEBRA
+    let mut out = Buffer2D::<f32, OR, OC>::zeros();
+    check(unsafe { sys::mf_predict_quantized(model.0, input.as_ptr() as *const c_void, out.as_mut_ptr()) });
+    out
 }
 
-/// New entry point: n independent samples, already NHWC int8, host buffers (pinned via mf_host_alloc for full PCIe speed).
-pub fn predict_many_quantized(model: &Handle, samples_nhwc: &[i8], n: usize, out: &mut [f32]) {
-    check(unsafe { sys::mf_predict_many_quantized(model.0, samples_nhwc.as_ptr() as *const c_void, n, out.as_mut_ptr()) });
+/// New entry point: n independent samples in the model's host layout (column-major per sample for handles made by
+/// `Handle::from_bytes`), host buffers (pinned via mf_host_alloc for full PCIe speed).
+pub fn predict_many_quantized(model: &Handle, samples: &[i8], n: usize, out: &mut [f32]) {
+    check(unsafe { sys::mf_predict_many_quantized(model.0, samples.as_ptr() as *const c_void, n, out.as_mut_ptr()) });
 }
 
 /// What the patched macro keeps in a `static`: one handle per `#[model]` struct.

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     L = mf.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.mf_abi_version() == 1
+    assert L.mf_abi_version() == 2
 
 
 def _has_gpu():
@@ -97,3 +97,23 @@ def test_model_dump(tmp_path):
     m.dump(p)
     text = p.read_text()
     assert "layer 1: op 4" in text and "c0:" in text
+
+
+def test_options_struct_is_versioned_by_struct_size():
+    """mf_options grew a `layout` field in ABI 2: a 16-byte ABI-1 struct is still accepted, an unknown layout is rejected."""
+    import ctypes as C
+    L = mf.lib()
+    assert L.mf_abi_version() == 2
+    data = (MODELS / "sine.tflite").read_bytes()
+
+    class OldOptions(C.Structure):
+        _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("chunk", C.c_uint32), ("flags", C.c_uint32)]
+
+    h = C.c_void_p()
+    old = OldOptions(C.sizeof(OldOptions), -1, 0, mf.FLAG_HOST_ONLY)
+    assert L.mf_model_create_from_tflite(data, len(data), C.cast(C.byref(old), C.POINTER(mf._Options)), C.byref(h)) == 0
+    L.mf_model_destroy(h)
+    with pytest.raises(mf.MicroflowError) as e:
+        mf.Model(MODELS / "sine.tflite", flags=mf.FLAG_HOST_ONLY, layout=7)
+    assert e.value.status == 9
+    mf.Model(MODELS / "person_detect.tflite", flags=mf.FLAG_HOST_ONLY, layout=mf.LAYOUT_NALGEBRA).close()

@@ -162,3 +162,37 @@ def test_small_calls_replay_a_cuda_graph_and_match_the_oracle(gpu_models, ora, n
     for rep in range(2):
         np.testing.assert_array_equal(m.predict_many(xf), want)
         np.testing.assert_array_equal(m.predict(xf[3]).reshape(-1), want[3])
+
+
+def test_nalgebra_layout_matches_nhwc(ora, samples):
+    """mf_options.layout = MF_LAYOUT_NALGEBRA: host buffers in the reference's own column-major Buffer4D order ([col][row][chan],
+    src/buffer.rs:10-16) give the same results as NHWC -- through the graph path (1 sample), the stream path, f32 and int8."""
+    o = ora["person_detect"]
+    a = mf.Model(MODELS / "person_detect.tflite")
+    b = mf.Model(MODELS / "person_detect.tflite", layout=mf.LAYOUT_NALGEBRA)
+    try:
+        n = 130
+        xs = splitmix_bytes(0x5EED0033, n * o.in_elems).reshape(n, 96, 96, 1)
+        xs[0] = np.asarray(samples["PERSON"]).reshape(96, 96, 1)
+        xt = np.ascontiguousarray(xs.transpose(0, 2, 1, 3))                      # [sample][col][row][chan]
+        want = a.predict_many_quantized(xs.reshape(n, -1))
+        np.testing.assert_array_equal(b.predict_many_quantized(xt.reshape(n, -1)), want)
+        np.testing.assert_array_equal(b.predict_quantized(xt[0].reshape(-1)).reshape(-1), f32([0.26953125, 0.73046875]))   # tests/person_detect.rs sample
+        qa, la = a.predict_many_logits(xs.reshape(n, -1)[:7])
+        qb, lb = b.predict_many_logits(xt.reshape(n, -1)[:7])
+        np.testing.assert_array_equal(qa, qb)
+        np.testing.assert_array_equal(la, lb)
+        xf = np.random.default_rng(9).uniform(-1, 1, (3, 96, 96, 1)).astype(np.float32)
+        np.testing.assert_array_equal(b.predict_many(np.ascontiguousarray(xf.transpose(0, 2, 1, 3)).reshape(3, -1)), a.predict_many(xf.reshape(3, -1)))
+    finally:
+        a.close(); b.close()
+
+
+@pytest.mark.parametrize("shape", [(3, 5, 7, 1), (2, 96, 96, 1), (4, 3, 3, 256), (1, 1, 9, 4), (2, 6, 1, 8)])
+@pytest.mark.parametrize("dtype", [np.int8, np.float32])
+def test_layout_transpose_kernel_both_directions(shape, dtype):
+    r = np.random.default_rng(sum(shape))
+    x = (r.integers(-128, 128, shape).astype(dtype) if dtype == np.int8 else r.standard_normal(shape).astype(dtype))
+    t = mf.ops.layout_transpose(x, to_nalgebra=True)
+    np.testing.assert_array_equal(t, x.transpose(0, 2, 1, 3))
+    np.testing.assert_array_equal(mf.ops.layout_transpose(t, to_nalgebra=False), x)
