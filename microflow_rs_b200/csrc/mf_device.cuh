@@ -125,6 +125,15 @@ template <bool FULL> __device__ __forceinline__ uint32_t requant4_biased(int a0,
     return pack4(y0, y1, y2, y3);
 }
 
+// same packed adds for accumulators of any magnitude (I2F on the XU pipe instead of the bias trick); full int8 clamp only
+__device__ __forceinline__ uint32_t requant4_i2f(int a0, int a1, int a2, int a3, float4 z, float4 s) {
+    const float2 t01 = fadd2(make_float2(z.x, z.y), make_float2(__fmul_rn(s.x, __int2float_rn(a0)), __fmul_rn(s.y, __int2float_rn(a1))));
+    const float2 t23 = fadd2(make_float2(z.z, z.w), make_float2(__fmul_rn(s.z, __int2float_rn(a2)), __fmul_rn(s.w, __int2float_rn(a3))));
+    const float2 r01 = fadd2(t01, make_float2(round_bias(t01.x), round_bias(t01.y)));
+    const float2 r23 = fadd2(t23, make_float2(round_bias(t23.x), round_bias(t23.y)));
+    return pack4(round_sat_s8<true>(r01.x, 0.f, 0.f), round_sat_s8<true>(r01.y, 0.f, 0.f), round_sat_s8<true>(r23.x, 0.f, 0.f), round_sat_s8<true>(r23.y, 0.f, 0.f));
+}
+
 // sign-extended byte k of a packed word: one PRMT (selector msb = replicate the sign of the selected byte)
 template <int K> __device__ __forceinline__ int sx8(uint32_t w) {
     int r;
