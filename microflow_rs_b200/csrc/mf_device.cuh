@@ -47,10 +47,9 @@ __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// XU-free variants for the hot kernels.  On sm_100 I2F / F2I / IDP.4A all issue to the XU pipe, which sustains only a few
-// lanes per clock per SM (ncu: XU at 130-150 % "of peak" in every first-generation kernel of this repo, profiles/).
-// The same results are obtained on the FMA / ALU pipes with exact bit tricks (each verified exhaustively on the host
-// against (float)x / roundf -- see DESIGN.md "XU-free epilogue"):
+// XU-free variants.  On sm_100 I2F / F2I issue to the XU pipe (measured: 4 and 8 clocks per warp instruction per sub-partition,
+// tools/ubench/pipes.cu; IDP.4A, IMAD, FADD2 share the FMA-heavy pipe at 2).  The same results are obtained on the FMA / ALU
+// pipes with exact bit tricks (each verified exhaustively on the host against (float)x / roundf -- see DESIGN.md):
 //   * i2f_exact<false>(x), |x| <= 2^22 : as_float(x + 0x4B400000) - 1.5*2^23   (ulp is 1 in [2^23, 2^24))
 //   * i2f_exact<true>(x), any int32    : x = hi*4096 + lo; hi*4096 and lo are built the same way in two binades and the
 //                                        single RN add of the two exact parts is the correctly rounded value of x
