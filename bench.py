@@ -309,7 +309,22 @@ def main():
     m.synchronize()
     e2e_s = time.perf_counter() - t0
     sampler.window(False)
+    n_timed = len(sampler.samples)
+    # The timed regions above last a few tens of milliseconds and an NVML query can take longer than that when several ranks
+    # poll at once, so the same device-resident steps keep running (untimed) for another half second while the sampler
+    # goes on: the clocks line then always rests on samples taken under this workload, and says how many fell where.
+    sampler.window(True)
+    t_end = time.perf_counter() + 0.5
+    i = 0
+    while time.perf_counter() < t_end:
+        step(i)
+        i += 1
+        if i % 8 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    sampler.window(False)
     clocks = sampler.stop()
+    clocks["samples_in_timed_regions"] = n_timed
     t = torch.tensor([e2e_s, e2e_block_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
