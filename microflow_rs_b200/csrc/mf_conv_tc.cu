@@ -73,6 +73,9 @@ struct ConvTcParams {
     long long num_tiles, OW, OH;
     float lo, hi;
     uint32_t idesc, stage_bytes, b_block_bytes, tmem_cols, nkb;
+    uint32_t stage_tx;          // bytes one stage's TMA load delivers (== stage_bytes unless the stage is padded to 1024)
+    uint32_t patch, patch_w;    // single-patch mode (ConvTcPlan::patch) and its patch width TW + KW - 1 in pixels
+    uint32_t acc_log2;          // log2 of the number of TMEM accumulator buffers (1 or 2): N <= 128 leaves room for four
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -132,10 +135,10 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t adesc, uint6
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows * 128 B = 1024)
 //   [46,48) version = 1 | [49,52) base_offset = 0 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t sbo_bytes = 1024) {
     uint64_t d = (uint64_t)((smem_addr >> 4) & 0x3FFFu);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
@@ -172,14 +175,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     float *s_c0z = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(bars) + 256);          // kTabSmem only
     float *s_c1 = s_c0z + p.N;
     int32_t *s_corr = reinterpret_cast<int32_t *>(s_c1 + p.N);                                 // [ncls][N]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 5);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 9);
 
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
     auto empty_bar = [&](uint32_t s) { return bar0 + 8u * (kMaxStages + s); };
     const uint32_t bfull_bar = bar0 + 8u * (2 * kMaxStages);
     auto tfull_bar = [&](uint32_t a) { return bar0 + 8u * (2 * kMaxStages + 1 + a); };
-    auto tempty_bar = [&](uint32_t a) { return bar0 + 8u * (2 * kMaxStages + 3 + a); };
+    auto tempty_bar = [&](uint32_t a) { return bar0 + 8u * (2 * kMaxStages + 5 + a); };
+    const uint32_t acc_mask = (1u << p.acc_log2) - 1u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KH = KH_T ? KH_T : p.KH, KW = KW_T ? KW_T : p.KW, CB = CB_T ? CB_T : p.CB;
@@ -194,8 +198,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == kWarpMma && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(bfull_bar, 1);
-        mbar_init(tfull_bar(0), 1); mbar_init(tfull_bar(1), 1);
-        mbar_init(tempty_bar(0), kEpiWarps); mbar_init(tempty_bar(1), kEpiWarps);
+        for (uint32_t a = 0; a <= acc_mask; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kWarpAlloc) {
@@ -227,10 +230,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     p.fd_img.divmod((uint32_t)tile, b, rem);
                     p.fd_tx.divmod(rem, ty, tx);
                 }
-                for (int n = 0; n < KW; ++n)
+                for (int n = 0; n < (p.patch ? 1 : KW); ++n)      // patch mode: one load per channel block brings every tap's data
                     for (int cb = 0; cb < CB; ++cb) {
                         mbar_wait(empty_bar(s), ph ^ 1);
-                        mbar_expect_tx(full_bar(s), p.stage_bytes);
+                        mbar_expect_tx(full_bar(s), p.stage_tx);
                         tma_load_4d(smem_u32(sA + (size_t)s * p.stage_bytes), &tmap_a, full_bar(s), cb * 128, (int)tx * p.TW + n - p.off_c,
                                     (int)ty * p.TH - p.off_r, (int)b);
                         if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
@@ -249,11 +252,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t stage16 = p.stage_bytes >> 4, bblk16 = p.b_block_bytes >> 4, arow16 = (uint32_t)p.TW * 8u;   // TW rows * 128 B / 16
             if (a0 + (uint32_t)p.stages * stage16 >= (1u << 14) || b0 + p.nkb * bblk16 >= (1u << 14)) __trap();     // descriptor start field would overflow
             for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+                const uint32_t acc = it & acc_mask, aph = (it >> p.acc_log2) & 1;
                 mbar_wait(tempty_bar(acc), aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.N;
                 uint32_t accumulate = 0;
+                if (p.patch) {
+                    // one stage per channel block holds the whole patch: tap (m, n) starts (m * patch_w + n) pixel rows into it and
+                    // the 8-row groups of the tile (TW == 8: one tile row each) are patch_w rows apart (SBO)
+                    const uint64_t desc_a = make_desc(0, p.patch_w * 128u);
+                    for (int cb = 0; cb < CB; ++cb) {
+                        mbar_wait(full_bar(s), ph);
+                        tc_fence_after();
+                        const uint64_t adesc = desc_a | (uint64_t)(a0 + s * stage16);
+                        const uint64_t bdesc = desc_hi | (uint64_t)(b0 + (uint32_t)cb * bblk16);
+#pragma unroll
+                        for (int m = 0; m < KH; ++m)
+#pragma unroll
+                            for (int n = 0; n < KW; ++n)
+#pragma unroll
+                                for (uint32_t ks = 0; ks < 4; ++ks) {
+                                    tc_mma_i8(d_tmem, adesc + (uint64_t)(((uint32_t)m * p.patch_w + (uint32_t)n) * 8u + 2 * ks),
+                                              bdesc + (uint64_t)((uint32_t)((m * KW + n) * CB) * bblk16 + 2 * ks), p.idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                        tc_commit(empty_bar(s));
+                        if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+                    }
+                } else
 #pragma unroll
                 for (int n = 0; n < KW; ++n)
 #pragma unroll
@@ -290,7 +316,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             pdl_wait();       // stores must not overtake the previous kernel's reads of the ping-pong buffer
             uint32_t it = 0;
             for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+                const uint32_t acc = it & acc_mask, aph = (it >> p.acc_log2) & 1;
                 bool valid;
                 bool on_border = false;                             // kTabBorder: does this warp own a pixel of a non-interior class in this tile?
                 const int32_t *corr = s_corr;
@@ -429,7 +455,7 @@ bool encode_map(CUtensorMap *map, const void *base, int rank, const cuuint64_t *
 
 size_t plan_smem(const ConvTcPlan &p, int stages) {
     const size_t b_bytes = (size_t)p.KH * p.KW * p.CB * p.N * 128;
-    const size_t stage = (size_t)(p.TH + p.KH - 1) * p.TW * 128;
+    const size_t stage = p.patch ? ((((size_t)(p.TH + p.KH - 1) * (p.TW + p.KW - 1) * 128) + 1023) & ~(size_t)1023) : (size_t)(p.TH + p.KH - 1) * p.TW * 128;
     const size_t tables = (size_t)p.N * 8 + (size_t)p.ncls * p.N * 4;
     return b_bytes + stage * stages + 256 + tables;
 }
@@ -483,6 +509,7 @@ bool conv_tc_finalize_plan(ConvTcPlan &p, std::string *why) {
     if ((int)p.h_c0z.size() != p.N || (int)p.h_c1.size() != p.N || (int)p.h_corr.size() != p.ncls * p.N) return no("epilogue tables have the wrong size");
     if (p.TH * p.TW != 128 || (p.TW & (p.TW - 1)) != 0 || p.TW < 8) return no("tile must be TH x TW = 128 pixels with TW a power of two >= 8");
     if (p.C != 128 * p.CB) return no("row bytes must be 128 * CB");
+    if (p.patch && (p.TW != 8 || (p.TW + p.KW - 1) * 128 >= (1 << 18))) return no("single-patch mode needs 8-pixel-wide tiles");
     if (p.TH + p.KH - 1 > 256) return no("patch too tall for one TMA box");
     int stages = 0;
     for (int s = 6; s >= 2; --s)
@@ -516,7 +543,8 @@ MapCache g_maps;
 cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_sms, cudaStream_t s, std::string *why) {
     CUtensorMap ta, tb;
     std::memcpy(&tb, p.tmap_b, sizeof tb);
-    const MapKey key{l.in, l.W, l.H, l.B, p.C, p.TW, p.TH + p.KH - 1};
+    const int box_w = p.patch ? p.TW + p.KW - 1 : p.TW;
+    const MapKey key{l.in, l.W, l.H, l.B, p.C, box_w, p.TH + p.KH - 1};
     bool found = false;
     {
         std::lock_guard<std::mutex> lock(g_maps.mu);
@@ -526,7 +554,7 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     if (!found) {
         cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)l.W, (cuuint64_t)l.H, (cuuint64_t)l.B};
         cuuint64_t strides[3] = {(cuuint64_t)p.C, (cuuint64_t)p.C * l.W, (cuuint64_t)p.C * l.W * l.H};
-        cuuint32_t box[4] = {128, (cuuint32_t)p.TW, (cuuint32_t)(p.TH + p.KH - 1), 1};
+        cuuint32_t box[4] = {128, (cuuint32_t)box_w, (cuuint32_t)(p.TH + p.KH - 1), 1};
         if (!encode_map(&ta, l.in, 4, dims, strides, box, why)) return cudaErrorInvalidValue;
         std::lock_guard<std::mutex> lock(g_maps.mu);
         if (g_maps.v.size() >= 256) g_maps.v.clear();
@@ -555,10 +583,19 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 @4, a/b format INT8 = 1 @7/@10,
     // K-major A and B (bits 15, 16 = 0), n_dim = N >> 3 @17, m_dim = 128 >> 4 @24
     k.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
-    k.stage_bytes = (uint32_t)((p.TH + p.KH - 1) * p.TW * 128);
+    k.stage_tx = (uint32_t)((p.TH + p.KH - 1) * box_w * 128);
+    k.stage_bytes = p.patch ? ((k.stage_tx + 1023u) & ~1023u) : k.stage_tx;      // every stage base stays 1024-byte aligned (swizzle atom)
+    k.patch = p.patch ? 1u : 0u;
+    k.patch_w = (uint32_t)(p.TW + p.KW - 1);
     k.b_block_bytes = (uint32_t)(p.N * 128);
     k.nkb = (uint32_t)(p.KH * p.KW * p.CB);
-    k.tmem_cols = 2 * p.N <= 32 ? 32 : (2 * p.N <= 64 ? 64 : (2 * p.N <= 128 ? 128 : (2 * p.N <= 256 ? 256 : 512)));
+    // TMEM accumulator ring: two buffers; MF_TC_ACC=4 uses four when they fit the 512 columns (N <= 128), letting the MMA issuer
+    // run three tiles ahead of the slowest epilogue warp.  Measured no faster (config 5: 0.1010 vs 0.1000 ms; person_detect
+    // 1.058 vs 1.057 ms/step, profiles/r01j_conv3x3_experiments.txt): the accumulator hand-off is not what limits either side.
+    static const int env_acc = [] { const char *e = std::getenv("MF_TC_ACC"); return e ? std::atoi(e) : 2; }();
+    k.acc_log2 = (4 * p.N <= 512 && env_acc >= 4) ? 2u : 1u;
+    const uint32_t need_cols = (uint32_t)p.N << k.acc_log2;
+    k.tmem_cols = need_cols <= 32 ? 32 : (need_cols <= 64 ? 64 : (need_cols <= 128 ? 128 : (need_cols <= 256 ? 256 : 512)));
     if (k.num_tiles <= 0) return cudaSuccess;
 
     // the F2I.S8 / I2F epilogue needs the full int8 clamp range (F2I.S8 saturation is the clamp); MF_TC_XUG=0 forces the XU-free one
@@ -590,7 +627,7 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
         if (periodic && env_tab != kTabGroup) fn = conv_tc_kernel<false, true, 1, 1, 1, kTabPeriod>;
         else if (p.N <= 128) fn = conv_tc_kernel<false, true, 1, 1, 1, kTabGroup>;
     }
-    // measured slower than kTabSmem on BASELINE config 5 (0.138 vs 0.103 ms per launch, profiles/r01j_conv3x3_tab_modes.txt): the
+    // measured slower than kTabSmem on BASELINE config 5 (0.138 vs 0.103 ms per launch, profiles/r01j_conv3x3_experiments.txt): the
     // four code copies per sub-partition cost more than the LDS traffic they remove, so the mode stays opt-in (MF_TC_TAB=3)
     if (shape == 1 && xu && p.big_acc && p.ncls == 9 && p.N <= 128 && env_tab == kTabBorder) {
         fn = conv_tc_kernel<true, true, 3, 3, 1, kTabBorder>;

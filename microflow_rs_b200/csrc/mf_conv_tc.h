@@ -34,6 +34,11 @@ struct ConvTcPlan {
     int ncls = 1;       // border classes (1, or 9 for 3x3)
     int stages = 2;
     size_t smem_bytes = 0;
+    // KxK only: one stage = the whole (TH+KH-1) x (TW+KW-1) input patch of a tile, loaded ONCE; every kernel tap is a UMMA
+    // descriptor whose start is offset by (m * (TW+KW-1) + n) pixels (128-byte rows) and whose 8-row group stride (SBO) is one
+    // patch row -- which needs TW == 8 so that an 8-row core-matrix group is one row of the tile.  The input then crosses
+    // L2 -> shared memory 1.4x (halo) instead of 3.75x (three column-shifted patches).
+    bool patch = false;
     // device buffer owned by the model blob
     const uint8_t *d_wmat = nullptr;   // [N][K_total] bytes, K_total = KH*KW*C
     // epilogue tables (host copies; they travel to the kernel as __grid_constant__ parameters = constant bank)

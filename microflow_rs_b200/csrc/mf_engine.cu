@@ -129,6 +129,10 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
                     const long long work = (long long)((L.OW + tw - 1) / tw) * tw * ((L.OH + th - 1) / th) * th;
                     if (best < 0 || work < best) { best = work; tc.TW = tw; tc.TH = th; }
                 }
+                {   // single-patch staging (mf_conv_tc.h): 16 x 8 tiles, the input patch is fetched once per tile
+                    static const bool env_patch = [] { const char *e = std::getenv("MF_TC_PATCH"); return !e || std::atoi(e) != 0; }();
+                    if (env_patch) { tc.patch = true; tc.TW = 8; tc.TH = 16; }
+                }
                 tc.lo = (float)L.act_lo; tc.hi = (float)L.act_hi; tc.big_acc = big_acc;
                 std::vector<int32_t> corr = conv_tc_border_corr_3x3(L.w.data(), L.Cout, L.Cin, L.in_zp, L.H, L.W);
                 o_tc_w = o_w;  // OHWI is already the [N][K_total] matrix
