@@ -196,3 +196,24 @@ def test_layout_transpose_kernel_both_directions(shape, dtype):
     t = mf.ops.layout_transpose(x, to_nalgebra=True)
     np.testing.assert_array_equal(t, x.transpose(0, 2, 1, 3))
     np.testing.assert_array_equal(mf.ops.layout_transpose(t, to_nalgebra=False), x)
+
+
+def test_device_resident_full_batch_splits_into_two_streams(gpu_models, ora):
+    """A device-resident call of >= 4096 samples per chunk runs as two half-chunks on the model's two internal streams, joined on
+    the caller's stream: the result must equal the host path (oracle-checked above) row for row, and be ordered on that stream."""
+    torch = pytest.importorskip("torch")
+    m, o = gpu_models["person_detect"], ora["person_detect"]
+    n = 8192 + 9
+    base = splitmix_bytes(0x5EED0044, 1031 * o.in_elems).reshape(1031, -1)
+    xs = np.concatenate([base] * (n // 1031) + [base[: n % 1031]])
+    want = m.predict_many_quantized(xs)
+    ref, _ = o.predict_many_quantized(xs[:32], threads=oracle.max_threads())
+    np.testing.assert_array_equal(want[:32], ref)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        d_in = torch.from_numpy(xs.copy()).cuda()
+        d_out = torch.zeros((n, o.out_elems), dtype=torch.float32, device="cuda")
+        for _ in range(3):                                   # back-to-back calls reuse both streams' buffers
+            m.predict_many_device(d_in.data_ptr(), n, d_out.data_ptr(), None, st.cuda_stream)
+        got = d_out.cpu().numpy()                            # ordered behind the calls on the same stream
+    np.testing.assert_array_equal(got, want)
