@@ -254,6 +254,7 @@ const char *LayerExec::launched_name(const uint8_t *in, uint8_t *out, long long 
         a.in = in; a.out = out; a.batch = batch;
         if (!no_smem && kernel == Kernel::DwConv3x3Rows && dwconv3x3_smem_eligible(a)) return "dwconv3x3_smem_kernel";
         if (!no_smem && kernel == Kernel::DwConvCin1 && dwconv_cin1_smem_eligible(a)) return "dwconv_cin1_smem_kernel";
+        if (!no_smem && kernel == Kernel::DwConvCin1 && dwconv_cin1_taps_eligible(a)) return "dwconv_cin1_taps_kernel";
     }
     return kernel_name(kernel);
 }
@@ -275,6 +276,7 @@ cudaError_t LayerExec::run(const uint8_t *in, uint8_t *out, long long batch, int
             {
                 static const bool no_smem = std::getenv("MF_DW_NO_SMEM") != nullptr;
                 if (!no_smem && dwconv_cin1_smem_eligible(a)) return launch_dwconv_cin1_smem(a, num_sms, s);
+                if (!no_smem && dwconv_cin1_taps_eligible(a)) return launch_dwconv_cin1_taps(a, num_sms, s);
             }
             return launch_dwconv_cin1(a, s);
         }

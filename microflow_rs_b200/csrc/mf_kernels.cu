@@ -11,6 +11,7 @@
 //
 // Reference semantics: src/ops/conv_2d.rs:50-107, depthwise_conv_2d.rs:50-104, fully_connected.rs:42-81,
 // average_pool_2d.rs:46-65, softmax.rs:20-26, src/tensor.rs:180-228 (view), src/quantize.rs:16-29.
+#include <algorithm>
 #include <cstdlib>
 
 #include "mf_device.cuh"
@@ -906,6 +907,172 @@ cudaError_t launch_dwconv_cin1_smem(const ConvArgs &a, int num_sms, cudaStream_t
     long long ctas = (long long)num_sms * per_sm;
     if (ctas > a.batch) ctas = a.batch;
     return launch_pdl(fn, dim3((unsigned)ctas), dim3(kDwSmemThreads), smem, s, a.pdl, a, in_bytes, buf_stride, nbuf, nstrip, rows);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depth-multiplier first layer with a LARGE kernel (speech layer 1: 10x8 taps, Cin == 1 -> 8 channels, stride 2): 80 MACs per
+// output, i.e. compute-bound -- the generic-shape kernel above spends one IMAD per tap and channel.  Here the whole sample sits
+// in shared memory inside a frame of zero-point bytes (rows and columns the window can reach outside the image), so the taps of
+// a kernel row are consecutive bytes of one padded row: two PRMT assemble them from three aligned words and ONE dp4a does four
+// taps of one channel.  A thread owns PX = 2 output pixels x 8 channels, so the weight words (shared memory, broadcast LDS.128)
+// are fetched once for both.  The next sample's words are prefetched into registers while the current one is computed
+// (two slots, one __syncthreads per sample).
+// ------------------------------------------------------------------------------------------------
+constexpr int kTapsThreads = 256;
+template <int NW, bool FULL>   // NW = ceil(KW / 4) words of taps per kernel row
+__global__ void __launch_bounds__(kTapsThreads, 3) dwconv_cin1_taps_kernel(ConvArgs a, int Hp, int Wp, int pad_l, uint32_t slot_bytes) {
+    constexpr int COUT = 8, PX = 2, PF = 4;                              // PF: prefetched words per thread (H * W / 4 <= PF * threads)
+    extern __shared__ __align__(16) uint8_t tsm[];
+    uint32_t *wsm = reinterpret_cast<uint32_t *>(tsm);                   // [KH][NW][COUT] packed tap words
+    uint8_t *slots = tsm + (((size_t)a.KH * NW * COUT * 4 + 15) & ~(size_t)15);
+    const int tid = threadIdx.x;
+    const long long first = blockIdx.x, step = gridDim.x;
+    for (int e = tid; e < a.KH * NW * COUT; e += kTapsThreads) {
+        const int c = e % COUT, q = (e / COUT) % NW, m = e / (COUT * NW);
+        uint32_t v = 0;
+        for (int k = 0; k < 4; ++k) {
+            const int n = 4 * q + k;
+            if (n < a.KW) v |= (uint32_t)a.w[(m * a.KW + n) * COUT + c] << (8 * k);
+        }
+        wsm[e] = v;
+    }
+    {   // both slots start as a frame of zero-point bytes; the sample interior is overwritten for every sample
+        const uint32_t izw = (uint32_t)(a.in_zp & 0xff) * 0x01010101u;
+        uint32_t *sw = reinterpret_cast<uint32_t *>(slots);
+        for (uint32_t i = tid; i < 2 * (slot_bytes >> 2); i += kTapsThreads) sw[i] = izw;
+    }
+    const int npx = a.OH * a.OW;
+    const int wrow = a.W >> 2;                                           // words per image row (W % 4 == 0)
+    const int nwords = a.H * wrow;
+    // where this thread's prefetched words go inside a slot (word k of the sample -> padded row off_r + k / wrow, column pad_l + ...)
+    uint32_t dstw[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+        const int k = tid + u * kTapsThreads;
+        const int r = k / wrow, cw = k - r * wrow;
+        dstw[u] = k < nwords ? (uint32_t)(((r + a.off_r) * Wp + pad_l) >> 2) + (uint32_t)cw : 0xffffffffu;
+    }
+    // this thread's two output pixels: byte offset of the window origin inside a slot, and the PRMT selector of its misalignment
+    uint32_t worg[PX], sel[PX];
+    bool pvalid[PX];
+#pragma unroll
+    for (int u = 0; u < PX; ++u) {
+        const int px = tid + u * kTapsThreads;
+        pvalid[u] = px < npx;
+        const int i = pvalid[u] ? px / a.OW : 0, j = pvalid[u] ? px - i * a.OW : 0;
+        const int pc0 = a.sw * j - a.off_c + pad_l;                     // >= 0
+        worg[u] = (uint32_t)(a.sh * i * Wp + (pc0 & ~3));
+        const uint32_t kk = (uint32_t)(pc0 & 3);
+        sel[u] = kk | ((kk + 1) << 4) | ((kk + 2) << 8) | ((kk + 3) << 12);
+    }
+    int init[COUT];
+    float zr[COUT], sr[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) { init[c] = kAccBias - __ldg(a.kcorr + c); zr[c] = __ldg(a.c0z + c); sr[c] = __ldg(a.c1 + c); }
+    const float lo = a.lo, hi = a.hi;
+    pdl_trigger();
+    pdl_wait();
+    uint32_t pre[PF];
+    auto fetch = [&](long long b) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.in + (size_t)b * a.H * a.W);
+#pragma unroll
+        for (int u = 0; u < PF; ++u)
+            if (dstw[u] != 0xffffffffu) pre[u] = __ldg(src + tid + u * kTapsThreads);
+    };
+    auto stash = [&](int slot) {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(slots + (size_t)slot * slot_bytes);
+#pragma unroll
+        for (int u = 0; u < PF; ++u)
+            if (dstw[u] != 0xffffffffu) dst[dstw[u]] = pre[u];
+    };
+    if (first < a.batch) { fetch(first); }
+    __syncthreads();                                                     // frames and weights written
+    if (first < a.batch) stash(0);
+    __syncthreads();
+    int slot = 0;
+    for (long long b = first; b < a.batch; b += step, slot ^= 1) {
+        const bool more = b + step < a.batch;
+        if (more) fetch(b + step);                                       // in flight while this sample is computed
+        const uint8_t *img = slots + (size_t)slot * slot_bytes;
+        int acc[PX][COUT];
+#pragma unroll
+        for (int u = 0; u < PX; ++u)
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) acc[u][c] = init[c];
+        const uint32_t *rowp0 = reinterpret_cast<const uint32_t *>(img + worg[0]);
+        const uint32_t *rowp1 = reinterpret_cast<const uint32_t *>(img + worg[1]);
+        const int wp4 = Wp >> 2;
+        const uint4 *wq = reinterpret_cast<const uint4 *>(wsm);
+        for (int m = 0; m < a.KH; ++m) {
+            uint32_t t[PX][NW];
+            {
+                uint32_t v[NW + 1];
+#pragma unroll
+                for (int q = 0; q <= NW; ++q) v[q] = rowp0[q];
+#pragma unroll
+                for (int q = 0; q < NW; ++q) asm("prmt.b32 %0, %1, %2, %3;" : "=r"(t[0][q]) : "r"(v[q]), "r"(v[q + 1]), "r"(sel[0]));
+#pragma unroll
+                for (int q = 0; q <= NW; ++q) v[q] = rowp1[q];
+#pragma unroll
+                for (int q = 0; q < NW; ++q) asm("prmt.b32 %0, %1, %2, %3;" : "=r"(t[1][q]) : "r"(v[q]), "r"(v[q + 1]), "r"(sel[1]));
+            }
+            rowp0 += wp4; rowp1 += wp4;
+#pragma unroll
+            for (int q = 0; q < NW; ++q) {
+                const uint4 wa = wq[(m * NW + q) * 2], wb = wq[(m * NW + q) * 2 + 1];
+                const uint32_t wv[COUT] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) {
+                    acc[0][c] = __dp4a((int)t[0][q], (int)wv[c], acc[0][c]);
+                    acc[1][c] = __dp4a((int)t[1][q], (int)wv[c], acc[1][c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PX; ++u)
+            if (pvalid[u]) {
+                uint2 *o = reinterpret_cast<uint2 *>(a.out) + (size_t)b * npx + tid + u * kTapsThreads;
+                *o = make_uint2(requant4_biased<FULL>(acc[u][0], acc[u][1], acc[u][2], acc[u][3], make_float4(zr[0], zr[1], zr[2], zr[3]), make_float4(sr[0], sr[1], sr[2], sr[3]), lo, hi),
+                                requant4_biased<FULL>(acc[u][4], acc[u][5], acc[u][6], acc[u][7], make_float4(zr[4], zr[5], zr[6], zr[7]), make_float4(sr[4], sr[5], sr[6], sr[7]), lo, hi));
+            }
+        if (more) stash(slot ^ 1);                                       // the other slot was last read one iteration ago (barrier below)
+        __syncthreads();
+    }
+}
+
+// Window geometry of the padded slot: rows 0 .. Hp-1 cover input rows -off_r .. , columns start pad_l bytes left of the image
+static void taps_geometry(const ConvArgs &a, int &Hp, int &Wp, int &pad_l) {
+    pad_l = (a.off_c + 3) & ~3;
+    const int need_r = std::max(a.H + a.off_r, (a.OH - 1) * a.sh + a.KH);
+    const int need_c = std::max(a.W + pad_l, (a.OW - 1) * a.sw - a.off_c + pad_l + ((a.KW + 3) & ~3) + 4);   // + one word: the PRMT reads NW + 1 words
+    Hp = need_r;
+    Wp = (need_c + 3) & ~3;
+}
+bool dwconv_cin1_taps_eligible(const ConvArgs &a) {
+    if (!(a.depthwise && !a.is_u8 && a.Cin == 1 && a.Cout == 8 && a.kcorr != nullptr && !a.big_acc)) return false;
+    if (a.KW < 1 || a.KW > 8 || a.KH < 1 || a.KH * a.KW > 128 || a.KH * a.KW <= 9) return false;            // 3x3 has its own kernel
+    if (a.W % 4 != 0 || a.off_r < 0 || a.off_c < 0 || a.batch < 148 * 2) return false;
+    if ((long long)a.H * a.W / 4 > 4ll * kTapsThreads || a.OH * a.OW > 2 * kTapsThreads) return false;
+    if (((uintptr_t)a.in % 4) != 0 || ((uintptr_t)a.out % 8) != 0 || ((long long)a.H * a.W) % 4 != 0) return false;
+    int Hp, Wp, pad_l;
+    taps_geometry(a, Hp, Wp, pad_l);
+    return 2ll * (((long long)Hp * Wp + 15) & ~15ll) + a.KH * 2 * 8 * 4 + 64 <= 64 * 1024;
+}
+cudaError_t launch_dwconv_cin1_taps(const ConvArgs &a, int num_sms, cudaStream_t s) {
+    int Hp, Wp, pad_l;
+    taps_geometry(a, Hp, Wp, pad_l);
+    const int NW = (a.KW + 3) / 4;
+    const uint32_t slot_bytes = (uint32_t)(((size_t)Hp * Wp + 15) & ~(size_t)15);
+    const size_t smem = (((size_t)a.KH * NW * 8 * 4 + 15) & ~(size_t)15) + 2 * (size_t)slot_bytes;
+    const bool full = a.lo == -128.f && a.hi == 127.f;
+    using Fn = void (*)(ConvArgs, int, int, int, uint32_t);
+    Fn fn = NW == 1 ? (full ? dwconv_cin1_taps_kernel<1, true> : dwconv_cin1_taps_kernel<1, false>)
+                    : (full ? dwconv_cin1_taps_kernel<2, true> : dwconv_cin1_taps_kernel<2, false>);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(64 * 1024));
+    if (e != cudaSuccess) return e;
+    long long ctas = (long long)num_sms * 3;
+    if (ctas > a.batch) ctas = a.batch;
+    return launch_pdl(fn, dim3((unsigned)ctas), dim3(kTapsThreads), smem, s, a.pdl, a, Hp, Wp, pad_l, slot_bytes);
 }
 
 bool dwconv_cin1_eligible(const ConvArgs &a) {

@@ -137,6 +137,8 @@ bool dwconv_cin1_eligible(const ConvArgs &a);    // depthwise with Cin == 1 (dep
 cudaError_t launch_dwconv_cin1(const ConvArgs &a, cudaStream_t s);
 bool dwconv_cin1_smem_eligible(const ConvArgs &a);   // 3x3, Cout == 8, whole input image staged by cp.async.bulk (large batches)
 cudaError_t launch_dwconv_cin1_smem(const ConvArgs &a, int num_sms, cudaStream_t s);
+bool dwconv_cin1_taps_eligible(const ConvArgs &a);   // Cin == 1 -> 8 channels, kernels of 10..128 taps (speech layer 1): dp4a along the kernel rows
+cudaError_t launch_dwconv_cin1_taps(const ConvArgs &a, int num_sms, cudaStream_t s);
 bool pwconv_dp4a_eligible(const ConvArgs &a);    // 1x1 conv (any stride), Cin % 4 == 0, any Cout
 cudaError_t launch_pwconv_dp4a(const ConvArgs &a, cudaStream_t s);
 bool fc_warp_eligible(const FcArgs &a);          // K % 16 == 0, N <= 8

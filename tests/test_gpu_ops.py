@@ -174,6 +174,11 @@ FAST_SIMT_CASES = [
     (300, 96, 96, 1, 8, 3, 3, 2, 2, "same", "relu6", True, "dwconv_cin1_smem"),            # person_detect layer 0 at full extent
     (300, 15, 48, 1, 8, 3, 3, 2, 2, "valid", "relu6", True, "dwconv_cin1"),
     (300, 20, 16, 1, 8, 3, 3, 2, 1, "same", "relu", True, "dwconv_cin1"),                  # mixed strides stay on the generic-shape fast kernel
+    # large kernels with Cin == 1: dp4a along the taps of a kernel row inside a zero-point frame (speech layer 1 and relatives)
+    (300, 49, 40, 1, 8, 10, 8, 2, 2, "same", "relu", True, "dwconv_cin1_taps"),            # speech layer 1 at full extent
+    (300, 20, 16, 1, 8, 4, 4, 1, 1, "valid", "none", True, "dwconv_cin1_taps"),            # one word of taps per row, no frame, full clamp
+    (300, 21, 24, 1, 8, 7, 5, 2, 1, "same", "relu6", True, "dwconv_cin1_taps"),            # 5 taps per row (zero-padded to 8), mixed strides
+    (300, 9, 8, 1, 8, 12, 8, 1, 1, "same", "relu", True, "dwconv_cin1_taps"),              # kernel taller than the image
     (3, 1, 1, 256, 2, 1, 1, 1, 1, "same", "none", False, "pwconv_dp4a"),            # person_detect's last conv (Cout = 2)
     (2, 4, 4, 16, 7, 1, 1, 1, 1, "same", "relu", False, "pwconv_dp4a"),
     (3, 12, 12, 8, 16, 1, 1, 1, 1, "same", "relu6", False, "pwconv_dp4a|conv_tc"),   # person_detect layer 2 shape
