@@ -69,6 +69,8 @@ struct mf_model {
     // reshapes, softmax.  Per-layer tracing runs the layers one by one instead.
     int tail_first = -1, tail_conv = -1, tail_last = -1;
     TailArgs tail;
+    // fully_connected (fc_warp_kernel) -> reshape* -> softmax (last layer) as one launch: layers [fc_tail_first .. fc_tail_last]
+    int fc_tail_first = -1, fc_tail_last = -1;
     size_t slot_rr = 0;                     // round-robin position of the host-path stream slots
     cudaEvent_t split_ev[3] = {nullptr, nullptr, nullptr};   // MF_SPLIT=2: fork / join events of the two half-batch streams
     // Small host-path calls (n <= kGraphMaxN, the reference's one-sample predict() above all) replay a captured CUDA graph:
@@ -177,6 +179,24 @@ int run_chunk(mf_model *m, Slot &s, const uint8_t *d_in, size_t n, float *d_out_
             i = (size_t)m->tail_last;
             continue;
         }
+        if ((int)i == m->fc_tail_first && !layer_outs_host) {   // fully_connected + softmax in one launch (speech's classifier)
+            FcArgs a = L.fc;
+            const SoftmaxArgs &sa = m->layers[(size_t)m->fc_tail_last].sm;
+            a.in = cur; a.out = d_logits; a.batch = (long long)n; a.pdl = pdl;
+            a.sm_out = s.act[flip];
+            a.exp_lut = sa.exp_lut; a.sm_rows = sa.rows; a.sm_cols = sa.cols;
+            a.sm_out_scale = sa.out_scale; a.sm_out_zp = sa.out_zp; a.sm_lo = sa.lo; a.sm_hi = sa.hi;
+            cudaError_t e = launch_fc_warp(a, st);
+            if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("fc_warp_kernel(+softmax) launch failed: ") + cudaGetErrorString(e));
+            m->launches += 1;
+            pdl = use_pdl;
+            cur = a.sm_out;
+            flip ^= 1;
+            if (prof)
+                for (size_t k = i; k <= (size_t)m->fc_tail_last; ++k) MF_CUDA(cudaEventRecord(prof[k + 1], st));
+            i = (size_t)m->fc_tail_last;
+            continue;
+        }
         if (d_logits && (int)i == m->softmax_tail) {
             MF_CUDA(cudaMemcpyAsync(d_logits, cur, n * L.spec.in_elems, cudaMemcpyDeviceToDevice, st));
             pdl = 0;
@@ -233,6 +253,19 @@ void plan_tail(mf_model *m) {
         m->tail_first = i; m->tail_conv = i + 1; m->tail_last = j;
         return;
     }
+}
+
+// Recognises fully_connected (<= 8 outputs, fc_warp_kernel) -> reshape* -> softmax as the last layers.
+void plan_fc_tail(mf_model *m) {
+    const int n = (int)m->layers.size();
+    if (m->softmax_tail != n - 1 || m->tail_first >= 0) return;
+    int j = n - 2;
+    while (j >= 0 && m->layers[(size_t)j].kernel == Kernel::None) --j;
+    if (j < 0 || m->layers[(size_t)j].kernel != Kernel::FcWarp) return;
+    const SoftmaxArgs &sa = m->layers[(size_t)n - 1].sm;
+    if (m->layers[(size_t)n - 1].kernel != Kernel::Softmax || sa.rows * sa.cols != m->layers[(size_t)j].fc.N) return;
+    m->fc_tail_first = j;
+    m->fc_tail_last = n - 1;
 }
 
 int need_device(const mf_model *m) {
@@ -446,7 +479,7 @@ int create_model(const uint8_t *buf, size_t len, const mf_options *opt, mf_model
         }
         for (auto &L : m->layers)
             if (!L.resolve(m->d_blob, &err)) return fail(MF_ERR_CUDA, err);
-        if (impl != 1 && !std::getenv("MF_NO_TAIL_FUSE")) plan_tail(m.get());
+        if (impl != 1 && !std::getenv("MF_NO_TAIL_FUSE")) { plan_tail(m.get()); plan_fc_tail(m.get()); }
         for (int k = 0; k < 2; ++k) {
             rc = alloc_slot(m.get(), m->slot[k]);
             if (rc) return rc;
@@ -548,6 +581,7 @@ int mf_model_layer_info(const mf_model *m, int i, mf_layer_info *o) {
     if (!m->host_only) kn = E.launched_name(m->slot[0].act[0], m->slot[0].act[1], 1 << 20);   // the variant large batches run on
     if (m->tail_first >= 0 && i >= m->tail_first && i <= m->tail_last && E.kernel != Kernel::None)
         kn = i == m->tail_first ? "tail_fused_kernel" : "(in tail_fused_kernel)";
+    if (m->fc_tail_first >= 0 && i > m->fc_tail_first && i <= m->fc_tail_last && E.kernel != Kernel::None) kn = "(in fc_warp_kernel)";
     std::snprintf(o->kernel, sizeof o->kernel, "%s", kn);
     return MF_OK;
 }

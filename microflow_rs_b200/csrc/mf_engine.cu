@@ -301,7 +301,7 @@ cudaError_t LayerExec::run(const uint8_t *in, uint8_t *out, long long batch, int
         }
         case Kernel::FcGeneric: case Kernel::FcWarp: {
             FcArgs a = fc;
-            a.in = in; a.out = out; a.batch = batch;
+            a.in = in; a.out = out; a.batch = batch; a.pdl = pdl;
             return kernel == Kernel::FcWarp ? launch_fc_warp(a, s) : launch_fc_generic(a, s);
         }
         case Kernel::PoolGeneric: {

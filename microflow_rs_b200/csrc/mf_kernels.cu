@@ -1151,6 +1151,8 @@ template <int N_T>
 __global__ void __launch_bounds__(256) fc_warp_kernel(FcArgs a) {
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();
     if (warp >= a.batch) return;
     const int4 *x = reinterpret_cast<const int4 *>(a.in + (size_t)warp * a.K);
     const int chunks = a.K >> 4;
@@ -1177,12 +1179,31 @@ __global__ void __launch_bounds__(256) fc_warp_kernel(FcArgs a) {
 #pragma unroll
         for (int j = 0; j < N_T; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
     }
+    if (a.sm_out == nullptr) {
 #pragma unroll
-    for (int j = 0; j < N_T; ++j) {
-        if (lane == j && j < a.N) {
-            const int t = acc[j] - rowsum * a.w_zp - a.c2[j] + a.c3;
-            a.out[(size_t)warp * a.N + j] = (uint8_t)requant(t, a.c0z[j], a.c1, a.lo, a.hi);
+        for (int j = 0; j < N_T; ++j) {
+            if (lane == j && j < a.N) {
+                const int t = acc[j] - rowsum * a.w_zp - a.c2[j] + a.c3;
+                a.out[(size_t)warp * a.N + j] = (uint8_t)requant(t, a.c0z[j], a.c1, a.lo, a.hi);
+            }
         }
+        return;
+    }
+    // fused softmax tail: every lane holds all N sums after the butterfly; lane 0 finishes the sample exactly as
+    // fc (above) + softmax_kernel would (same summation order, same divisions)
+    if (lane != 0) return;
+    int q[N_T];
+#pragma unroll
+    for (int j = 0; j < N_T; ++j)
+        q[j] = j < a.N ? (requant(acc[j] - rowsum * a.w_zp - a.c2[j] + a.c3, a.c0z[j], a.c1, a.lo, a.hi) & 0xff) : 0;
+    if (a.out)
+        for (int j = 0; j < a.N; ++j) a.out[(size_t)warp * a.N + j] = (uint8_t)q[j];
+    float sumexp = 0.0f;
+    for (int j = 0; j < a.sm_cols; ++j)
+        for (int i = 0; i < a.sm_rows; ++i) sumexp = __fadd_rn(sumexp, __ldg(a.exp_lut + q[i * a.sm_cols + j]));
+    for (int k = 0; k < a.N; ++k) {
+        const float t = __fadd_rn(__fdiv_rn(__fdiv_rn(__ldg(a.exp_lut + q[k]), sumexp), a.sm_out_scale), a.sm_out_zp);
+        a.sm_out[(size_t)warp * a.N + k] = (uint8_t)round_clamp(t, a.sm_lo, a.sm_hi);
     }
 }
 
@@ -1263,9 +1284,8 @@ bool fc_warp_eligible(const FcArgs &a) { return !a.is_u8 && (a.K % 16) == 0 && a
 cudaError_t launch_fc_warp(const FcArgs &a, cudaStream_t s) {
     if (a.batch <= 0) return cudaSuccess;
     const unsigned grid = grid_for(a.batch * 32, 256);
-    if (a.N <= 4) fc_warp_kernel<4><<<grid, 256, 0, s>>>(a);
-    else fc_warp_kernel<8><<<grid, 256, 0, s>>>(a);
-    return cudaGetLastError();
+    if (a.N <= 4) return launch_pdl(fc_warp_kernel<4>, dim3(grid), dim3(256), 0, s, a.pdl, a);
+    return launch_pdl(fc_warp_kernel<8>, dim3(grid), dim3(256), 0, s, a.pdl, a);
 }
 
 }  // namespace mf

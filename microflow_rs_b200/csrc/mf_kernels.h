@@ -75,6 +75,13 @@ struct FcArgs {
     float lo = -128.f, hi = 127.f;
     int is_u8 = 0;
     long long batch = 0;
+    // fc_warp_kernel only: a trailing softmax over the N outputs of each sample run by the same warp (softmax_kernel's arithmetic).
+    // sm_out == nullptr: plain fully_connected.  `out` then receives the FC result (the softmax input = "logits") if non-null.
+    uint8_t *sm_out = nullptr;
+    const float *exp_lut = nullptr;
+    int sm_rows = 1, sm_cols = 1;
+    float sm_out_scale = 1.f, sm_out_zp = 0.f, sm_lo = -128.f, sm_hi = 127.f;
+    int pdl = 0;
 };
 
 struct PoolArgs {
