@@ -252,7 +252,7 @@ const char *LayerExec::launched_name(const uint8_t *in, uint8_t *out, long long 
         static const bool no_smem = std::getenv("MF_DW_NO_SMEM") != nullptr;
         ConvArgs a = conv;
         a.in = in; a.out = out; a.batch = batch;
-        if (!no_smem && kernel == Kernel::DwConv3x3Rows && dwconv3x3_smem_eligible(a)) return "dwconv3x3_smem_kernel";
+        if (!no_smem && kernel == Kernel::DwConv3x3Rows && dwconv3x3_smem_eligible(a)) return dwconv3x3_uses_pair(a) ? "dwconv3x3_pair_kernel" : "dwconv3x3_smem_kernel";
         if (!no_smem && kernel == Kernel::DwConvCin1 && dwconv_cin1_smem_eligible(a)) return "dwconv_cin1_smem_kernel";
         if (!no_smem && kernel == Kernel::DwConvCin1 && dwconv_cin1_taps_eligible(a)) return "dwconv_cin1_taps_kernel";
     }

@@ -460,7 +460,7 @@ __device__ __forceinline__ void transpose_3x4(uint32_t v0, uint32_t v1, uint32_t
 // whatever lies one pixel left / right in memory (the neighbouring row, the header or the tail padding): its three weight
 // bytes are zeroed in that thread's registers, so the garbage is multiplied by 0, and the thread's correction term only sums
 // the weights that remain -- exactly the reference's masked filter sum (conv_2d.rs:83-89 / depthwise_conv_2d.rs:80-86).
-constexpr uint32_t kDwHead = 512, kDwTail = 256;     // >= 4 * (C / 4) bytes for C <= 256 on either side
+constexpr uint32_t kDwHead = 512, kDwTail = 768;     // head >= one pixel (C <= 256 bytes) + the 128-byte barrier block; tail >= two pixels (pair kernel) + slack
 
 template <int S, bool FULL, int MINB>
 __global__ void __launch_bounds__(kDwSmemThreads, MINB) dwconv3x3_smem_kernel(ConvArgs a, uint32_t in_bytes, uint32_t buf_stride, int nbuf, int xw, int nstrip,
@@ -609,6 +609,169 @@ __global__ void __launch_bounds__(kDwSmemThreads, MINB) dwconv3x3_smem_kernel(Co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stride-1 variant with TWO output columns per thread.  The window of the column pair (2jj, 2jj+1) is four input columns:
+// a 4x4 byte transpose (8 PRMT) leaves, per channel, one register holding (col0, col1, col2, col3), and the two outputs are
+// dp4a against (w0, w1, w2, 0) and (0, w0, w1, w2).  Per 8 outputs: 4 LDS + 8 PRMT instead of 6 + 12, half the address / loop /
+// barrier instructions, and two independent accumulator chains per thread for the scheduler to interleave.  Same slot layout,
+// border handling (zeroed weight bytes + per-thread correction) and epilogue as dwconv3x3_smem_kernel; CTAs are 96 or 128
+// threads (one strip of a 192-word-wide row is 96 pairs), 5 per SM.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void transpose_4x4(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t (&t)[4]) {
+    const uint32_t lo01 = prmt<0x5140>(v0, v1), hi01 = prmt<0x7362>(v0, v1);
+    const uint32_t lo23 = prmt<0x5140>(v2, v3), hi23 = prmt<0x7362>(v2, v3);
+    t[0] = prmt<0x5410>(lo01, lo23);
+    t[1] = prmt<0x7632>(lo01, lo23);
+    t[2] = prmt<0x5410>(hi01, hi23);
+    t[3] = prmt<0x7632>(hi01, hi23);
+}
+constexpr int kDwPairMaxThreads = 128;
+template <bool FULL, int MINB>
+__global__ void __launch_bounds__(kDwPairMaxThreads, MINB) dwconv3x3_pair_kernel(ConvArgs a, uint32_t in_bytes, uint32_t buf_stride, int nbuf, int xwp, int nstrip,
+                                                                                int rows_per_strip) {
+    extern __shared__ __align__(128) uint8_t dsm[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(dsm);
+    uint8_t *bufs = dsm + kDwHead;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+    const uint32_t buf0 = (uint32_t)__cvta_generic_to_shared(bufs);
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const uint32_t nwarps = (uint32_t)nthreads >> 5;
+    const long long first = blockIdx.x, step = gridDim.x;
+    const int G = a.Cout >> 2;
+    const uint32_t row_bytes = (uint32_t)(a.W * G) * 4u;
+    if (tid == 0) {
+        for (int k = 0; k < nbuf; ++k) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * k), "r"(1u) : "memory");
+            reinterpret_cast<uint32_t *>(dsm + 64)[k] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const uint32_t izw = (uint32_t)(a.in_zp & 0xff) * 0x01010101u;
+        const int rw = (int)(row_bytes >> 2);
+        for (int k = 0; k < nbuf; ++k) {
+            uint32_t *top = reinterpret_cast<uint32_t *>(bufs + (size_t)k * buf_stride);
+            uint32_t *bot = reinterpret_cast<uint32_t *>(bufs + (size_t)k * buf_stride + row_bytes + in_bytes);
+            for (int i = tid; i < rw; i += nthreads) { top[i] = izw; bot[i] = izw; }
+        }
+    }
+    __syncthreads();
+    auto request = [&](long long b, int slot) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8u * slot), "r"(in_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf0 + (uint32_t)slot * buf_stride + row_bytes),
+                     "l"(a.in + (size_t)b * in_bytes), "r"(in_bytes), "r"(bar0 + 8u * slot)
+                     : "memory");
+    };
+    pdl_trigger();
+    if (tid == 0) {
+        pdl_wait();
+        for (int k = 0; k < nbuf; ++k)
+            if (first + (long long)k * step < a.batch) request(first + (long long)k * step, k);
+    }
+
+    const bool active = tid < xwp * nstrip;
+    const int strip = active ? tid / xwp : 0;
+    const int x = active ? tid - strip * xwp : 0;
+    const int jj = x / G, g = x - jj * G;
+    const int j0 = 2 * jj;
+    const bool second = j0 + 1 < a.OW;                                  // an odd output width leaves the last pair half empty
+    const int c0 = j0 - a.off_c;                                        // leftmost of the four window columns
+    // wa[T][c] = (w[T][0], w[T][1], w[T][2], 0) for column j0, wb[T][c] = (0, w[T][0], w[T][1], w[T][2]) for column j0 + 1, each with
+    // the taps that fall on window columns outside the image zeroed
+    uint32_t wa[3][4], wb[3][4];
+    int fresh_a[4], fresh_b[4];
+    {
+        const uint32_t *ww = reinterpret_cast<const uint32_t *>(a.w);
+        uint32_t keep = 0;                                              // byte k <-> window column c0 + k
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((unsigned)(c0 + k) < (unsigned)a.W) keep |= 0xffu << (8 * k);
+        int sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int T = 0; T < 3; ++T) {
+            uint32_t wq[4];
+            transpose_3x4(__ldg(ww + (size_t)(3 * T) * G + g), __ldg(ww + (size_t)(3 * T + 1) * G + g), __ldg(ww + (size_t)(3 * T + 2) * G + g), wq);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t w3 = wq[c] & 0x00ffffffu;
+                wa[T][c] = w3 & keep;
+                wb[T][c] = (w3 << 8) & keep;
+                sa[c] = __dp4a((int)wa[T][c], 0x01010101, sa[c]);
+                sb[c] = __dp4a((int)wb[T][c], 0x01010101, sb[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { fresh_a[c] = kAccBias - a.in_zp * sa[c]; fresh_b[c] = kAccBias - a.in_zp * sb[c]; }
+    }
+    const float4 z = __ldg(reinterpret_cast<const float4 *>(a.c0z) + g);
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(a.c1) + g);
+    const int i0 = strip * rows_per_strip;
+    const int i1 = active ? min(a.OH, i0 + rows_per_strip) : i0;
+    const int out_row_words = a.OW * G;
+    const float lo = a.lo, hi = a.hi;
+    const int poff = (int)(row_bytes >> 2) * (1 + i0 - a.off_r) + c0 * G + g;
+    const int row_words = (int)(row_bytes >> 2);
+
+    pdl_wait();
+    int slot = 0;
+    uint32_t phase = 0;
+    const uint32_t *pslot = reinterpret_cast<const uint32_t *>(bufs) + poff;
+    uint32_t *osample = reinterpret_cast<uint32_t *>(a.out) + ((size_t)first * a.OH + i0) * out_row_words + (size_t)j0 * G + g;
+    const size_t ostep = (size_t)step * a.OH * out_row_words;
+    const uint32_t slot_words = buf_stride >> 2;
+    for (long long b = first; b < a.batch; b += step) {
+        sm_mbar_wait(bar0 + 8u * slot, phase);
+        if (i1 > i0) {
+            const uint32_t *p = pslot;
+            uint32_t *o = osample;
+            auto take = [&](uint32_t (&t)[4]) {
+                const uint32_t v0 = p[0], v1 = p[G], v2 = p[2 * G], v3 = p[3 * G];
+                p += row_words;
+                transpose_4x4(v0, v1, v2, v3, t);
+            };
+            struct Acc { int a[4], b[4]; };
+            Acc init;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { init.a[c] = fresh_a[c]; init.b[c] = fresh_b[c]; }
+            auto mac = [&](Acc &A, const uint32_t (&t)[4], int T) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    A.a[c] = __dp4a((int)t[c], (int)wa[T][c], A.a[c]);
+                    A.b[c] = __dp4a((int)t[c], (int)wb[T][c], A.b[c]);
+                }
+            };
+            auto store = [&](const Acc &A) {
+                o[0] = requant4_biased<FULL>(A.a[0], A.a[1], A.a[2], A.a[3], z, sc, lo, hi);
+                const uint32_t y1 = requant4_biased<FULL>(A.b[0], A.b[1], A.b[2], A.b[3], z, sc, lo, hi);
+                if (second) o[G] = y1;
+                o += out_row_words;
+            };
+            uint32_t t[4];
+            Acc A = init, B = init, C = init;
+            int left = i1 - i0;
+            take(t); mac(A, t, 0);
+            take(t); mac(A, t, 1); mac(B, t, 0);
+            while (true) {
+                take(t); mac(A, t, 2); mac(B, t, 1); C = init; mac(C, t, 0); store(A); if (--left == 0) break;
+                take(t); mac(B, t, 2); mac(C, t, 1); A = init; mac(A, t, 0); store(B); if (--left == 0) break;
+                take(t); mac(C, t, 2); mac(A, t, 1); B = init; mac(B, t, 0); store(C); if (--left == 0) break;
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) {
+            uint32_t old;
+            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(bar0 + 64u + 4u * slot) : "memory");
+            if (old == nwarps - 1u) {
+                reinterpret_cast<volatile uint32_t *>(dsm + 64)[slot] = 0;
+                if (b + (long long)nbuf * step < a.batch) request(b + (long long)nbuf * step, slot);
+            }
+        }
+        osample += ostep;
+        pslot += slot_words;
+        if (++slot == nbuf) { slot = 0; phase ^= 1u; pslot -= (size_t)nbuf * slot_words; }
+    }
+}
+
 // shapes the sample-resident kernel takes: 3x3, stride 1x1 / 2x2, one block spans the full output width, whole input fits a ring buffer
 bool dwconv3x3_smem_eligible(const ConvArgs &a) {
     if (!(dwconv_c4_eligible(a) && a.KH == 3 && a.KW == 3 && a.sh == a.sw && (a.sh == 1 || a.sh == 2))) return false;
@@ -621,10 +784,48 @@ bool dwconv3x3_smem_eligible(const ConvArgs &a) {
           
            ((uintptr_t)a.in % 16) == 0;
 }
+bool dwconv3x3_uses_pair(const ConvArgs &a) {
+    static const int env_pair = [] { const char *e = std::getenv("MF_DW_PAIR"); return e ? std::atoi(e) : 1; }();
+    // an odd output width leaves the last pair half empty: measured slower on the 3-wide map (22.8 vs 20.8 us), so pairs need an
+    // even width or one wide enough for the idle half-pair not to matter (MF_DW_PAIR=2 forces pairs everywhere, for tests)
+    const bool width_ok = (a.OW % 2) == 0 || a.OW >= 9 || env_pair == 2;
+    return env_pair && a.sh == 1 && width_ok && ((a.OW + 1) / 2) * (a.Cout / 4) <= kDwPairMaxThreads;
+}
 cudaError_t launch_dwconv3x3_smem(const ConvArgs &a, int num_sms, cudaStream_t s) {
     const uint32_t in_bytes = (uint32_t)(a.H * a.W * a.Cin);
     const uint32_t buf_stride = (in_bytes + 2u * (uint32_t)(a.W * a.Cin) + 127u) & ~127u;   // sample + a zero-point row either side
     const int xw = a.OW * (a.Cout / 4);
+    const int xwp = ((a.OW + 1) / 2) * (a.Cout / 4);
+    if (dwconv3x3_uses_pair(a)) {   // stride 1: two output columns per thread
+        // CTA size and CTAs/SM measured on person_detect's layers (profiles/r01k_dw_pair_sweep.txt): 96/128 threads x 4 per SM
+        // beats x 3, x 5, x 6 and 192-thread CTAs
+        int nstrip = kDwPairMaxThreads / xwp;
+        if (nstrip > a.OH) nstrip = a.OH;
+        const int rows = (a.OH + nstrip - 1) / nstrip;
+        nstrip = (a.OH + rows - 1) / rows;
+        const int threads = (xwp * nstrip + 31) & ~31;
+        static const int env_pminb = [] { const char *e = std::getenv("MF_DW_PAIR_MINB"); return e ? std::atoi(e) : 4; }();
+        int per_sm = env_pminb < 2 ? 2 : (env_pminb > 6 ? 6 : env_pminb), nbuf = 0;
+        const int minb = per_sm;
+        for (; per_sm >= 1; --per_sm) {
+            const long long share = (227ll * 1024) / per_sm - 1024 - (long long)(kDwHead + kDwTail);
+            nbuf = (int)(share / buf_stride);
+            if (nbuf > 4) nbuf = 4;
+            if (nbuf >= 2 || per_sm == 1) break;
+        }
+        if (nbuf < 1) return cudaErrorInvalidConfiguration;
+        const size_t smem = kDwHead + (size_t)nbuf * buf_stride + kDwTail;
+        const bool full = a.lo == -128.f && a.hi == 127.f;
+        using Fn = void (*)(ConvArgs, uint32_t, uint32_t, int, int, int, int);
+#define MF_DWP_PICK(M) (full ? dwconv3x3_pair_kernel<true, M> : dwconv3x3_pair_kernel<false, M>)
+        Fn fn = minb >= 6 ? MF_DWP_PICK(6) : (minb == 5 ? MF_DWP_PICK(5) : (minb == 4 ? MF_DWP_PICK(4) : (minb == 3 ? MF_DWP_PICK(3) : MF_DWP_PICK(2))));
+#undef MF_DWP_PICK
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+        if (e != cudaSuccess) return e;
+        long long ctas = (long long)num_sms * per_sm;
+        if (ctas > a.batch) ctas = a.batch;
+        return launch_pdl(fn, dim3((unsigned)ctas), dim3((unsigned)threads), smem, s, a.pdl, a, in_bytes, buf_stride, nbuf, xwp, nstrip, rows);
+    }
     int nstrip = kDwSmemThreads / xw;
     if (nstrip > a.OH) nstrip = a.OH;
     const int rows = (a.OH + nstrip - 1) / nstrip;

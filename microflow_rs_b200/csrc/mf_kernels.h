@@ -140,6 +140,7 @@ bool dwconv3x3_rows_eligible(const ConvArgs &a); // + 3x3, stride 1x1 or 2x2: sl
 cudaError_t launch_dwconv3x3_rows(const ConvArgs &a, cudaStream_t s);
 bool dwconv3x3_smem_eligible(const ConvArgs &a); // + whole sample staged in shared memory by cp.async.bulk (large batches)
 cudaError_t launch_dwconv3x3_smem(const ConvArgs &a, int num_sms, cudaStream_t s);
+bool dwconv3x3_uses_pair(const ConvArgs &a);     // stride 1: launch_dwconv3x3_smem runs dwconv3x3_pair_kernel (two output columns per thread)
 bool dwconv_cin1_eligible(const ConvArgs &a);    // depthwise with Cin == 1 (depth multiplier), Cout % 4 == 0, Cout <= 16
 cudaError_t launch_dwconv_cin1(const ConvArgs &a, cudaStream_t s);
 bool dwconv_cin1_smem_eligible(const ConvArgs &a);   // 3x3, Cout == 8, whole input image staged by cp.async.bulk (large batches)

@@ -157,17 +157,17 @@ FAST_SIMT_CASES = [
     (2, 17, 5, 4, 4, 3, 3, 1, 1, "same", "none", True, "dwconv3x3_rows"),
     (2, 9, 9, 8, 8, 3, 3, 2, 1, "same", "none", True, "dwconv_c4"),
     # batch >= 296 switches the 3x3 depthwise to the sample-resident (cp.async.bulk) kernel
-    (300, 12, 12, 8, 8, 3, 3, 1, 1, "same", "relu6", True, "dwconv3x3_smem"),
-    (300, 8, 8, 32, 32, 3, 3, 2, 2, "same", "relu6", True, "dwconv3x3_smem"),
-    (333, 6, 6, 128, 128, 3, 3, 1, 1, "same", "relu", True, "dwconv3x3_smem"),
-    (300, 9, 7, 16, 16, 3, 3, 1, 1, "valid", "none", True, "dwconv3x3_(smem|rows)"),
-    (300, 11, 13, 8, 8, 3, 3, 2, 2, "valid", "relu6", True, "dwconv3x3_(smem|rows)"),
-    (300, 3, 3, 256, 256, 3, 3, 1, 1, "same", "relu6", True, "dwconv3x3_smem"),
+    (300, 12, 12, 8, 8, 3, 3, 1, 1, "same", "relu6", True, "dwconv3x3_(smem|pair)"),
+    (300, 8, 8, 32, 32, 3, 3, 2, 2, "same", "relu6", True, "dwconv3x3_(smem|pair)"),
+    (333, 6, 6, 128, 128, 3, 3, 1, 1, "same", "relu", True, "dwconv3x3_(smem|pair)"),
+    (300, 9, 7, 16, 16, 3, 3, 1, 1, "valid", "none", True, "dwconv3x3_(smem|rows|pair)"),
+    (300, 11, 13, 8, 8, 3, 3, 2, 2, "valid", "relu6", True, "dwconv3x3_(smem|rows|pair)"),
+    (300, 3, 3, 256, 256, 3, 3, 1, 1, "same", "relu6", True, "dwconv3x3_(smem|pair)"),
     # window columns outside the image are handled by zeroed per-thread weights + a per-thread correction term:
-    (300, 7, 5, 16, 16, 3, 3, 2, 2, "same", "relu6", True, "dwconv3x3_smem"),              # odd width, stride 2: the right column falls outside
-    (300, 4, 1, 32, 32, 3, 3, 1, 1, "same", "none", True, "dwconv3x3_smem"),               # one-pixel-wide image: left AND right outside for the same thread
-    (300, 6, 6, 64, 64, 3, 3, 1, 1, "same", "relu", True, "dwconv3x3_smem"),               # clamp narrower than int8 (FULL = false epilogue)
-    (300, 2, 2, 8, 8, 3, 3, 1, 1, "same", "relu6", True, "dwconv3x3_smem"),                # every output pixel is a corner
+    (300, 7, 5, 16, 16, 3, 3, 2, 2, "same", "relu6", True, "dwconv3x3_(smem|pair)"),              # odd width, stride 2: the right column falls outside
+    (300, 4, 1, 32, 32, 3, 3, 1, 1, "same", "none", True, "dwconv3x3_(smem|pair)"),               # one-pixel-wide image: left AND right outside for the same thread
+    (300, 6, 6, 64, 64, 3, 3, 1, 1, "same", "relu", True, "dwconv3x3_(smem|pair)"),               # clamp narrower than int8 (FULL = false epilogue)
+    (300, 2, 2, 8, 8, 3, 3, 1, 1, "same", "relu6", True, "dwconv3x3_(smem|pair)"),                # every output pixel is a corner
     (300, 32, 32, 1, 8, 3, 3, 2, 2, "same", "relu6", True, "dwconv_cin1_smem"),        # sample-resident Cin=1 kernel (layer-0 shape, scaled down)
     (300, 20, 16, 1, 8, 3, 3, 1, 1, "valid", "relu", True, "dwconv_cin1"),                 # same kernel, stride 1, no padding, partial clamp
     (300, 10, 32, 1, 8, 3, 3, 1, 1, "same", "none", True, "dwconv_cin1"),                  # stride 1: a column outside on both sides
