@@ -99,24 +99,33 @@ class ClockSampler:
     def window(self, on):
         self.active = on
 
-    def stop(self):
+    @staticmethod
+    def _reasons(samples):
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80}
+        return sorted({k for _, rs in samples for k, bit in names.items() if rs & bit})
+
+    def stop(self, n_timed=None):
+        """n_timed: how many of the samples fell inside the timed regions (the rest: the untimed extension under the same load).
+        `sm_mhz` / `reasons` describe the timed regions when they hold samples, else the extension; both are reported."""
         self.stop_flag = True
         if self.thread:
             self.thread.join(timeout=1)
         if self.nv is None or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         nv = self.nv
-        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80}
-        reasons = set()
-        for _, rs in self.samples:
-            for k, bit in names.items():
-                if rs & bit:
-                    reasons.add(k)
         try:
             mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
         except Exception:
             mx = None
-        return {"sm_mhz": float(np.median([s for s, _ in self.samples])), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(self.samples)}
+        n_timed = len(self.samples) if n_timed is None else n_timed
+        timed, ext = self.samples[:n_timed], self.samples[n_timed:]
+        main = timed if timed else ext
+        out = {"sm_mhz": float(np.median([s for s, _ in main])), "sm_max_mhz": mx, "reasons": self._reasons(main), "samples": len(self.samples),
+               "samples_in_timed_regions": len(timed)}
+        if ext:
+            out["extension"] = {"sm_mhz": float(np.median([s for s, _ in ext])), "reasons": self._reasons(ext), "samples": len(ext),
+                                "what": "0.5 s of the same device-resident steps, untimed, right after the timed regions"}
+        return out
 
 
 def cpu_baseline(workload, seconds=12.0, threads=1, max_samples=4096):
@@ -323,8 +332,7 @@ def main():
             torch.cuda.synchronize()
     torch.cuda.synchronize()
     sampler.window(False)
-    clocks = sampler.stop()
-    clocks["samples_in_timed_regions"] = n_timed
+    clocks = sampler.stop(n_timed)
     t = torch.tensor([e2e_s, e2e_block_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
