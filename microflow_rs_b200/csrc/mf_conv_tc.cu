@@ -75,7 +75,6 @@ struct ConvTcParams {
     uint32_t idesc, stage_bytes, b_block_bytes, tmem_cols, nkb;
     uint32_t stage_tx;          // bytes one stage's TMA load delivers (== stage_bytes unless the stage is padded to 1024)
     uint32_t patch, patch_w;    // single-patch mode (ConvTcPlan::patch) and its patch width TW + KW - 1 in pixels
-    uint32_t acc_log2;          // log2 of the number of TMEM accumulator buffers (1 or 2): N <= 128 leaves room for four
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -183,7 +182,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t bfull_bar = bar0 + 8u * (2 * kMaxStages);
     auto tfull_bar = [&](uint32_t a) { return bar0 + 8u * (2 * kMaxStages + 1 + a); };
     auto tempty_bar = [&](uint32_t a) { return bar0 + 8u * (2 * kMaxStages + 5 + a); };
-    const uint32_t acc_mask = (1u << p.acc_log2) - 1u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KH = KH_T ? KH_T : p.KH, KW = KW_T ? KW_T : p.KW, CB = CB_T ? CB_T : p.CB;
@@ -198,7 +196,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == kWarpMma && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(bfull_bar, 1);
-        for (uint32_t a = 0; a <= acc_mask; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
+        for (uint32_t a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kWarpAlloc) {
@@ -252,7 +250,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t stage16 = p.stage_bytes >> 4, bblk16 = p.b_block_bytes >> 4, arow16 = (uint32_t)p.TW * 8u;   // TW rows * 128 B / 16
             if (a0 + (uint32_t)p.stages * stage16 >= (1u << 14) || b0 + p.nkb * bblk16 >= (1u << 14)) __trap();     // descriptor start field would overflow
             for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-                const uint32_t acc = it & acc_mask, aph = (it >> p.acc_log2) & 1;
+                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
                 mbar_wait(tempty_bar(acc), aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.N;
@@ -315,16 +313,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const float lo = p.lo, hi = p.hi;
             pdl_wait();       // stores must not overtake the previous kernel's reads of the ping-pong buffer
             uint32_t it = 0;
-            for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-                const uint32_t acc = it & acc_mask, aph = (it >> p.acc_log2) & 1;
+            // LINEAR: this thread's row and output pointer advance by a constant per tile (no multiplies in the tile loop)
+            uint32_t lin_ox = blockIdx.x * 128u + (uint32_t)row;
+            uint8_t *lin_row = p.out + (size_t)lin_ox * (size_t)p.N;
+            const uint32_t lin_step = gridDim.x * 128u;
+            const size_t lin_bytes = (size_t)lin_step * (size_t)p.N;
+            const uint32_t ntiles = (uint32_t)p.num_tiles;
+            for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
                 bool valid;
                 bool on_border = false;                             // kTabBorder: does this warp own a pixel of a non-interior class in this tile?
                 const int32_t *corr = s_corr;
                 uint8_t *orow;
                 if (LINEAR) {                                       // one row of 128-byte (packed) pixels: tile t covers rows [128 t, 128 t + 128)
-                    const long long ox = tile * 128 + row;
-                    valid = ox < p.OW;
-                    orow = p.out + ox * p.N;
+                    valid = lin_ox < (uint32_t)p.OW;                // conv_tc_launch keeps OW below 2^31 for the LINEAR instantiations
+                    orow = lin_row;
+                    lin_ox += lin_step;
+                    lin_row += lin_bytes;
                 } else {
                     uint32_t b, rem, ty, tx;
                     p.fd_img.divmod((uint32_t)tile, b, rem);
@@ -341,7 +346,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 mbar_wait(tfull_bar(acc), aph);
                 tc_fence_after();
                 const uint32_t t_base = tmem_base + acc * (uint32_t)p.N + ((q * 32u) << 16);
-                for (int c0 = 32 * cg; c0 < p.N; c0 += 128) {
+                constexpr bool ONE_CHUNK = TAB == kTabGroup || TAB == kTabBorder;      // N <= 128: a warp's only chunk
+                for (int c0 = 32 * cg; c0 < p.N; c0 += (ONE_CHUNK ? 1 << 20 : 128)) {
                     uint32_t r[32];
                     tmem_ld32(t_base + (uint32_t)c0, r);
                     uint32_t w[8];
@@ -589,12 +595,9 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     k.patch_w = (uint32_t)(p.TW + p.KW - 1);
     k.b_block_bytes = (uint32_t)(p.N * 128);
     k.nkb = (uint32_t)(p.KH * p.KW * p.CB);
-    // TMEM accumulator ring: two buffers; MF_TC_ACC=4 uses four when they fit the 512 columns (N <= 128), letting the MMA issuer
-    // run three tiles ahead of the slowest epilogue warp.  Measured no faster (config 5: 0.1010 vs 0.1000 ms; person_detect
-    // 1.058 vs 1.057 ms/step, profiles/r01j_conv3x3_experiments.txt): the accumulator hand-off is not what limits either side.
-    static const int env_acc = [] { const char *e = std::getenv("MF_TC_ACC"); return e ? std::atoi(e) : 2; }();
-    k.acc_log2 = (4 * p.N <= 512 && env_acc >= 4) ? 2u : 1u;
-    const uint32_t need_cols = (uint32_t)p.N << k.acc_log2;
+    // TMEM accumulator ring: two buffers.  Four (they fit the 512 columns when N <= 128) were measured no faster -- config 5: 0.1010
+    // vs 0.1000 ms; person_detect 1.058 vs 1.057 ms/step (profiles/r01j_conv3x3_experiments.txt) -- and were removed again.
+    const uint32_t need_cols = 2u * (uint32_t)p.N;
     k.tmem_cols = need_cols <= 32 ? 32 : (need_cols <= 64 ? 64 : (need_cols <= 128 ? 128 : (need_cols <= 256 ? 256 : 512)));
     if (k.num_tiles <= 0) return cudaSuccess;
 
@@ -603,7 +606,7 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     const bool xu = p.lo == -128.f && p.hi == 127.f && env_xug != 0;
     if (xu && packed_epilogue)   // pre-biased accumulators: the table entry is added, not subtracted (conv_tc_kernel, PACKED)
         for (int k = 0; k < p.ncls * p.N; ++k) tab.corr[k] = kAccBias - tab.corr[k];
-    const bool linear = p.KH == 1 && p.KW == 1 && p.TW == 128 && p.TH == 1 && l.H == 1 && l.B == 1 && l.OH == 1 && p.ncls == 1;
+    const bool linear = p.KH == 1 && p.KW == 1 && p.TW == 128 && p.TH == 1 && l.H == 1 && l.B == 1 && l.OH == 1 && p.ncls == 1 && l.OW < (1ll << 31) - 128;
     const int shape = (p.KH == 3 && p.KW == 3 && p.CB == 1) ? 1 : ((linear && p.CB == 1) ? 2 : ((linear && p.CB == 2) ? 3 : 0));
     using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const ConvTcTables, const ConvTcParams);
     KernelFn fn = nullptr;
