@@ -53,16 +53,14 @@ constexpr uint32_t kSmemLimit = 232448;  // 227 KB usable per CTA on sm_100
 //               operands of the FMUL / FADD / IADD that use them -- no LDS at all
 //   kTabGroup   N <= 128: one code copy per column group (4 x 32 columns), same idea; with N = 256 the four copies (two
 //               chunks each) no longer fit the instruction cache of a sub-partition and this is slower than kTabSmem
-//   kTabBorder  kTabGroup for the 3x3 kernel: c0z / c1 and the INTERIOR border class of the correction table are constant
-//               operands; the other eight classes live in shared memory as deltas against the interior one and are read only
-//               by warps that own a pixel on the image border (a warp-uniform branch).  It takes the epilogue's LDS traffic
-//               (32 % of the L1/shared data pipe in profiles/r01i_conv3x3.txt, next to the tensor core's 54 %) off the pipe
-//               the MMA operands come through -- and was still measured SLOWER than kTabSmem, so it is opt-in (MF_TC_TAB=3).
-enum { kTabSmem = 0, kTabGroup = 1, kTabPeriod = 2, kTabBorder = 3 };
+// (A fourth mode -- kTabGroup for the 3x3 kernel with the eight non-interior border classes kept in shared memory as deltas -- removed
+// the epilogue's 32 % share of the L1/shared data pipe and was still slower, 0.138 vs 0.103 ms on BASELINE config 5; it is not kept:
+// profiles/r01j_conv3x3_experiments.txt.)
+enum { kTabSmem = 0, kTabGroup = 1, kTabPeriod = 2 };
 struct ConvTcTables {
     float c0z[256];
     float c1[256];
-    int32_t corr[9 * 256];   // [ncls][N] with row pitch N;  kTabBorder (N <= 128): [interior class][N], then 9 x [N] deltas against it
+    int32_t corr[9 * 256];   // [ncls][N] with row pitch N
 };
 
 struct ConvTcParams {
@@ -207,8 +205,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int k = threadIdx.x; k < p.N; k += 32 * kEpiWarps) { s_c0z[k] = tab.c0z[k]; s_c1[k] = tab.c1[k]; }
         for (int k = threadIdx.x; k < p.ncls * p.N; k += 32 * kEpiWarps) s_corr[k] = tab.corr[k];
     }
-    if (TAB == kTabBorder && warp < kEpiWarps)
-        for (int k = threadIdx.x; k < 9 * p.N; k += 32 * kEpiWarps) s_corr[k] = tab.corr[p.N + k];   // the per-class deltas
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -322,7 +318,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const uint32_t acc = it & 1, aph = (it >> 1) & 1;
                 bool valid;
-                bool on_border = false;                             // kTabBorder: does this warp own a pixel of a non-interior class in this tile?
                 const int32_t *corr = s_corr;
                 uint8_t *orow;
                 if (LINEAR) {                                       // one row of 128-byte (packed) pixels: tile t covers rows [128 t, 128 t + 128)
@@ -337,16 +332,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const long long oy = (long long)ty * p.TH + rr, ox = (long long)tx * p.TW + rc;
                     valid = oy < p.OH && ox < p.OW;
                     int cls = 0;
-                    if ((TAB == kTabSmem && p.ncls == 9) || TAB == kTabBorder) cls = 3 * (oy == 0 ? 0 : (oy == p.OH - 1 ? 2 : 1)) + (ox == 0 ? 0 : (ox == p.OW - 1 ? 2 : 1));
+                    if (TAB == kTabSmem && p.ncls == 9) cls = 3 * (oy == 0 ? 0 : (oy == p.OH - 1 ? 2 : 1)) + (ox == 0 ? 0 : (ox == p.OW - 1 ? 2 : 1));
                     corr = s_corr + cls * p.N;
-                    if (TAB == kTabBorder) on_border = __any_sync(0xffffffffu, cls != 4);
                     orow = p.out + (((long long)b * p.OH + oy) * p.OW + ox) * p.N;
                 }
 
                 mbar_wait(tfull_bar(acc), aph);
                 tc_fence_after();
                 const uint32_t t_base = tmem_base + acc * (uint32_t)p.N + ((q * 32u) << 16);
-                constexpr bool ONE_CHUNK = TAB == kTabGroup || TAB == kTabBorder;      // N <= 128: a warp's only chunk
+                constexpr bool ONE_CHUNK = TAB == kTabGroup;      // N <= 128: a warp's only chunk
                 for (int c0 = 32 * cg; c0 < p.N; c0 += (ONE_CHUNK ? 1 << 20 : 128)) {
                     uint32_t r[32];
                     tmem_ld32(t_base + (uint32_t)c0, r);
@@ -368,13 +362,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         } else {
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                // kTabPeriod: the tables repeat every 32 columns; kTabGroup / kTabBorder: N <= 128, this warp's only chunk is 32 * CG
+                                // kTabPeriod: the tables repeat every 32 columns; kTabGroup: N <= 128, this warp's only chunk is 32 * CG
                                 const int n = (TAB == kTabPeriod ? 0 : 32 * CG) + 4 * g + u;
                                 zz[u] = tab.c0z[n]; ss[u] = tab.c1[n]; kk[u] = tab.corr[n];
-                            }
-                            if (TAB == kTabBorder && on_border) {   // rare: add this pixel's class delta (zero for interior lanes)
-                                const int4 d = *reinterpret_cast<const int4 *>(corr + c0 + 4 * g);
-                                kk[0] += d.x; kk[1] += d.y; kk[2] += d.z; kk[3] += d.w;
                             }
                         }
                         if (PACKED) {
@@ -401,7 +391,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
             }
         };
-        if (TAB == kTabGroup || TAB == kTabBorder) {
+        if (TAB == kTabGroup) {
             switch (warp >> 2) {
                 case 0: epilogue(std::integral_constant<int, 0>{}); break;
                 case 1: epilogue(std::integral_constant<int, 1>{}); break;
@@ -629,17 +619,6 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
         const bool periodic = p.Cout > 0 && 32 % p.Cout == 0 && p.N % p.Cout == 0 && p.P * p.Cout == p.N;
         if (periodic && env_tab != kTabGroup) fn = conv_tc_kernel<false, true, 1, 1, 1, kTabPeriod>;
         else if (p.N <= 128) fn = conv_tc_kernel<false, true, 1, 1, 1, kTabGroup>;
-    }
-    // measured slower than kTabSmem on BASELINE config 5 (0.138 vs 0.103 ms per launch, profiles/r01j_conv3x3_experiments.txt): the
-    // four code copies per sub-partition cost more than the LDS traffic they remove, so the mode stays opt-in (MF_TC_TAB=3)
-    if (shape == 1 && xu && p.big_acc && p.ncls == 9 && p.N <= 128 && env_tab == kTabBorder) {
-        fn = conv_tc_kernel<true, true, 3, 3, 1, kTabBorder>;
-        std::vector<int32_t> t((size_t)10 * p.N);
-        for (int n = 0; n < p.N; ++n) {
-            t[(size_t)n] = p.h_corr[(size_t)4 * p.N + n];                                                     // interior class
-            for (int c = 0; c < 9; ++c) t[(size_t)(1 + c) * p.N + n] = p.h_corr[(size_t)c * p.N + n] - p.h_corr[(size_t)4 * p.N + n];
-        }
-        std::memcpy(tab.corr, t.data(), t.size() * 4);
     }
     static std::mutex attr_mu;
     static std::vector<KernelFn> attr_done;
