@@ -157,6 +157,8 @@ int run_chunk(mf_model *m, Slot &s, const uint8_t *d_in, size_t n, float *d_out_
               cudaEvent_t *prof, void *const *layer_outs_host, size_t sample_offset) {
     const uint8_t *cur = d_in;
     int flip = 0;
+    bool f32_done = false;   // a fused classifier tail also wrote the dequantized output
+    const bool i8_out = !m->spec.is_u8_out;
     // Programmatic dependent launch between consecutive layers (mf_kernels.h): off while per-layer events or trace copies sit
     // between the kernels, and for the first kernel of a chunk (its predecessor in the stream is a copy or another call).
     static const bool env_pdl = [] { const char *e = std::getenv("MF_PDL"); return !e || std::atoi(e) != 0; }();
@@ -168,6 +170,7 @@ int run_chunk(mf_model *m, Slot &s, const uint8_t *d_in, size_t n, float *d_out_
         if ((int)i == m->tail_first && !layer_outs_host) {      // pool + conv + softmax in one launch
             TailArgs t = m->tail;
             t.in = cur; t.out = s.act[flip]; t.logits = d_logits; t.batch = (long long)n; t.pdl = pdl;
+            if (d_out_f32 && i8_out) { t.out_f32 = d_out_f32; t.dq_scale = m->spec.out_scale; t.dq_zp = (float)m->spec.out_zp; f32_done = true; }
             cudaError_t e = launch_tail_fused(t, st);
             if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("tail_fused_kernel launch failed: ") + cudaGetErrorString(e));
             m->launches += 1;
@@ -186,6 +189,7 @@ int run_chunk(mf_model *m, Slot &s, const uint8_t *d_in, size_t n, float *d_out_
             a.sm_out = s.act[flip];
             a.exp_lut = sa.exp_lut; a.sm_rows = sa.rows; a.sm_cols = sa.cols;
             a.sm_out_scale = sa.out_scale; a.sm_out_zp = sa.out_zp; a.sm_lo = sa.lo; a.sm_hi = sa.hi;
+            if (d_out_f32 && i8_out) { a.out_f32 = d_out_f32; a.dq_scale = m->spec.out_scale; a.dq_zp = (float)m->spec.out_zp; f32_done = true; }
             cudaError_t e = launch_fc_warp(a, st);
             if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("fc_warp_kernel(+softmax) launch failed: ") + cudaGetErrorString(e));
             m->launches += 1;
@@ -216,7 +220,7 @@ int run_chunk(mf_model *m, Slot &s, const uint8_t *d_in, size_t n, float *d_out_
         if (prof) MF_CUDA(cudaEventRecord(prof[i + 1], st));
     }
     const size_t total = n * m->spec.out_elems;
-    if (d_out_f32) {
+    if (d_out_f32 && !f32_done) {
         cudaError_t e = launch_dequantize(cur, d_out_f32, total, m->spec.out_scale, (float)m->spec.out_zp, m->spec.is_u8_out, st, pdl);   // src/tensor.rs:89-92
         if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("dequantize launch failed: ") + cudaGetErrorString(e));
         m->launches += 1;

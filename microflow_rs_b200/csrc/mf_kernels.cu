@@ -1404,7 +1404,9 @@ __global__ void __launch_bounds__(256) fc_warp_kernel(FcArgs a) {
         for (int i = 0; i < a.sm_rows; ++i) sumexp = __fadd_rn(sumexp, __ldg(a.exp_lut + q[i * a.sm_cols + j]));
     for (int k = 0; k < a.N; ++k) {
         const float t = __fadd_rn(__fdiv_rn(__fdiv_rn(__ldg(a.exp_lut + q[k]), sumexp), a.sm_out_scale), a.sm_out_zp);
-        a.sm_out[(size_t)warp * a.N + k] = (uint8_t)round_clamp(t, a.sm_lo, a.sm_hi);
+        const int y = round_clamp(t, a.sm_lo, a.sm_hi);
+        a.sm_out[(size_t)warp * a.N + k] = (uint8_t)y;
+        if (a.out_f32) a.out_f32[(size_t)warp * a.N + k] = __fmul_rn(a.dq_scale, __fsub_rn(__int2float_rn(y), a.dq_zp));   // dequantize_kernel's arithmetic
     }
 }
 
@@ -1465,7 +1467,9 @@ __global__ void __launch_bounds__(256) tail_fused_kernel(TailArgs a) {
         for (int i = 0; i < a.sm_rows; ++i) sumexp = __fadd_rn(sumexp, __ldg(a.exp_lut + q[i * a.sm_cols + j]));
     for (int k = 0; k < a.N; ++k) {
         const float t = __fadd_rn(__fdiv_rn(__fdiv_rn(__ldg(a.exp_lut + q[k]), sumexp), a.out_scale), a.out_zp);
-        a.out[(size_t)b * a.N + k] = (uint8_t)round_clamp(t, a.sm_lo, a.sm_hi);
+        const int y = round_clamp(t, a.sm_lo, a.sm_hi);
+        a.out[(size_t)b * a.N + k] = (uint8_t)y;
+        if (a.out_f32) a.out_f32[(size_t)b * a.N + k] = __fmul_rn(a.dq_scale, __fsub_rn(__int2float_rn(y), a.dq_zp));     // dequantize_kernel's arithmetic
     }
 }
 

@@ -82,6 +82,8 @@ struct FcArgs {
     int sm_rows = 1, sm_cols = 1;
     float sm_out_scale = 1.f, sm_out_zp = 0.f, sm_lo = -128.f, sm_hi = 127.f;
     int pdl = 0;
+    float *out_f32 = nullptr;      // with sm_out: also the model's final dequantize of the softmax output
+    float dq_scale = 1.f, dq_zp = 0.f;
 };
 
 struct PoolArgs {
@@ -118,6 +120,9 @@ struct TailArgs {
     float out_scale = 1.f, out_zp = 0.f, sm_lo = -128.f, sm_hi = 127.f;
     long long batch = 0;
     int pdl = 0;
+    // optional: the model's final dequantize (src/tensor.rs:89-92) of the softmax output in the same launch
+    float *out_f32 = nullptr;
+    float dq_scale = 1.f, dq_zp = 0.f;
 };
 cudaError_t launch_tail_fused(const TailArgs &a, cudaStream_t s);
 
