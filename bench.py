@@ -217,7 +217,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    # NCCL prints its version banner on stdout when the communicator is created (NCCL_DEBUG=VERSION on these boxes); stdout must
+    # carry exactly one JSON line, so file descriptor 1 points at stderr until the first collectives are through.
+    saved_stdout = None
     if world > 1:
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     wl = args.workload
@@ -232,6 +238,12 @@ def main():
         blob = torch.as_tensor(sharding.DeviceBytes(ptr, nbytes), device=f"cuda:{local_rank}")
         sharding.broadcast_weights(dist, blob, rank)
         torch.cuda.synchronize()
+    if saved_stdout is not None:
+        dist.barrier()                      # communicator exists on every rank now
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
 
     ie, oe = m.in_elems, m.out_elems
     # inputs: contiguous shard of the global sample range [rank*batch, (rank+1)*batch), R rotating batches so that
