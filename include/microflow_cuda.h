@@ -142,13 +142,17 @@ int mf_predict_quantized(mf_model *m, const void *in_q, float *out_f32);
 int mf_predict_many(mf_model *m, const float *in_f32, size_t n, float *out_f32);
 int mf_predict_many_quantized(mf_model *m, const void *in_q, size_t n, float *out_f32);
 /* same, but returns as soon as the copies and kernels are enqueued; the host buffers must be PINNED (mf_host_alloc) and stay
- * valid until mf_model_synchronize().  Back-to-back calls pipeline: the H2D of call k+1 overlaps the kernels of call k. */
+ * valid until mf_model_synchronize().  Back-to-back calls pipeline: the H2D of call k+1 overlaps the kernels of call k.
+ * (The blocking calls above serve requests of <= 64 samples by replaying a captured CUDA graph) */
 int mf_predict_many_quantized_async(mf_model *m, const void *in_q, size_t n, float *out_f32);
 /* strict-parity variant: final quantized output (out_q, out_elems bytes/sample) and, optionally, the input of
  * the trailing softmax ("logits", may be NULL) */
 int mf_predict_many_logits(mf_model *m, const void *in_q, size_t n, void *out_q, void *logits_q);
-/* device-resident buffers; asynchronous on `stream` (cudaStream_t, NULL = the model's own stream).
- * d_out_f32 and d_out_q may each be NULL. */
+/* device-resident buffers (NHWC); asynchronous on `stream` (cudaStream_t, NULL = the model's own stream): everything the call
+ * enqueues is ordered after the work already on `stream` and before work enqueued on it afterwards (large chunks run on two
+ * internal streams that are forked from / joined to `stream` by events).  d_out_f32 and d_out_q may each be NULL.  The model's
+ * workspaces are shared with the host-path entry points: synchronize (mf_model_synchronize) between un-waited
+ * mf_predict_many_quantized_async calls and a device-path call on a different stream. */
 int mf_predict_many_device(mf_model *m, const void *d_in_q, size_t n, float *d_out_f32, void *d_out_q, void *stream);
 /* every layer's quantized output for n samples, into host buffers layer_outs[i] (n * out_elems(i) bytes; NULL = skip) */
 int mf_predict_trace(mf_model *m, const void *in_q, size_t n, void *const *layer_outs);
