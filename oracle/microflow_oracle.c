@@ -44,7 +44,9 @@ static inline int32_t ld_elem(const uint8_t *p, int is_u8) {
 static inline int32_t sat_cast(float x, int is_u8) {
     if (x != x) return 0;
     if (is_u8) { if (x <= 0.0f) return 0; if (x >= 255.0f) return 255; return (int32_t)x; }
-    if (x <= -128.0f) return -128; if (x >= 127.0f) return 127; return (int32_t)x;
+    if (x <= -128.0f) return -128;
+    if (x >= 127.0f) return 127;
+    return (int32_t)x;
 }
 
 /* ---- src/quantize.rs:16-18 / :27-29 -------------------------------------------------------- */
