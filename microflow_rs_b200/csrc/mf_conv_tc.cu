@@ -380,11 +380,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             w[g] = pack4(y[0], y[1], y[2], y[3]);
                         }
                     }
-                    if (valid) {
-                        uint4 *dst = reinterpret_cast<uint4 *>(orow + c0);
-                        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                    }
+                    if (valid)     // the thread's 32 output bytes = one aligned 32-byte sector: a single 256-bit store (STG.256), so L2 sees
+                                   // full-sector writes (two 16-byte halves per sector kept L2 at 68 % of its request rate, profiles/r01l_tc_pw.txt)
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + c0), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                                     "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                                     : "memory");
                 }
                 tc_fence_before();
                 __syncwarp();
