@@ -193,7 +193,7 @@ typedef struct mf_conv_desc {          /* microflow::ops::conv_2d / depthwise_co
 int mf_op_conv_2d(const mf_conv_desc *d, const void *in, void *out, size_t batch);
 
 /* persistent form of the same operator: plan once (weights/constants uploaded, kernel selected), then run on
- * DEVICE-resident NHWC buffers, asynchronously on `stream` (cudaStream_t).  Used by pipelines and by bench.py's
+ * DEVICE-resident NHWC buffers (32-byte aligned, as cudaMalloc returns them), asynchronously on `stream` (cudaStream_t).  Used by pipelines and by bench.py's
  * BASELINE config 5 (synthetic 224x224x128->128 Conv2D roofline). */
 typedef struct mf_op mf_op;
 int mf_op_conv_2d_create(const mf_conv_desc *d, mf_op **out);

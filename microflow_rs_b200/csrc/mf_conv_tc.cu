@@ -537,6 +537,10 @@ MapCache g_maps;
 }  // namespace
 
 cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_sms, cudaStream_t s, std::string *why) {
+    if ((reinterpret_cast<uintptr_t>(l.out) & 31u) != 0 || (reinterpret_cast<uintptr_t>(l.in) & 15u) != 0) {   // STG.256 rows / TMA base
+        if (why) *why = "tcgen05 conv: the input must be 16-byte and the output 32-byte aligned";
+        return cudaErrorMisalignedAddress;
+    }
     CUtensorMap ta, tb;
     std::memcpy(&tb, p.tmap_b, sizeof tb);
     const int box_w = p.patch ? p.TW + p.KW - 1 : p.TW;
