@@ -376,7 +376,11 @@ int predict_many_host(mf_model *m, const void *in_q, const float *in_f32, size_t
     // host path: pieces small enough that the H2D of piece c+1 overlaps the compute of piece c (two streams), large enough
     // to keep the per-launch fixed costs amortised
     size_t piece = std::min(m->chunk, std::max<size_t>(1024, (n + 1) / 2));
-    if (piece > 4096) piece = 4096;
+    // a blocking call cannot hide the compute of its last piece behind a later copy, so it uses smaller pieces than the
+    // asynchronous form (whose calls pipeline into each other); MF_HOST_PIECE overrides both for experiments
+    static const int env_piece = [] { const char *e = std::getenv("MF_HOST_PIECE"); return e ? std::atoi(e) : 0; }();
+    const size_t cap = env_piece > 0 ? (size_t)env_piece : (wait ? 2048 : 4096);
+    if (piece > cap) piece = cap;
     size_t ci = m->slot_rr;
     for (size_t off = 0; off < n; off += piece, ++ci) {
         Slot &s = m->slot[ci & 1];
