@@ -3,6 +3,7 @@ fails loudly without a GPU (no CPU fallback), and its run-time loader (the proc-
 i.e. the reference's -- pre-processing constants bit for bit.  No compute calls here."""
 import ctypes as C
 import re
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -117,3 +118,45 @@ def test_options_struct_is_versioned_by_struct_size():
         mf.Model(MODELS / "sine.tflite", flags=mf.FLAG_HOST_ONLY, layout=7)
     assert e.value.status == 9
     mf.Model(MODELS / "person_detect.tflite", flags=mf.FLAG_HOST_ONLY, layout=mf.LAYOUT_NALGEBRA).close()
+
+
+def _sass_by_function():
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(exe).exists():
+        pytest.skip("cuobjdump not available")
+    mf.lib()                                                           # builds the library if needed
+    out = subprocess.run([exe, "-sass", str(mf.LIB_PATH)], capture_output=True, text=True, timeout=600).stdout
+    funcs, cur = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = funcs.setdefault(m.group(1), [])
+        elif cur is not None and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+            cur.append(line)
+    return funcs
+
+
+def test_sass_epilogues_are_never_contracted_into_fma():
+    """Bit-exactness rests on separate f32 multiply and add (src/ops/conv_2d.rs:93-98).  ptxas contracts mul.rn.f32x2 + add.rn.f32x2
+    into FFMA2 even under -fmad=false, so the machine code of every conv / depthwise / fully-connected kernel is
+    checked: no FFMA, no FFMA2.  (The pool, softmax, quantize and classifier-tail kernels contain FFMAs inside __fdiv_rn.)"""
+    funcs = _sass_by_function()
+    hot = {n: body for n, body in funcs.items() if re.search(r"conv_tc_kernel|dwconv|pwconv|conv_generic|fc_generic|layout_transpose", n)}
+    assert len(hot) >= 20, sorted(funcs)
+    for name, body in hot.items():
+        bad = [ln for ln in body if re.search(r"\bFFMA2?\b", ln)]
+        assert not bad, f"{name}: {bad[:3]}"
+
+
+def test_sass_shows_the_blackwell_paths():
+    """The tcgen05 kernel issues UTCIMMA (tcgen05.mma kind::i8) fed by UTMALDG (TMA tensor loads), reads TMEM with LDTM and stores
+    256-bit sectors; the sample-resident depthwise kernels use bulk TMA copies (UBLKCP), IDP.4A and packed FADD2."""
+    funcs = _sass_by_function()
+    text = {n: "\n".join(b) for n, b in funcs.items()}
+    tc = [t for n, t in text.items() if "conv_tc_kernel" in n]
+    assert tc and all("UTCIMMA" in t and "UTMALDG" in t and "LDTM" in t for t in tc)
+    assert any("STG.E.ENL2.256" in t for t in tc)
+    dw = [t for n, t in text.items() if re.search(r"dwconv3x3_(smem|pair)_kernel|dwconv_cin1_smem_kernel", n)]
+    assert dw and all("UBLKCP" in t and "IDP.4A" in t and "FADD2" in t for t in dw)
