@@ -23,10 +23,15 @@ fi
 if has prof; then
   timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-conv2d > gpurun_out/ncu_bench.log 2>&1
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:dwconv3x3 -s 26 -c 2 -f -o gpurun_out/prof_dw \
-      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-conv2d > gpurun_out/ncu_dw.log 2>&1
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 28 -c 3 -f -o gpurun_out/prof_tc_pw \
-      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-conv2d > gpurun_out/ncu_tc.log 2>&1
+  # full captures of single layers at batch 8192 (tools/layer_bench.py launches one kernel type per process: deterministic)
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:dwconv3x3 -s 10 -c 1 -f -o gpurun_out/prof_dw \
+      python tools/layer_bench.py 8192 L1_dw8 > gpurun_out/ncu_dw.log 2>&1
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:dwconv3x3 -s 10 -c 1 -f -o gpurun_out/prof_dw_s2 \
+      python tools/layer_bench.py 8192 L3_dw16_s2 > gpurun_out/ncu_dw_s2.log 2>&1
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 10 -c 1 -f -o gpurun_out/prof_tc_pw \
+      python tools/layer_bench.py 8192 L6_pw32_32 > gpurun_out/ncu_tc.log 2>&1
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 10 -c 1 -f -o gpurun_out/prof_tc_pw128 \
+      python tools/layer_bench.py 8192 L14_pw128 > gpurun_out/ncu_tc128.log 2>&1
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 5 -c 1 -f -o gpurun_out/prof_conv3x3 \
       python -m microflow_rs_b200._convbench 16 4 > gpurun_out/ncu_conv3x3.log 2>&1
 fi
