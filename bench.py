@@ -148,14 +148,30 @@ def cpu_baseline(workload, seconds=12.0, threads=1, max_samples=4096):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own algorithm on the box's host cores (oracle port; Rust cannot be built here)."""
+    """--impl reference: the reference's own algorithm on the box's host cores (oracle port; Rust cannot be built here).
+    Every step processes the SAME batch as the CUDA arm (8192 person_detect samples) when the whole run then stays under
+    ~6 minutes on this box; otherwise a bounded sample, and `config.same_config` says so.  MF_REF_THREADS fixes the thread count
+    (default: every hardware thread), so that numbers from boxes with different core counts can be compared."""
     if rank != 0:
         return
     import oracle
     wl = args.workload
     threads = oracle.max_threads()
+    if os.environ.get("MF_REF_THREADS"):
+        threads = max(1, min(threads, int(os.environ["MF_REF_THREADS"])))
     o = oracle.Model(MODELS / f"{wl}.tflite", fast=True)
-    per_step = {"person_detect": 48, "speech": 384, "sine": 16384}[wl] * threads   # bounded sample per step (~0.5-1 s)
+    batch = args.batch or DEFAULT_BATCH[wl]
+    probe_n = {"person_detect": 16, "speech": 128, "sine": 4096}[wl] * threads
+    xs = splitmix_bytes(SEEDS[wl], probe_n * o.in_elems).reshape(probe_n, -1)
+    o.predict_many_quantized(xs, threads=threads)
+    t0 = time.perf_counter()
+    o.predict_many_quantized(xs, threads=threads)
+    rate = probe_n / (time.perf_counter() - t0)
+    budget_s = float(os.environ.get("MF_REF_BUDGET_S", "360"))
+    per_step = batch
+    if batch * (args.steps + args.warmup) / rate > budget_s:
+        per_step = max(threads, int(rate * budget_s / (args.steps + args.warmup)) // threads * threads)
+    same = per_step == batch
     xs = splitmix_bytes(SEEDS[wl], per_step * o.in_elems).reshape(per_step, -1)
     for _ in range(args.warmup):
         o.predict_many_quantized(xs, threads=threads)
@@ -165,9 +181,11 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     val = per_step * args.steps / dt
     sample = f"{per_step} synthetic {wl} samples per step on {threads} host threads (oracle port of the reference algorithm)"
+    cfg = {"workload": f"{wl}.tflite int8, batch {per_step} per step" + (" (BASELINE configs[2])" if same and wl == "person_detect" else " (bounded CPU sample)"),
+           "same_config": same, "threads": threads}
     line = {"impl": "reference", "metric": f"inferences/s {wl} int8", "value": val, "unit": "inferences/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int8", "data": "synthetic", "config": {"workload": f"{wl}.tflite int8, bounded CPU sample of {per_step} samples/step"},
+            "dtype": "int8", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": val, "unit": "inferences/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "inferences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -186,6 +204,127 @@ def conv2d_roofline(torch, mf, peaks, steps, warmup, batch=16):
     from microflow_rs_b200 import _convbench
     return _convbench.run(torch, w, c0, c1, in_zp=-128, out_zp=-128, out_scale=0.0235294, H=H, W=W, batch=batch, steps=steps, warmup=warmup,
                           peaks=peaks, seed=seed)
+
+
+def verify_ranks(dist, torch, m, wl, rank, world, batch):
+    """BASELINE configs[3]: "result must equal the 1-GPU result row-for-row".  Outside every timed region each rank runs the
+    first 256 samples of RANK 0's shard plus 32 samples of its own shard; the int8 outputs and pre-softmax logits are
+    all-gathered; rank 0 checks that every rank produced rank 0's bytes on the common rows (a broken weight broadcast or a
+    mis-addressed shard cannot pass) and checks its own 32 rows against the oracle."""
+    ie = m.in_elems
+    common_n, own_n = 256, 32
+    common = splitmix_bytes(SEEDS[wl], common_n * ie, offset=0).reshape(common_n, ie)
+    own = splitmix_bytes(SEEDS[wl], own_n * ie, offset=rank * batch * ie).reshape(own_n, ie)
+    xs = np.concatenate([common, own])
+    out_q, logits = m.predict_many_logits(xs)
+    mine = np.concatenate([out_q.reshape(len(xs), -1).view(np.uint8), logits.reshape(len(xs), -1).view(np.uint8)], axis=1) if logits is not None else \
+        out_q.reshape(len(xs), -1).view(np.uint8)
+    t = torch.from_numpy(np.ascontiguousarray(mine)).cuda()
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    res = None
+    if rank == 0:
+        import oracle
+        ok_common = all(bool(torch.equal(parts[r][:common_n], parts[0][:common_n])) for r in range(world))
+        o = oracle.Model(MODELS / f"{wl}.tflite", fast=True)
+        _, want_q = o.predict_many_quantized(own)
+        ok_oracle = bool(np.array_equal(out_q[common_n:].reshape(own_n, -1).view(np.uint8), np.asarray(want_q).reshape(own_n, -1).view(np.uint8)))
+        res = {"ranks": world, "rows": common_n * world + own_n, "common_rows_equal_on_all_ranks": ok_common, "own_rows_equal_oracle": ok_oracle,
+               "ok": ok_common and ok_oracle, "what": "first 256 samples of rank 0's shard on every rank (all_gather, byte-equal) + 32 own rows vs the oracle"}
+    return res
+
+
+def main_single_process(args):
+    """`python bench.py --gpus N` WITHOUT torchrun: the N GPUs are driven by ONE process through the library's own multi-device
+    model (mf_options.devices): weights broadcast once at create, predict_many shards the samples inside the C-ABI call."""
+    import torch
+    import microflow_rs_b200 as mf
+    wl = args.workload
+    G = args.gpus
+    batch = args.batch or DEFAULT_BATCH[wl]
+    m = mf.Model(MODELS / f"{wl}.tflite", devices=list(range(G)), chunk=args.chunk, flags=args.flags)
+    ie, oe = m.in_elems, m.out_elems
+    host_in = [mf.PinnedBuffer((G * batch, ie), np.int8) for _ in range(2)]
+    for r_i, hb in enumerate(host_in):
+        hb.array[:] = splitmix_bytes(SEEDS[wl] + r_i, G * batch * ie).reshape(G * batch, ie)
+    host_out = [mf.PinnedBuffer((G * batch, oe), np.float32) for _ in range(2)]
+    # device-resident leg: per device its contiguous shard, enqueued by one Python thread per device (ctypes drops the GIL)
+    R = max(2, int(np.ceil(160e6 / (batch * ie))) + 1)
+    d_in, d_out, streams, evs = [], [], [], []
+    for g in range(G):
+        with torch.cuda.device(g):
+            d_in.append([torch.from_numpy(host_in[i % 2].array[g * batch:(g + 1) * batch]).cuda() for i in range(R)])
+            d_out.append(torch.empty((batch, oe), dtype=torch.float32, device=f"cuda:{g}"))
+            streams.append(torch.cuda.Stream(device=g))
+            evs.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+
+    def run_dev(g, first, count, timed):
+        with torch.cuda.device(g):
+            if timed:
+                evs[g][0].record(streams[g])
+            for i in range(first, first + count):
+                m.predict_many_device_on(g, d_in[g][i % R].data_ptr(), batch, d_out[g].data_ptr(), None, streams[g].cuda_stream)
+            if timed:
+                evs[g][1].record(streams[g])
+
+    def all_devs(first, count, timed):
+        ths = [threading.Thread(target=run_dev, args=(g, first, count, timed)) for g in range(G)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        for g in range(G):
+            torch.cuda.synchronize(g)
+
+    all_devs(0, args.warmup, False)
+    launches0 = m.launch_count()
+    sampler = ClockSampler(0)
+    sampler.start()
+    sampler.window(True)
+    all_devs(args.warmup, args.steps, True)
+    sampler.window(False)
+    ms = max(evs[g][0].elapsed_time(evs[g][1]) for g in range(G))
+    launches = m.launch_count() - launches0
+    value = G * batch * args.steps / (ms * 1e-3)
+    # e2e: ONE C-ABI call per step shards G * batch host samples over the devices (H2D + D2H inside)
+    for i in range(3):
+        m.predict_many_quantized(host_in[i & 1].array, out=host_out[i & 1].array)
+    sampler.window(True)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        m.predict_many_quantized(host_in[i & 1].array, out=host_out[i & 1].array)
+    e2e_block_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        m.predict_many_quantized_async(host_in[i & 1].array, host_out[i & 1].array)
+    m.synchronize()
+    e2e_s = time.perf_counter() - t0
+    sampler.window(False)
+    clocks = sampler.stop()
+    # row-for-row equality with the 1-GPU result (BASELINE configs[3]): the same rows through a one-device model
+    m1 = mf.Model(MODELS / f"{wl}.tflite", device=0)
+    nchk = min(G * batch, 4096)
+    sel = np.linspace(0, G * batch - 1, nchk).astype(np.int64)       # rows from every shard
+    xs = np.ascontiguousarray(host_in[0].array[sel])
+    q1, l1 = m1.predict_many_logits(xs)
+    qG, lG = m.predict_many_logits(host_in[0].array)
+    ok = bool(np.array_equal(qG[sel], q1)) and (l1 is None or bool(np.array_equal(lG[sel], l1)))
+    m1.close()
+    line = {"metric": f"inferences/s {wl} int8", "value": value, "unit": "inferences/s", "n_gpus": G, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": {"workload": f"{wl}.tflite int8, batch {batch} per GPU" + (" (BASELINE configs[3] shape)" if wl == "person_detect" else ""),
+                       "global_batch": batch * G, "parallelism": f"dp{G} in ONE process: mf_options.devices = {m.devices}, weights by one '{m.weight_broadcast}' "
+                                                                 "broadcast at create, contiguous shards inside mf_predict_many*",
+                       "l2": f"inputs rotate over {R} device batches per GPU"},
+            "e2e": {"value": G * batch * args.steps / e2e_s, "unit": "inferences/s", "h2d_bytes_per_step": G * batch * ie, "d2h_bytes_per_step": G * batch * oe * 4,
+                    "api": "mf_predict_many_quantized_async (one call shards over all devices) x K + mf_model_synchronize", "blocking": G * batch * args.steps / e2e_block_s},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "verified": {"devices": G, "rows": int(nchk), "ok": ok, "what": "multi-device predict_many rows == the same rows through a one-device model (int8 outputs and logits)"},
+            "roofline": None, "cpu_baseline": None}
+    print(json.dumps(line), flush=True)
+    m.close()
+    if not ok:
+        raise SystemExit("bench.py: multi-device result differs from the 1-GPU result")
 
 
 def main():
@@ -208,6 +347,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        main_single_process(args)
         return
 
     import torch
@@ -270,6 +412,8 @@ def main():
 
     for i in range(args.warmup):
         step(i)
+    barrier()
+    verified = verify_ranks(dist, torch, m, wl, rank, world, batch) if world > 1 else None
     barrier()
     # ---- timed region: exactly K steps, CUDA events on the launching stream (consecutive layers overlap their launch
     # ramps through programmatic dependent launch, so no per-layer events here)
@@ -426,7 +570,7 @@ def main():
                             "link_bound_per_gpu = that bandwidth / input bytes per sample: the ceiling of e2e per GPU on this host"},
             "single_sample_latency_us": {"value": lat_us, "api": "mf_predict_quantized (one sample, host buffers, blocking; CUDA-graph replay)",
                                          "note": "median of 200 calls incl. the Python/ctypes call overhead"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "gpu_launches": int(launches), "clocks": clocks, "verified": verified, "roofline": roofline, "kernels": kernels,
             "layers": [{"i": i, "op": L["op"], "kernel": L["kernel"], "us_per_step": round(1e3 * float(t) / args.steps, 2),
                         "GBps": round((L["bytes"] - L["weight_bytes"]) * batch * args.steps / (float(t) * 1e-3) / 1e9, 1) if t > 0 else None}
                        for i, (L, t) in enumerate(zip(m.layers, layer_ms)) if not L["kernel"].startswith("none")],
@@ -448,6 +592,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and verified is not None and not verified["ok"]:
+        raise SystemExit("bench.py: ranks disagree on the common rows or rank 0 differs from the oracle")
 
 
 if __name__ == "__main__":

@@ -33,7 +33,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
 #endif
 
-#define MF_ABI_VERSION 2
+#define MF_ABI_VERSION 3
 
 typedef enum mf_status {
     MF_OK = 0,
@@ -80,12 +80,22 @@ typedef enum mf_status {
 #define MF_LAYOUT_NALGEBRA 1u /* the reference's own buffers: Buffer4D = [SMatrix<[T; CH], R, C>; B] and Buffer2D = SMatrix<T, R, C>,
                                  both column-major (src/buffer.rs:5-16): [sample][col][row][chan] */
 
+#define MF_MAX_DEVICES 16
+
 typedef struct mf_options {
     uint32_t struct_size; /* = sizeof(mf_options) of the caller; a shorter (older) struct leaves the missing fields at 0 */
-    int32_t device;       /* CUDA device ordinal; -1 = current device */
+    int32_t device;       /* CUDA device ordinal; -1 = current device (ignored when n_devices > 0) */
     uint32_t chunk;       /* samples per internal chunk of predict_many (0 = default) */
     uint32_t flags;       /* MF_FLAG_* */
     uint32_t layout;      /* MF_LAYOUT_* (ABI version 2) */
+    /* ABI version 3: the GPUs of the box this model runs on.  n_devices == 0: the single `device` above.  n_devices == -1: every
+     * visible device.  n_devices >= 1: devices[0 .. n_devices).  With more than one device the model is replicated: the static
+     * weight blob is uploaded to devices[0] and copied to the others by ONE broadcast at create (NCCL when libnccl.so.2 can be
+     * loaded, else cudaMemcpyPeer), and mf_predict_many* shard the n independent samples into contiguous ranges
+     * [r*ceil(n/G), min(n, (r+1)*ceil(n/G))), one per device, each driven by its own host thread -- no collective and no
+     * exchange of any kind on the inference path (the reference handles one sample per call, src/ops/conv_2d.rs:40). */
+    int32_t n_devices;
+    int32_t devices[MF_MAX_DEVICES];
 } mf_options;
 
 typedef struct mf_tensor_info {
@@ -154,6 +164,9 @@ int mf_predict_many_logits(mf_model *m, const void *in_q, size_t n, void *out_q,
  * workspaces are shared with the host-path entry points: synchronize (mf_model_synchronize) between un-waited
  * mf_predict_many_quantized_async calls and a device-path call on a different stream. */
 int mf_predict_many_device(mf_model *m, const void *d_in_q, size_t n, float *d_out_f32, void *d_out_q, void *stream);
+/* multi-device models: the same call on the replica of devices[index] (buffers and stream must belong to that device);
+ * mf_predict_many_device itself addresses devices[0] */
+int mf_predict_many_device_on(mf_model *m, int index, const void *d_in_q, size_t n, float *d_out_f32, void *d_out_q, void *stream);
 /* every layer's quantized output for n samples, into host buffers layer_outs[i] (n * out_elems(i) bytes; NULL = skip) */
 int mf_predict_trace(mf_model *m, const void *in_q, size_t n, void *const *layer_outs);
 int mf_model_synchronize(mf_model *m);
@@ -164,6 +177,13 @@ int mf_model_set_profiling(mf_model *m, int enabled);
 int mf_model_layer_times_ms(mf_model *m, float *ms, int cap);
 /* number of kernels launched by this model since creation (for bench.py's gpu_launches) */
 int mf_model_launch_count(const mf_model *m, uint64_t *count);
+/* name of the kernel the most recent predict* / trace call actually launched for `layer` ("" = none yet, or the layer ran inside
+ * the previous layer's fused launch); mf_layer_info.kernel is the engine's choice for large batches, this is what ran */
+const char *mf_model_layer_launched(const mf_model *m, int layer);
+/* devices this model runs on (ABI 3): returns the count, fills devices[0 .. min(count, cap)) */
+int mf_model_devices(const mf_model *m, int32_t *devices, int cap);
+/* how the weight blob reached devices[1..]: "none" (one device), "nccl" or "memcpy_peer" */
+const char *mf_model_weight_broadcast(const mf_model *m);
 
 /* ---- static weights blob (multi-GPU init: one broadcast of d_ptr[0..bytes) from rank 0) ------ */
 int mf_model_blob(const mf_model *m, void **d_ptr, size_t *bytes);

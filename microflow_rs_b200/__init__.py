@@ -45,8 +45,12 @@ class MicroflowError(RuntimeError):
 LAYOUT_NHWC, LAYOUT_NALGEBRA = 0, 1   # mf_options.layout: host buffers row-major NHWC, or the reference's column-major nalgebra buffers
 
 
+MAX_DEVICES = 16
+
+
 class _Options(C.Structure):
-    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("chunk", C.c_uint32), ("flags", C.c_uint32), ("layout", C.c_uint32)]
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("chunk", C.c_uint32), ("flags", C.c_uint32), ("layout", C.c_uint32),
+                ("n_devices", C.c_int32), ("devices", C.c_int32 * MAX_DEVICES)]
 
 
 class _TensorInfo(C.Structure):
@@ -91,7 +95,7 @@ ABI_SYMBOLS = [
     "mf_predict", "mf_predict_quantized", "mf_predict_many", "mf_predict_many_quantized", "mf_predict_many_quantized_async", "mf_predict_many_logits", "mf_predict_many_device",
     "mf_predict_trace", "mf_model_synchronize", "mf_model_set_profiling", "mf_model_layer_times_ms", "mf_model_launch_count", "mf_model_blob",
     "mf_host_alloc", "mf_host_free", "mf_op_conv_2d", "mf_op_conv_2d_create", "mf_op_run_device", "mf_op_kernel_name", "mf_op_destroy", "mf_op_fully_connected", "mf_op_average_pool_2d", "mf_op_softmax", "mf_op_quantize",
-    "mf_op_dequantize", "mf_op_layout_transpose",
+    "mf_op_dequantize", "mf_op_layout_transpose", "mf_model_layer_launched", "mf_model_devices", "mf_model_weight_broadcast", "mf_predict_many_device_on",
 ]
 
 _lib = None
@@ -137,6 +141,12 @@ def lib():
         L.mf_model_layer_times_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.mf_model_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.mf_model_blob.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.mf_model_layer_launched.argtypes = [C.c_void_p, C.c_int]
+        L.mf_model_layer_launched.restype = C.c_char_p
+        L.mf_model_devices.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int]
+        L.mf_model_weight_broadcast.argtypes = [C.c_void_p]
+        L.mf_model_weight_broadcast.restype = C.c_char_p
+        L.mf_predict_many_device_on.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mf_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
         L.mf_host_free.argtypes = [C.c_void_p]
         L.mf_device_count.argtypes = [C.POINTER(C.c_int)]
@@ -203,9 +213,20 @@ def _dtype_code(a):
 class Model:
     """What `#[model("path.tflite")]` generates in the reference: predict / predict_quantized (+ predict_many)."""
 
-    def __init__(self, path_or_bytes, device=-1, chunk=0, flags=0, layout=LAYOUT_NHWC):
+    def __init__(self, path_or_bytes, device=-1, chunk=0, flags=0, layout=LAYOUT_NHWC, devices=None):
+        """devices: None = the single `device`; "all" = every visible GPU; a list of ordinals = those GPUs.  With more than one
+        device predict_many* shard the samples into contiguous ranges, one per GPU, inside the library (mf_options.devices)."""
         self._h = C.c_void_p()
         opt = _Options(C.sizeof(_Options), device, chunk, flags, layout)
+        if isinstance(devices, str) and devices == "all":
+            opt.n_devices = -1
+        elif devices is not None:
+            devices = [int(d) for d in devices]
+            if len(devices) > MAX_DEVICES:
+                raise ValueError(f"at most {MAX_DEVICES} devices")
+            opt.n_devices = len(devices)
+            for i, d in enumerate(devices):
+                opt.devices[i] = d
         if isinstance(path_or_bytes, (str, os.PathLike)):
             _check(lib().mf_model_create_from_file(str(path_or_bytes).encode(), C.byref(opt), C.byref(self._h)))
         else:
@@ -281,21 +302,38 @@ class Model:
             raise ValueError(f"input size {xs.size} is not a multiple of {self.in_elems}")
         return xs, xs.size // self.in_elems
 
+    def _out(self, out, n):
+        """A caller-supplied result array is written by the library through its raw pointer: it must be exactly what the C side
+        expects (float32, C-contiguous, writable, n * out_elems elements)."""
+        if out is None:
+            return np.zeros((n, self.out_elems), np.float32)
+        if not isinstance(out, np.ndarray) or out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"] or \
+                out.size != n * self.out_elems:
+            raise ValueError(f"out must be a writable C-contiguous float32 array of {n} x {self.out_elems} elements")
+        return out
+
     def predict_many(self, xs, out=None):
         xs, n = self._n(xs, np.float32)
-        out = np.zeros((n, self.out_elems), np.float32) if out is None else out
+        out = self._out(out, n)
         _check(lib().mf_predict_many(self._h, xs.ctypes.data, n, out.ctypes.data))
         return out
 
     def predict_many_quantized(self, xs, out=None):
         xs, n = self._n(xs, self.dtype)
-        out = np.zeros((n, self.out_elems), np.float32) if out is None else out
+        out = self._out(out, n)
         _check(lib().mf_predict_many_quantized(self._h, xs.ctypes.data, n, out.ctypes.data))
         return out
 
     def predict_many_quantized_async(self, xs_pinned, out_pinned):
-        """Enqueue only (pinned numpy views from PinnedBuffer); call synchronize() before reading `out_pinned`."""
+        """Enqueue only (pinned numpy views from PinnedBuffer); call synchronize() before reading `out_pinned`.
+        The copies land after this call returns, so both arrays are used in place: no silent conversion copies."""
+        if not isinstance(xs_pinned, np.ndarray) or xs_pinned.dtype != self.dtype or not xs_pinned.flags["C_CONTIGUOUS"] or \
+                xs_pinned.size % self.in_elems:
+            raise ValueError(f"xs_pinned must be a C-contiguous {np.dtype(self.dtype)} array of n x {self.in_elems} elements")
         n = xs_pinned.size // self.in_elems
+        if out_pinned is None:
+            raise ValueError("out_pinned is required (the result arrives asynchronously)")
+        out_pinned = self._out(out_pinned, n)
         _check(lib().mf_predict_many_quantized_async(self._h, xs_pinned.ctypes.data, n, out_pinned.ctypes.data))
 
     def predict_many_logits(self, xs, want_logits=True):
@@ -337,6 +375,25 @@ class Model:
         ms = np.zeros(len(self.layers), np.float32)
         _check(lib().mf_model_layer_times_ms(self._h, ms.ctypes.data, len(ms)))
         return ms
+
+    def launched_kernels(self):
+        """Per layer: the kernel the most recent predict*/trace call actually launched ('' = none / inside the previous launch)."""
+        return [(lib().mf_model_layer_launched(self._h, i) or b"").decode() for i in range(len(self.layers))]
+
+    @property
+    def devices(self):
+        buf = (C.c_int32 * MAX_DEVICES)()
+        n = lib().mf_model_devices(self._h, buf, MAX_DEVICES)
+        return [int(buf[i]) for i in range(min(n, MAX_DEVICES))]
+
+    @property
+    def weight_broadcast(self):
+        return lib().mf_model_weight_broadcast(self._h).decode()
+
+    def predict_many_device_on(self, index, d_in_ptr, n, d_out_f32_ptr=None, d_out_q_ptr=None, stream=None):
+        """predict_many_device on the replica of devices[index] of a multi-device model."""
+        _check(lib().mf_predict_many_device_on(self._h, index, C.c_void_p(d_in_ptr), n, C.c_void_p(d_out_f32_ptr or 0), C.c_void_p(d_out_q_ptr or 0),
+                                               C.c_void_p(stream or 0)))
 
     def launch_count(self):
         c = C.c_uint64(0)

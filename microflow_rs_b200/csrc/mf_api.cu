@@ -4,14 +4,20 @@
 // MF_ERR_NO_DEVICE (only MF_FLAG_HOST_ONLY models -- parse + preprocess, i.e. the proc-macro's job -- work).
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+
 #include <algorithm>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <fstream>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/microflow_cuda.h"
@@ -45,9 +51,71 @@ struct Slot {
     uint8_t *out_t = nullptr;
 };
 
+// One host thread per device of a multi-device model: it owns every CUDA call made for its replica (enqueueing a step is ~60
+// driver calls; eight devices fed from one thread would be launch-bound).  Tasks run in FIFO order.
+class Worker {
+  public:
+    Worker() : th_([this] { loop(); }) {}
+    ~Worker() {
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        th_.join();
+    }
+    void post(std::function<void()> f) {
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            q_.push_back(std::move(f));
+            ++pending_;
+        }
+        cv_.notify_all();
+    }
+    void drain() {
+        std::unique_lock<std::mutex> l(mu_);
+        done_.wait(l, [this] { return pending_ == 0; });
+    }
+
+  private:
+    void loop() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> l(mu_);
+                cv_.wait(l, [this] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                f = std::move(q_.front());
+                q_.pop_front();
+            }
+            f();
+            {
+                std::lock_guard<std::mutex> l(mu_);
+                --pending_;
+            }
+            done_.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::deque<std::function<void()>> q_;
+    size_t pending_ = 0;
+    bool stop_ = false;
+    std::thread th_;
+};
+
 }  // namespace
 
 struct mf_model {
+    // ---- multi-device model (mf_options.n_devices > 1): this object only routes; replicas[r] is a complete single-device model on
+    // devices[r], workers[r] the host thread that drives it.  Everything below `replicas` is unused in a routing object.
+    std::vector<mf_model *> replicas;
+    std::vector<std::unique_ptr<Worker>> workers;
+    const char *bcast = "none";             // how the weight blob reached replicas[1..]
+    std::mutex group_mu;                    // serialises group calls and guards the deferred error of asynchronous ones
+    int deferred_rc = 0;
+    std::string deferred_err;
+    std::vector<const char *> launched;     // per layer: kernel the most recent predict*/trace call launched ("" = none)
     ModelSpec spec;
     std::vector<LayerExec> layers;
     uint32_t flags = 0;
@@ -119,12 +187,21 @@ int alloc_slot(mf_model *m, Slot &s) {
     MF_CUDA(cudaMalloc(&s.act[0], c * m->spec.max_elems));
     MF_CUDA(cudaMalloc(&s.act[1], c * m->spec.max_elems));
     MF_CUDA(cudaMalloc(&s.in_q, c * m->spec.in_elems));
-    MF_CUDA(cudaMalloc(&s.in_f32, c * m->spec.in_elems * sizeof(float)));
+    // in_f32 (4 bytes per input element: 1.2 GB per slot for person_detect at the default chunk) is only needed by the f32
+    // predict() entry points: allocated on their first use (ensure_f32_staging)
     MF_CUDA(cudaMalloc(&s.out_f32, c * m->spec.out_elems * sizeof(float)));
     MF_CUDA(cudaMalloc(&s.out_q, c * m->spec.out_elems));
-    MF_CUDA(cudaMalloc(&s.logits, c * m->spec.max_elems));
+    {   // "logits" = the input of the trailing softmax (a few bytes per sample), not a whole activation tensor
+        const size_t le = m->softmax_tail >= 0 ? m->layers[(size_t)m->softmax_tail].spec.in_elems : 0;
+        MF_CUDA(cudaMalloc(&s.logits, c * (le ? le : 1)));
+    }
     if (m->geo_in.transpose) MF_CUDA(cudaMalloc(&s.in_t, c * m->spec.in_elems));
     if (m->geo_out.transpose) MF_CUDA(cudaMalloc(&s.out_t, c * m->spec.out_elems * sizeof(float)));
+    return MF_OK;
+}
+
+int ensure_f32_staging(mf_model *m, Slot &s) {
+    if (!s.in_f32) MF_CUDA(cudaMalloc(&s.in_f32, m->chunk * m->spec.in_elems * sizeof(float)));
     return MF_OK;
 }
 
@@ -174,6 +251,8 @@ int run_chunk(mf_model *m, Slot &s, const uint8_t *d_in, size_t n, float *d_out_
             cudaError_t e = launch_tail_fused(t, st);
             if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("tail_fused_kernel launch failed: ") + cudaGetErrorString(e));
             m->launches += 1;
+            m->launched[i] = "tail_fused_kernel";
+            for (size_t k = i + 1; k <= (size_t)m->tail_last; ++k) m->launched[k] = "";
             pdl = use_pdl;
             cur = t.out;
             flip ^= 1;
@@ -193,6 +272,8 @@ int run_chunk(mf_model *m, Slot &s, const uint8_t *d_in, size_t n, float *d_out_
             cudaError_t e = launch_fc_warp(a, st);
             if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("fc_warp_kernel(+softmax) launch failed: ") + cudaGetErrorString(e));
             m->launches += 1;
+            m->launched[i] = "fc_warp_kernel";
+            for (size_t k = i + 1; k <= (size_t)m->fc_tail_last; ++k) m->launched[k] = "";
             pdl = use_pdl;
             cur = a.sm_out;
             flip ^= 1;
@@ -211,6 +292,7 @@ int run_chunk(mf_model *m, Slot &s, const uint8_t *d_in, size_t n, float *d_out_
             cudaError_t e = L.run(cur, dst, (long long)n, m->num_sms, st, &err, pdl);
             if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string(kernel_name(L.kernel)) + " launch failed: " + cudaGetErrorString(e) + " " + err);
             m->launches += 1;
+            m->launched[i] = L.launched_name(cur, dst, (long long)n);
             pdl = use_pdl;
             cur = dst;
             flip ^= 1;
@@ -288,6 +370,7 @@ int predict_small_graph(mf_model *m, const void *in_q, const float *in_f32, size
     const size_t le = m->softmax_tail >= 0 ? m->layers[(size_t)m->softmax_tail].spec.in_elems : 0;
     const int kind = (in_f32 ? 1 : 0) | (out_f32 ? 2 : 0) | (out_q ? 4 : 0) | (logits ? 8 : 0);
     Slot &s = m->slot[0];
+    if (in_f32 && ensure_f32_staging(m, s) != MF_OK) { (void)cudaGetLastError(); return -1; }
     if (!m->h_stage_in) {
         if (cudaMallocHost(&m->h_stage_in, kGraphMaxN * ie * sizeof(float)) != cudaSuccess ||
             cudaMallocHost(&m->h_stage_out_f32, kGraphMaxN * oe * sizeof(float)) != cudaSuccess ||
@@ -386,6 +469,8 @@ int predict_many_host(mf_model *m, const void *in_q, const float *in_f32, size_t
         Slot &s = m->slot[ci & 1];
         const size_t cn = std::min(piece, n - off);
         if (in_f32) {   // predict(): quantize the f32 input on the device (src/tensor.rs:80-86, :246-256)
+            rc = ensure_f32_staging(m, s);
+            if (rc) return rc;
             MF_CUDA(cudaMemcpyAsync(s.in_f32, in_f32 + off * ie, cn * ie * sizeof(float), cudaMemcpyHostToDevice, s.stream));
             cudaError_t e = launch_quantize(s.in_f32, s.in_q, cn * ie, m->spec.in_scale, (float)m->spec.in_zp, m->spec.is_u8_in, s.stream);
             if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("quantize launch failed: ") + cudaGetErrorString(e));
@@ -419,18 +504,9 @@ int predict_many_host(mf_model *m, const void *in_q, const float *in_f32, size_t
     return MF_OK;
 }
 
-int create_model(const uint8_t *buf, size_t len, const mf_options *opt, mf_model **out) {
-    if (!out) return fail(MF_ERR_INVALID_ARG, "null output pointer");
-    *out = nullptr;
-    mf_options o{};
-    o.struct_size = sizeof(mf_options);
-    o.device = -1;
-    if (opt) {   // struct_size versions the struct: an ABI-1 caller (16 bytes, no `layout`) is accepted, unknown trailing bytes are ignored
-        if (opt->struct_size < 16) return fail(MF_ERR_INVALID_ARG, "mf_options.struct_size too small");
-        std::memcpy(&o, opt, std::min<size_t>(opt->struct_size, sizeof(mf_options)));
-        o.struct_size = sizeof(mf_options);
-    }
-    if (o.layout != MF_LAYOUT_NHWC && o.layout != MF_LAYOUT_NALGEBRA) return fail(MF_ERR_INVALID_ARG, "mf_options.layout must be MF_LAYOUT_NHWC or MF_LAYOUT_NALGEBRA");
+// One complete single-device model on o.device.  upload_weights == false (replicas 1.. of a multi-device model): the blob is
+// allocated and zeroed, its contents arrive by the broadcast in create_model.
+int create_single(const uint8_t *buf, size_t len, const mf_options &o, bool upload_weights, mf_model **out) {
     std::unique_ptr<mf_model, void (*)(mf_model *)> m(new mf_model(), mf_model_destroy);
     std::string err;
     int rc = parse_tflite(buf, len, m->spec, err);
@@ -479,11 +555,13 @@ int create_model(const uint8_t *buf, size_t len, const mf_options *opt, mf_model
             break;
         }
     m->blob_bytes = bb.bytes().size();
+    m->launched.assign(m->layers.size(), "");
     if (have_device) {
         m->chunk = o.chunk ? o.chunk : 8192;
         if (m->blob_bytes) {
             MF_CUDA(cudaMalloc(&m->d_blob, m->blob_bytes));
-            MF_CUDA(cudaMemcpy(m->d_blob, bb.bytes().data(), m->blob_bytes, cudaMemcpyHostToDevice));
+            if (upload_weights) MF_CUDA(cudaMemcpy(m->d_blob, bb.bytes().data(), m->blob_bytes, cudaMemcpyHostToDevice));
+            else MF_CUDA(cudaMemset(m->d_blob, 0, m->blob_bytes));
         }
         for (auto &L : m->layers)
             if (!L.resolve(m->d_blob, &err)) return fail(MF_ERR_CUDA, err);
@@ -496,6 +574,169 @@ int create_model(const uint8_t *buf, size_t len, const mf_options *opt, mf_model
     *out = m.release();
     return MF_OK;
 }
+
+// ---- one broadcast of the static weight blob from replicas[0] to the others -------------------------------------------------
+// NCCL is loaded at run time (libnccl.so.2: the torch-bundled or the system one) so the library has no link-time dependency on
+// it; without it the same bytes travel by cudaMemcpyPeer.  Either way it happens once, at create; nothing is exchanged later.
+struct NcclApi {
+    typedef int (*InitAllFn)(void **, int, const int *);
+    typedef int (*BcastFn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+    typedef int (*VoidFn)(void);
+    typedef int (*DestroyFn)(void *);
+    InitAllFn comm_init_all = nullptr;
+    BcastFn broadcast = nullptr;
+    VoidFn group_start = nullptr, group_end = nullptr;
+    DestroyFn comm_destroy = nullptr;
+    bool ok = false;
+};
+const NcclApi &nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        if (std::getenv("MF_NO_NCCL")) return a;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return a;
+        a.comm_init_all = (NcclApi::InitAllFn)dlsym(h, "ncclCommInitAll");
+        a.broadcast = (NcclApi::BcastFn)dlsym(h, "ncclBroadcast");
+        a.group_start = (NcclApi::VoidFn)dlsym(h, "ncclGroupStart");
+        a.group_end = (NcclApi::VoidFn)dlsym(h, "ncclGroupEnd");
+        a.comm_destroy = (NcclApi::DestroyFn)dlsym(h, "ncclCommDestroy");
+        a.ok = a.comm_init_all && a.broadcast && a.group_start && a.group_end && a.comm_destroy;
+        return a;
+    }();
+    return api;
+}
+
+int broadcast_blob(mf_model *g) {
+    const size_t G = g->replicas.size(), bytes = g->replicas[0]->blob_bytes;
+    g->bcast = "none";
+    if (G < 2 || !bytes) return MF_OK;
+    const NcclApi &nc = nccl_api();
+    bool distinct = true;
+    for (size_t r = 0; r < G; ++r)
+        for (size_t q = 0; q < r; ++q) distinct = distinct && g->replicas[r]->device != g->replicas[q]->device;
+    if (nc.ok && distinct) {
+        std::vector<void *> comms(G, nullptr);
+        std::vector<int> devs(G);
+        for (size_t r = 0; r < G; ++r) devs[r] = g->replicas[r]->device;
+        bool ok = nc.comm_init_all(comms.data(), (int)G, devs.data()) == 0;
+        if (ok) {
+            ok = nc.group_start() == 0;
+            for (size_t r = 0; ok && r < G; ++r) {
+                ok = cudaSetDevice(devs[r]) == cudaSuccess &&
+                     nc.broadcast(g->replicas[0]->d_blob, g->replicas[r]->d_blob, bytes, /*ncclUint8*/ 1, /*root*/ 0, comms[r], g->replicas[r]->slot[0].stream) == 0;
+            }
+            ok = (nc.group_end() == 0) && ok;
+            for (size_t r = 0; r < G; ++r)
+                if (cudaSetDevice(devs[r]) != cudaSuccess || cudaStreamSynchronize(g->replicas[r]->slot[0].stream) != cudaSuccess) ok = false;
+        }
+        for (void *c : comms)
+            if (c) nc.comm_destroy(c);
+        if (ok) { g->bcast = "nccl"; return MF_OK; }
+        (void)cudaGetLastError();
+    }
+    for (size_t r = 1; r < G; ++r)
+        MF_CUDA(cudaMemcpyPeer(g->replicas[r]->d_blob, g->replicas[r]->device, g->replicas[0]->d_blob, g->replicas[0]->device, bytes));
+    g->bcast = "memcpy_peer";
+    return MF_OK;
+}
+
+int create_model(const uint8_t *buf, size_t len, const mf_options *opt, mf_model **out) {
+    if (!out) return fail(MF_ERR_INVALID_ARG, "null output pointer");
+    *out = nullptr;
+    mf_options o{};
+    o.struct_size = sizeof(mf_options);
+    o.device = -1;
+    if (opt) {   // struct_size versions the struct: an ABI-1 caller (16 bytes, no `layout`) or an ABI-2 caller (20 bytes, no device list) is accepted
+        if (opt->struct_size < 16) return fail(MF_ERR_INVALID_ARG, "mf_options.struct_size too small");
+        std::memcpy(&o, opt, std::min<size_t>(opt->struct_size, sizeof(mf_options)));
+        o.struct_size = sizeof(mf_options);
+    }
+    if (o.layout != MF_LAYOUT_NHWC && o.layout != MF_LAYOUT_NALGEBRA) return fail(MF_ERR_INVALID_ARG, "mf_options.layout must be MF_LAYOUT_NHWC or MF_LAYOUT_NALGEBRA");
+    if (o.n_devices > MF_MAX_DEVICES || o.n_devices < -1) return fail(MF_ERR_INVALID_ARG, "mf_options.n_devices out of range");
+    std::vector<int> devs;
+    if (o.n_devices != 0 && !(o.flags & MF_FLAG_HOST_ONLY)) {
+        int n = 0;
+        int rc = check_device(&n);
+        if (rc) return rc;
+        if (o.n_devices == -1) { for (int d = 0; d < n && d < MF_MAX_DEVICES; ++d) devs.push_back(d); }
+        else devs.assign(o.devices, o.devices + o.n_devices);
+        for (size_t i = 0; i < devs.size(); ++i) {
+            if (devs[i] < 0 || devs[i] >= n) return fail(MF_ERR_INVALID_ARG, "mf_options.devices: ordinal out of range");
+            // MF_ALLOW_DUPLICATE_DEVICES=1 (tests only): several replicas on one GPU, so that a one-GPU box exercises the routing,
+            // the per-replica host threads and the sharding of a multi-device model
+            for (size_t j = 0; j < i; ++j)
+                if (devs[j] == devs[i] && !std::getenv("MF_ALLOW_DUPLICATE_DEVICES")) return fail(MF_ERR_INVALID_ARG, "mf_options.devices: duplicate ordinal");
+        }
+    }
+    if (devs.size() <= 1) {
+        if (devs.size() == 1) o.device = devs[0];
+        return create_single(buf, len, o, true, out);
+    }
+    int prev = 0;
+    (void)cudaGetDevice(&prev);
+    std::unique_ptr<mf_model, void (*)(mf_model *)> g(new mf_model(), mf_model_destroy);
+    for (size_t r = 0; r < devs.size(); ++r) {
+        mf_options od = o;
+        od.device = devs[r];
+        mf_model *rep = nullptr;
+        int rc = create_single(buf, len, od, r == 0, &rep);
+        if (rc) { (void)cudaSetDevice(prev); return rc; }
+        g->replicas.push_back(rep);
+        g->workers.emplace_back(new Worker());
+    }
+    int rc = broadcast_blob(g.get());
+    (void)cudaSetDevice(prev);
+    if (rc) return rc;
+    *out = g.release();
+    return MF_OK;
+}
+
+// contiguous shard of replica r: [r * ceil(n / G), min(n, (r + 1) * ceil(n / G)))
+inline void shard_range(size_t n, size_t r, size_t G, size_t &lo, size_t &hi) {
+    const size_t per = (n + G - 1) / G;
+    lo = std::min(n, r * per);
+    hi = std::min(n, lo + per);
+}
+
+// multi-device predict_many*: every replica runs its shard on its own host thread; nothing is exchanged
+int group_predict_many(mf_model *g, const void *in_q, const float *in_f32, size_t n, float *out_f32, void *out_q, void *logits, bool wait) {
+    if ((!in_q && !in_f32) || (!out_f32 && !out_q)) return fail(MF_ERR_INVALID_ARG, "null input or output buffer");
+    std::lock_guard<std::mutex> lock(g->group_mu);
+    const size_t G = g->replicas.size();
+    const mf_model *p = g->replicas[0];
+    const size_t ie = p->spec.in_elems, oe = p->spec.out_elems;
+    const size_t le = p->softmax_tail >= 0 ? p->layers[(size_t)p->softmax_tail].spec.in_elems : 0;
+    struct Res { int rc = 0; std::string err; };
+    auto res = std::make_shared<std::vector<Res>>(G);
+    for (size_t r = 0; r < G; ++r) {
+        size_t lo, hi;
+        shard_range(n, r, G, lo, hi);
+        if (hi <= lo) continue;
+        mf_model *rep = g->replicas[r];
+        g->workers[r]->post([=] {
+            int rc = predict_many_host(rep, in_q ? (const uint8_t *)in_q + lo * ie : nullptr, in_f32 ? in_f32 + lo * ie : nullptr, hi - lo,
+                                       out_f32 ? out_f32 + lo * oe : nullptr, out_q ? (uint8_t *)out_q + lo * oe : nullptr,
+                                       logits ? (uint8_t *)logits + lo * le : nullptr, wait);
+            if (rc) {
+                (*res)[r].rc = rc;
+                (*res)[r].err = g_err;
+                if (!wait) {   // asynchronous call: the error surfaces at mf_model_synchronize
+                    std::lock_guard<std::mutex> l(g->group_mu);
+                    if (!g->deferred_rc) { g->deferred_rc = rc; g->deferred_err = g_err; }
+                }
+            }
+        });
+    }
+    if (!wait) return MF_OK;
+    for (auto &w : g->workers) w->drain();
+    for (size_t r = 0; r < G; ++r)
+        if ((*res)[r].rc) return fail((*res)[r].rc, "device " + std::to_string(g->replicas[r]->device) + ": " + (*res)[r].err);
+    return MF_OK;
+}
+
+inline mf_model *primary(mf_model *m) { return (m && !m->replicas.empty()) ? m->replicas[0] : m; }
+inline const mf_model *primary(const mf_model *m) { return (m && !m->replicas.empty()) ? m->replicas[0] : m; }
 
 }  // namespace
 
@@ -537,6 +778,13 @@ int mf_model_create_from_file(const char *path, const mf_options *opt, mf_model 
 }
 void mf_model_destroy(mf_model *m) {
     if (!m) return;
+    if (!m->replicas.empty() || !m->workers.empty()) {   // routing object of a multi-device model
+        for (auto &w : m->workers) w->drain();
+        m->workers.clear();
+        for (mf_model *r : m->replicas) mf_model_destroy(r);
+        delete m;
+        return;
+    }
     if (!m->host_only) {
         cudaSetDevice(m->device);
         cudaDeviceSynchronize();
@@ -555,6 +803,7 @@ void mf_model_destroy(mf_model *m) {
 
 int mf_model_io_info(const mf_model *m, mf_tensor_info *in, mf_tensor_info *out) {
     if (!m) return fail(MF_ERR_INVALID_ARG, "null model");
+    m = primary(m);
     if (in) {
         *in = mf_tensor_info{};
         in->rank = m->spec.in_rank;
@@ -571,8 +820,9 @@ int mf_model_io_info(const mf_model *m, mf_tensor_info *in, mf_tensor_info *out)
     }
     return MF_OK;
 }
-int mf_model_num_layers(const mf_model *m) { return m ? (int)m->layers.size() : 0; }
+int mf_model_num_layers(const mf_model *m) { return m ? (int)primary(m)->layers.size() : 0; }
 int mf_model_layer_info(const mf_model *m, int i, mf_layer_info *o) {
+    m = primary(m);
     if (!m || !o || i < 0 || (size_t)i >= m->layers.size()) return fail(MF_ERR_INVALID_ARG, "bad layer index");
     const LayerExec &E = m->layers[(size_t)i];
     const LayerSpec &L = E.spec;
@@ -594,6 +844,7 @@ int mf_model_layer_info(const mf_model *m, int i, mf_layer_info *o) {
     return MF_OK;
 }
 int mf_model_layer_constants(const mf_model *m, int i, float *c0, float *c1, int32_t *c2, int32_t *c3, int cap) {
+    m = primary(m);
     if (!m || i < 0 || (size_t)i >= m->layers.size() || cap < 0) return fail(MF_ERR_INVALID_ARG, "bad layer index");
     const LayerSpec &L = m->layers[(size_t)i].spec;
     for (size_t k = 0; c0 && k < L.c0.size() && k < (size_t)cap; ++k) c0[k] = L.c0[k];
@@ -604,6 +855,7 @@ int mf_model_layer_constants(const mf_model *m, int i, float *c0, float *c1, int
 }
 int mf_model_dump(const mf_model *m, const char *path) {
     if (!m || !path) return fail(MF_ERR_INVALID_ARG, "null argument");
+    m = primary(m);
     FILE *f = std::fopen(path, "w");
     if (!f) return fail(MF_ERR_FILE, std::string("cannot open '") + path + "' for writing");
     std::fprintf(f, "# microflow_cuda model dump (equivalent of target/microflow-expansion.rs)\n");
@@ -633,19 +885,34 @@ int mf_model_dump(const mf_model *m, const char *path) {
     return MF_OK;
 }
 
-int mf_predict(mf_model *m, const float *in, float *out) { return predict_many_host(m, nullptr, in, 1, out, nullptr, nullptr); }
-int mf_predict_quantized(mf_model *m, const void *in_q, float *out) { return predict_many_host(m, in_q, nullptr, 1, out, nullptr, nullptr); }
-int mf_predict_many(mf_model *m, const float *in, size_t n, float *out) { return predict_many_host(m, nullptr, in, n, out, nullptr, nullptr); }
-int mf_predict_many_quantized(mf_model *m, const void *in_q, size_t n, float *out) { return predict_many_host(m, in_q, nullptr, n, out, nullptr, nullptr); }
+// host-buffer entry points: a multi-device model shards the samples over its replicas, a single-device model runs them itself
+static int predict_host_any(mf_model *m, const void *in_q, const float *in_f32, size_t n, float *out_f32, void *out_q, void *logits, bool wait = true) {
+    if (!m) return fail(MF_ERR_INVALID_ARG, "null model");
+    if (!m->replicas.empty()) return group_predict_many(m, in_q, in_f32, n, out_f32, out_q, logits, wait);
+    return predict_many_host(m, in_q, in_f32, n, out_f32, out_q, logits, wait);
+}
+int mf_predict(mf_model *m, const float *in, float *out) { return predict_host_any(m, nullptr, in, 1, out, nullptr, nullptr); }
+int mf_predict_quantized(mf_model *m, const void *in_q, float *out) { return predict_host_any(m, in_q, nullptr, 1, out, nullptr, nullptr); }
+int mf_predict_many(mf_model *m, const float *in, size_t n, float *out) { return predict_host_any(m, nullptr, in, n, out, nullptr, nullptr); }
+int mf_predict_many_quantized(mf_model *m, const void *in_q, size_t n, float *out) { return predict_host_any(m, in_q, nullptr, n, out, nullptr, nullptr); }
 int mf_predict_many_quantized_async(mf_model *m, const void *in_q, size_t n, float *out) {
-    return predict_many_host(m, in_q, nullptr, n, out, nullptr, nullptr, /*wait=*/false);
+    return predict_host_any(m, in_q, nullptr, n, out, nullptr, nullptr, /*wait=*/false);
 }
 int mf_predict_many_logits(mf_model *m, const void *in_q, size_t n, void *out_q, void *logits_q) {
     if (!out_q) return fail(MF_ERR_INVALID_ARG, "null out_q");
-    return predict_many_host(m, in_q, nullptr, n, nullptr, out_q, logits_q);
+    if (m && logits_q && primary(m)->softmax_tail < 0) return fail(MF_ERR_INVALID_ARG, "model has no softmax layer: no logits to return");
+    return predict_host_any(m, in_q, nullptr, n, nullptr, out_q, logits_q);
+}
+
+int mf_predict_many_device_on(mf_model *m, int index, const void *d_in_q, size_t n, float *d_out_f32, void *d_out_q, void *stream) {
+    if (!m) return fail(MF_ERR_INVALID_ARG, "null model");
+    if (m->replicas.empty()) return index == 0 ? mf_predict_many_device(m, d_in_q, n, d_out_f32, d_out_q, stream) : fail(MF_ERR_INVALID_ARG, "device index out of range");
+    if (index < 0 || (size_t)index >= m->replicas.size()) return fail(MF_ERR_INVALID_ARG, "device index out of range");
+    return mf_predict_many_device(m->replicas[(size_t)index], d_in_q, n, d_out_f32, d_out_q, stream);
 }
 
 int mf_predict_many_device(mf_model *m, const void *d_in_q, size_t n, float *d_out_f32, void *d_out_q, void *stream) {
+    m = primary(m);      // device buffers belong to one device: a multi-device model serves this call on devices[0] (see mf_predict_many_device_on)
     int rc = need_device(m);
     if (rc) return rc;
     if (!d_in_q) return fail(MF_ERR_INVALID_ARG, "null device input");
@@ -699,6 +966,7 @@ int mf_predict_many_device(mf_model *m, const void *d_in_q, size_t n, float *d_o
 }
 
 int mf_predict_trace(mf_model *m, const void *in_q, size_t n, void *const *layer_outs) {
+    m = primary(m);
     int rc = need_device(m);
     if (rc) return rc;
     if (!in_q || !layer_outs) return fail(MF_ERR_INVALID_ARG, "null argument");
@@ -717,6 +985,23 @@ int mf_predict_trace(mf_model *m, const void *in_q, size_t n, void *const *layer
 }
 
 int mf_model_synchronize(mf_model *m) {
+    if (m && !m->replicas.empty()) {
+        for (auto &w : m->workers) w->drain();
+        int first = MF_OK;
+        for (mf_model *r : m->replicas) {
+            int rc = mf_model_synchronize(r);
+            if (rc && !first) first = rc;
+        }
+        std::lock_guard<std::mutex> lock(m->group_mu);
+        if (m->deferred_rc) {
+            const int rc = m->deferred_rc;
+            const std::string e = m->deferred_err;
+            m->deferred_rc = 0;
+            m->deferred_err.clear();
+            return fail(rc, e);
+        }
+        return first;
+    }
     int rc = need_device(m);
     if (rc) return rc;
     MF_CUDA(cudaSetDevice(m->device));
@@ -724,16 +1009,20 @@ int mf_model_synchronize(mf_model *m) {
     return MF_OK;
 }
 int mf_model_set_profiling(mf_model *m, int enabled) {
+    m = primary(m);
     int rc = need_device(m);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lock(m->mu);
     m->profiling = enabled != 0;
     m->prof_chunks = 0;
     return MF_OK;
 }
 int mf_model_layer_times_ms(mf_model *m, float *ms, int cap) {
+    m = primary(m);
     int rc = need_device(m);
     if (rc) return rc;
     if (!ms || cap < (int)m->layers.size()) return fail(MF_ERR_INVALID_ARG, "ms buffer too small");
+    std::lock_guard<std::mutex> lock(m->mu);
     MF_CUDA(cudaSetDevice(m->device));
     MF_CUDA(cudaDeviceSynchronize());
     const size_t L = m->layers.size();
@@ -750,9 +1039,27 @@ int mf_model_layer_times_ms(mf_model *m, float *ms, int cap) {
 int mf_model_launch_count(const mf_model *m, uint64_t *count) {
     if (!m || !count) return fail(MF_ERR_INVALID_ARG, "null argument");
     *count = m->launches;
+    for (const mf_model *r : m->replicas) *count += r->launches;
     return MF_OK;
 }
+const char *mf_model_layer_launched(const mf_model *m, int layer) {
+    m = primary(m);
+    if (!m || layer < 0 || (size_t)layer >= m->launched.size()) return "";
+    return m->launched[(size_t)layer];
+}
+int mf_model_devices(const mf_model *m, int32_t *devices, int cap) {
+    if (!m) return 0;
+    if (m->replicas.empty()) {
+        if (m->host_only) return 0;
+        if (devices && cap > 0) devices[0] = m->device;
+        return 1;
+    }
+    for (size_t r = 0; r < m->replicas.size() && devices && (int)r < cap; ++r) devices[r] = m->replicas[r]->device;
+    return (int)m->replicas.size();
+}
+const char *mf_model_weight_broadcast(const mf_model *m) { return m ? m->bcast : "none"; }
 int mf_model_blob(const mf_model *m, void **d_ptr, size_t *bytes) {
+    m = primary(m);
     int rc = need_device(m);
     if (rc) return rc;
     if (d_ptr) *d_ptr = m->d_blob;
@@ -764,7 +1071,7 @@ int mf_host_alloc(void **p, size_t bytes) {
     if (!p) return fail(MF_ERR_INVALID_ARG, "null pointer");
     int rc = check_device(nullptr);
     if (rc) return rc;
-    MF_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+    MF_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable));   // usable by every device of a multi-device model
     return MF_OK;
 }
 int mf_host_free(void *p) {

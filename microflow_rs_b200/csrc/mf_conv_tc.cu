@@ -624,16 +624,20 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
         if (periodic && env_tab != kTabGroup) fn = conv_tc_kernel<false, true, 1, 1, 1, kTabPeriod>;
         else if (p.N <= 128) fn = conv_tc_kernel<false, true, 1, 1, 1, kTabGroup>;
     }
+    // the opt-in to > 48 KB of dynamic shared memory is per device (context): remember it per (device, kernel)
     static std::mutex attr_mu;
-    static std::vector<KernelFn> attr_done;
+    static std::vector<std::pair<int, KernelFn>> attr_done;
     {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
         std::lock_guard<std::mutex> lock(attr_mu);
         bool have = false;
-        for (auto f : attr_done) have = have || f == fn;
+        for (auto &f : attr_done) have = have || (f.first == dev && f.second == fn);
         if (!have) {
-            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
             if (e != cudaSuccess) return e;
-            attr_done.push_back(fn);
+            attr_done.emplace_back(dev, fn);
         }
     }
     const unsigned grid = (unsigned)(k.num_tiles < num_sms ? k.num_tiles : num_sms);

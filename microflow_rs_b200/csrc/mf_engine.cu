@@ -206,12 +206,17 @@ bool LayerExec::resolve(const uint8_t *d, std::string *err) {
         a.off_c = L.pad == MF_PAD_SAME ? (L.KW - 1) / 2 : 0;
         a.in_zp = L.in_zp; a.lo = (float)L.act_lo; a.hi = (float)L.act_hi; a.is_u8 = L.is_u8; a.depthwise = L.op == MF_OP_DEPTHWISE_CONV_2D;
         a.big_acc = big_acc;
+        // plan() chose from the LayerSpec alone; the launch-side predicates (alignment, shared-memory budget, window geometry)
+        // have the last word, so a shape they refuse runs on the generic kernel instead of failing at launch
+        if (kernel == Kernel::PwConvDp4a && !pwconv_dp4a_eligible(a)) { kernel = Kernel::ConvGeneric; why_not_fast = "1x1 conv reads outside the input: generic kernel"; }
+        if (kernel == Kernel::DwConvCin1 && !dwconv_cin1_eligible(a)) { kernel = Kernel::ConvGeneric; why_not_fast = "Cin=1 depthwise kernel too large for the fast kernel"; }
+        if ((kernel == Kernel::DwConvC4 || kernel == Kernel::DwConv3x3Rows) && !dwconv_c4_eligible(a)) { kernel = Kernel::ConvGeneric; why_not_fast = "depthwise shape refused by the fast kernel"; }
         if (kernel == Kernel::ConvTcPointwise || kernel == Kernel::ConvTc3x3) {
             tc.d_wmat = at(o_tc_w);
             std::string why;
             if (!conv_tc_finalize_plan(tc, &why)) {  // fall back to the SIMT path, never to the CPU
                 why_not_fast = "tensor core plan rejected: " + why;
-                kernel = (L.KH == 1 && L.KW == 1 && L.Cin % 4 == 0) ? Kernel::PwConvDp4a : Kernel::ConvGeneric;
+                kernel = (L.KH == 1 && L.KW == 1 && L.Cin % 4 == 0 && pwconv_dp4a_eligible(a)) ? Kernel::PwConvDp4a : Kernel::ConvGeneric;
             }
         }
     } else if (L.op == MF_OP_FULLY_CONNECTED) {

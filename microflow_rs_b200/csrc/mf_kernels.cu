@@ -1334,7 +1334,10 @@ __global__ void __launch_bounds__(256) pwconv_dp4a_kernel(ConvArgs a, uint32_t i
 }
 
 bool pwconv_dp4a_eligible(const ConvArgs &a) {
-    return !a.depthwise && !a.is_u8 && a.KH == 1 && a.KW == 1 && (a.Cin % 4) == 0 && a.kcorr != nullptr;
+    // the kernel reads in[(sh*i)*W + sw*j] unchecked: every output position must map inside the input (a model whose declared
+    // output is larger than the strided input would need the reference's padding semantics -> generic kernel)
+    return !a.depthwise && !a.is_u8 && a.KH == 1 && a.KW == 1 && (a.Cin % 4) == 0 && a.kcorr != nullptr && (long long)a.sh * (a.OH - 1) < a.H &&
+           (long long)a.sw * (a.OW - 1) < a.W;
 }
 cudaError_t launch_pwconv_dp4a(const ConvArgs &a, cudaStream_t s) {
     const int G = (a.Cout + 3) / 4;

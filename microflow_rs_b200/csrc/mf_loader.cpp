@@ -121,9 +121,16 @@ bool read_tensor(const Fb &fb, const Fb::Vec &tensors, const Fb::Vec &buffers, i
 // i64 -> T by truncation (microflow-macros/src/tensor.rs:81-88 `to_subset_unchecked`)
 inline int zp_cast(int64_t z, bool is_u8) { return is_u8 ? (int)(uint8_t)z : (int)(int8_t)z; }
 inline int elem(uint8_t b, bool is_u8) { return is_u8 ? (int)b : (int)(int8_t)b; }
+// element count of a shape; dimensions are untrusted: a negative one counts as 0 and anything beyond kMaxElems (2^31, far above
+// every tensor the kernels can index with 32-bit offsets) saturates to kTooMany, which every caller rejects
+constexpr size_t kMaxElems = (size_t)1 << 31, kTooMany = ~(size_t)0;
 inline size_t prod(const std::vector<int> &s) {
     size_t p = 1;
-    for (int d : s) p *= (size_t)(d < 0 ? 0 : d);
+    for (int d : s) {
+        if (d <= 0) return 0;
+        if (p > kMaxElems / (size_t)d) return kTooMany;
+        p *= (size_t)d;
+    }
     return p;
 }
 inline bool finite_all(const std::vector<float> &v) {
@@ -236,6 +243,7 @@ int parse_tflite(const uint8_t *buf, size_t len, ModelSpec &M, std::string &err)
     M.in_scale = ti.scale[0];
     M.in_zp = zp_cast(ti.zp[0], M.is_u8_in);
     M.in_elems = prod(ishape);
+    if (M.in_elems == kTooMany) return fail(MF_ERR_UNSUPPORTED_SHAPE, "input tensor has more than 2^31 elements");
     M.max_elems = M.in_elems;
 
     // ---- operators, in execution order; each consumes the previous op's output (lib.rs:130-151, :198-201)
@@ -269,6 +277,8 @@ int parse_tflite(const uint8_t *buf, size_t len, ModelSpec &M, std::string &err)
         for (int i = 0; i < L.out_rank; ++i) L.out_dims[i] = oshape[i];
         L.in_elems = prod(tin.shape);
         L.out_elems = prod(oshape);
+        if (L.in_elems == kTooMany || L.out_elems == kTooMany)
+            return fail(MF_ERR_UNSUPPORTED_SHAPE, "operator " + std::to_string(oi) + ": tensor with more than 2^31 elements");
         if (!tin.scale.empty()) L.in_scale = tin.scale[0];
         if (!tin.zp.empty()) L.in_zp = zp_cast(tin.zp[0], L.is_u8);
         if (!tout.scale.empty()) L.out_scale = tout.scale[0];
@@ -289,12 +299,16 @@ int parse_tflite(const uint8_t *buf, size_t len, ModelSpec &M, std::string &err)
                 return fail(MF_ERR_INVALID_MODEL, "invalid model: bad filter/bias tensor");
             if (tw.shape.size() != 4 || !tw.data || !tb.data || tw.scale.empty() || tw.zp.empty() || tb.scale.empty() || tb.zp.empty())
                 return fail(MF_ERR_INVALID_MODEL, "invalid model: convolution filter/bias without data or quantization");
+            // the reference's ops take Tensor4D<T, 1, ...> (src/ops/conv_2d.rs:40: BATCHES fixed to 1) and depthwise weights of shape
+            // [1, KH, KW, C]: anything else would not type-check there, and every kernel here strides samples by H*W*C
+            if (tin.shape[0] != 1 || tout.shape[0] != 1 || (dw && tw.shape[0] != 1))
+                return fail(MF_ERR_UNSUPPORTED_SHAPE, "convolution " + std::to_string(oi) + ": tensor batch dimension must be 1");
             L.H = tin.shape[1]; L.W = tin.shape[2]; L.Cin = tin.shape[3];
             L.OH = tout.shape[1]; L.OW = tout.shape[2];
             L.KH = tw.shape[1]; L.KW = tw.shape[2];
             L.Cout = dw ? tw.shape[3] : tw.shape[0];
-            if (L.Cout != tout.shape[3] || (!dw && tw.shape[3] != L.Cin) || tw.data_len < prod(tw.shape) || tb.data_len < (size_t)L.Cout * 4 ||
-                L.Cout <= 0 || L.KH <= 0 || L.KW <= 0)
+            if (L.Cout != tout.shape[3] || (!dw && tw.shape[3] != L.Cin) || prod(tw.shape) == kTooMany || tw.data_len < prod(tw.shape) ||
+                tb.data_len < (size_t)L.Cout * 4 || L.Cout <= 0 || L.KH <= 0 || L.KW <= 0)
                 return fail(MF_ERR_UNSUPPORTED_SHAPE, "convolution " + std::to_string(oi) + ": inconsistent filter/bias/output shapes");
             L.w.assign(tw.data, tw.data + prod(tw.shape));
             for (int64_t z : tw.zp) L.w_zp.push_back(zp_cast(z, L.is_u8));
@@ -350,6 +364,7 @@ int parse_tflite(const uint8_t *buf, size_t len, ModelSpec &M, std::string &err)
             L.macs = (uint64_t)N * K;
         } else if (code == MF_OP_AVERAGE_POOL_2D) {
             if (tin.shape.size() != 4 || tout.shape.size() != 4) return fail(MF_ERR_UNSUPPORTED_RANK, "average_pool_2d needs 4-D input and output tensors");
+            if (tin.shape[0] != 1 || tout.shape[0] != 1) return fail(MF_ERR_UNSUPPORTED_SHAPE, "average_pool_2d: tensor batch dimension must be 1");
             L.H = tin.shape[1]; L.W = tin.shape[2]; L.Cin = L.Cout = tin.shape[3];
             L.OH = tout.shape[1]; L.OW = tout.shape[2];
             if (tout.shape[3] != L.Cin) return fail(MF_ERR_UNSUPPORTED_SHAPE, "average_pool_2d: channel mismatch");
@@ -409,6 +424,7 @@ int parse_tflite(const uint8_t *buf, size_t len, ModelSpec &M, std::string &err)
     M.out_scale = to.scale[0];
     M.out_zp = zp_cast(to.zp[0], M.is_u8_out);
     M.out_elems = prod(oshape);
+    if (M.out_elems == kTooMany) return fail(MF_ERR_UNSUPPORTED_SHAPE, "output tensor has more than 2^31 elements");
     if (M.out_elems != cur_elems) return fail(MF_ERR_UNSUPPORTED_SHAPE, "model output shape does not match the last operator");
     if (M.in_elems == 0 || M.out_elems == 0) return fail(MF_ERR_UNSUPPORTED_SHAPE, "empty input or output tensor");
     return MF_OK;

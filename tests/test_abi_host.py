@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     L = mf.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.mf_abi_version() == 2
+    assert L.mf_abi_version() == 3
 
 
 def _has_gpu():
@@ -104,7 +104,7 @@ def test_options_struct_is_versioned_by_struct_size():
     """mf_options grew a `layout` field in ABI 2: a 16-byte ABI-1 struct is still accepted, an unknown layout is rejected."""
     import ctypes as C
     L = mf.lib()
-    assert L.mf_abi_version() == 2
+    assert L.mf_abi_version() == 3
     data = (MODELS / "sine.tflite").read_bytes()
 
     class OldOptions(C.Structure):
@@ -160,3 +160,26 @@ def test_sass_shows_the_blackwell_paths():
     assert any("STG.E.ENL2.256" in t for t in tc)
     dw = [t for n, t in text.items() if re.search(r"dwconv3x3_(smem|pair)_kernel|dwconv_cin1_smem_kernel", n)]
     assert dw and all("UBLKCP" in t and "IDP.4A" in t and "FADD2" in t for t in dw)
+
+
+def test_device_list_options_are_validated_without_a_gpu():
+    """ABI 3: mf_options.n_devices / devices[].  A 20-byte ABI-2 struct (no device list) is still accepted; a list longer than
+    MF_MAX_DEVICES is refused; with MF_FLAG_HOST_ONLY (parse + preprocess only) the device list is not consulted."""
+    L = mf.lib()
+    data = (MODELS / "sine.tflite").read_bytes()
+
+    class Abi2Options(C.Structure):
+        _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("chunk", C.c_uint32), ("flags", C.c_uint32), ("layout", C.c_uint32)]
+
+    h = C.c_void_p()
+    old = Abi2Options(C.sizeof(Abi2Options), -1, 0, mf.FLAG_HOST_ONLY, 0)
+    assert L.mf_model_create_from_tflite(data, len(data), C.cast(C.byref(old), C.POINTER(mf._Options)), C.byref(h)) == 0
+    assert L.mf_model_devices(h, None, 0) == 0            # host-only: runs nowhere
+    assert L.mf_model_weight_broadcast(h) == b"none"
+    L.mf_model_destroy(h)
+    opt = mf._Options(C.sizeof(mf._Options), -1, 0, mf.FLAG_HOST_ONLY, 0)
+    opt.n_devices = mf.MAX_DEVICES + 1
+    assert L.mf_model_create_from_tflite(data, len(data), C.byref(opt), C.byref(h)) == 9      # MF_ERR_INVALID_ARG
+    m = mf.Model(MODELS / "sine.tflite", flags=mf.FLAG_HOST_ONLY, devices=[0, 1, 2])
+    assert m.devices == [] and m.launched_kernels() == [""] * len(m.layers)
+    m.close()
