@@ -532,11 +532,15 @@ def main():
         for L, tms in zip(m.layers, layer_ms):
             if not L["kernel"] or L["kernel"].startswith("none"):
                 continue
-            g = groups.setdefault(L["kernel"], {"ms": 0.0, "bytes": 0, "macs": 0, "launches": 0})
+            # layers that run inside another layer's launch ("(in fused_chain_kernel)") count towards that kernel: its time is recorded on
+            # the first layer of the launch, its algorithmic bytes / MACs are the sum over the layers it executes
+            inside = L["kernel"].startswith("(in ")
+            kname = L["kernel"][4:-1] if inside else L["kernel"]
+            g = groups.setdefault(kname, {"ms": 0.0, "bytes": 0, "macs": 0, "launches": 0})
             g["ms"] += float(tms)
             g["bytes"] += (L["bytes"] - L["weight_bytes"]) * batch * args.steps + L["weight_bytes"] * args.steps
             g["macs"] += L["macs"] * batch * args.steps
-            g["launches"] += 1
+            g["launches"] += 0 if inside else 1
         total_layer_ms = sum(g["ms"] for g in groups.values()) or 1.0
         dom_name, dom = max(groups.items(), key=lambda kv: kv[1]["ms"])
         achieved = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9

@@ -212,6 +212,12 @@ typedef struct mf_conv_desc {          /* microflow::ops::conv_2d / depthwise_co
 } mf_conv_desc;
 int mf_op_conv_2d(const mf_conv_desc *d, const void *in, void *out, size_t batch);
 
+/* a straight-line sequence of conv_2d / depthwise_conv_2d operators (the chain the macro emits, microflow-macros/src/lib.rs:198-201,
+ * restricted to convolutions): op k consumes op k-1's output.  fuse = 0: one kernel per operator.  fuse = 1: the sequence must be
+ * n x [depthwise 3x3 / stride 1 / SAME, 128 channels] -> [1x1 conv, 128 -> 128] on a feature map of <= 128 pixels and runs as ONE
+ * launch of the fused low-resolution stage kernel (activations stay in shared memory); anything else: MF_ERR_UNSUPPORTED_SHAPE. */
+int mf_op_conv_chain(const mf_conv_desc *ops, int n_ops, const void *in, void *out, size_t batch, int fuse);
+
 /* persistent form of the same operator: plan once (weights/constants uploaded, kernel selected), then run on
  * DEVICE-resident NHWC buffers (32-byte aligned, as cudaMalloc returns them), asynchronously on `stream` (cudaStream_t).  Used by pipelines and by bench.py's
  * BASELINE config 5 (synthetic 224x224x128->128 Conv2D roofline). */

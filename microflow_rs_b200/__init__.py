@@ -95,7 +95,7 @@ ABI_SYMBOLS = [
     "mf_predict", "mf_predict_quantized", "mf_predict_many", "mf_predict_many_quantized", "mf_predict_many_quantized_async", "mf_predict_many_logits", "mf_predict_many_device",
     "mf_predict_trace", "mf_model_synchronize", "mf_model_set_profiling", "mf_model_layer_times_ms", "mf_model_launch_count", "mf_model_blob",
     "mf_host_alloc", "mf_host_free", "mf_op_conv_2d", "mf_op_conv_2d_create", "mf_op_run_device", "mf_op_kernel_name", "mf_op_destroy", "mf_op_fully_connected", "mf_op_average_pool_2d", "mf_op_softmax", "mf_op_quantize",
-    "mf_op_dequantize", "mf_op_layout_transpose", "mf_model_layer_launched", "mf_model_devices", "mf_model_weight_broadcast", "mf_predict_many_device_on",
+    "mf_op_dequantize", "mf_op_layout_transpose", "mf_model_layer_launched", "mf_model_devices", "mf_model_weight_broadcast", "mf_predict_many_device_on", "mf_op_conv_chain",
 ]
 
 _lib = None
@@ -151,6 +151,7 @@ def lib():
         L.mf_host_free.argtypes = [C.c_void_p]
         L.mf_device_count.argtypes = [C.POINTER(C.c_int)]
         L.mf_op_conv_2d.argtypes = [C.POINTER(_ConvDesc), C.c_void_p, C.c_void_p, C.c_size_t]
+        L.mf_op_conv_chain.argtypes = [C.POINTER(_ConvDesc), C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
         L.mf_op_conv_2d_create.argtypes = [C.POINTER(_ConvDesc), C.POINTER(C.c_void_p)]
         L.mf_op_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.mf_op_kernel_name.argtypes = [C.c_void_p]
@@ -480,6 +481,33 @@ class _Ops:
 
     def depthwise_conv_2d(self, *a, **k):
         return self.conv_2d(*a, depthwise=True, **k)
+
+    def conv_chain(self, x, layers, fuse):
+        """layers: list of dicts with the keyword arguments of conv_2d (in_zp, filters, filter_zp, out_scale, out_zp, act, pad, strides,
+        c0, c1, out_hw, depthwise); op k consumes op k-1's output.  fuse=True: one fused_chain_kernel launch (or MicroflowError 7)."""
+        x = np.ascontiguousarray(x)
+        B, H, W, Cc = x.shape
+        descs = (_ConvDesc * len(layers))()
+        keep = []
+        for i, L in enumerate(layers):
+            filters = np.ascontiguousarray(L["filters"])
+            dw = bool(L.get("depthwise", False))
+            if dw:
+                _, KH, KW, Cout = filters.shape
+            else:
+                Cout, KH, KW, _ = filters.shape
+            fz = np.ascontiguousarray(np.atleast_1d(L["filter_zp"]), np.int32)
+            c0 = np.ascontiguousarray(L["c0"], np.float32)
+            c1 = np.ascontiguousarray(np.atleast_1d(L["c1"]), np.float32)
+            keep += [filters, fz, c0, c1]
+            oh, ow = L["out_hw"]
+            descs[i] = _ConvDesc(_dtype_code(x), int(dw), H, W, Cc, oh, ow, Cout, KH, KW, L["strides"][0], L["strides"][1], PAD[L["pad"]], ACT[L["act"]],
+                                 int(L["in_zp"]), np.float32(L["out_scale"]), int(L["out_zp"]), filters.ctypes.data, fz.ctypes.data, len(fz),
+                                 c0.ctypes.data, c1.ctypes.data, len(c1), 0)
+            H, W, Cc = oh, ow, Cout
+        out = np.zeros((B, H, W, Cc), x.dtype)
+        self._done(lib().mf_op_conv_chain(descs, len(layers), x.ctypes.data, out.ctypes.data, B, int(bool(fuse))))
+        return out
 
     def fully_connected(self, x, w_nk, w_zp, out_scale, out_zp, act, c0, c1, c2, c3, impl=0):
         x = np.ascontiguousarray(x)

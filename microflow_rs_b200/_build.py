@@ -7,7 +7,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libmicroflow_cuda.so"
-SOURCES = ["mf_loader.cpp", "mf_kernels.cu", "mf_conv_tc.cu", "mf_engine.cu", "mf_api.cu"]
+SOURCES = ["mf_loader.cpp", "mf_kernels.cu", "mf_conv_tc.cu", "mf_fused.cu", "mf_engine.cu", "mf_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",                                  # never contract the f32 epilogue into FMAs

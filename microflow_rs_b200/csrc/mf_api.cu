@@ -22,6 +22,7 @@
 
 #include "../../include/microflow_cuda.h"
 #include "mf_engine.h"
+#include "mf_fused.h"
 
 using namespace mf;
 
@@ -104,6 +105,13 @@ class Worker {
     std::thread th_;
 };
 
+// a fused low-resolution chain (mf_fused.h): layers [first .. last] = n_pairs x (depthwise 3x3 s1, pointwise 1x1) in one launch
+struct Chain {
+    int first = -1, last = -1;
+    FusedChainPlan plan;
+    size_t o_wimg = SIZE_MAX, o_consts = SIZE_MAX;
+};
+
 }  // namespace
 
 struct mf_model {
@@ -139,6 +147,8 @@ struct mf_model {
     TailArgs tail;
     // fully_connected (fc_warp_kernel) -> reshape* -> softmax (last layer) as one launch: layers [fc_tail_first .. fc_tail_last]
     int fc_tail_first = -1, fc_tail_last = -1;
+    // fused low-resolution chains (mf_fused.h): layers [first .. last] = n_pairs x (depthwise 3x3 s1, pointwise 1x1) in one launch
+    std::vector<Chain> chains;
     size_t slot_rr = 0;                     // round-robin position of the host-path stream slots
     cudaEvent_t split_ev[3] = {nullptr, nullptr, nullptr};   // MF_SPLIT=2: fork / join events of the two half-batch streams
     // Small host-path calls (n <= kGraphMaxN, the reference's one-sample predict() above all) replay a captured CUDA graph:
@@ -244,6 +254,25 @@ int run_chunk(mf_model *m, Slot &s, const uint8_t *d_in, size_t n, float *d_out_
     if (prof) MF_CUDA(cudaEventRecord(prof[0], st));
     for (size_t i = 0; i < m->layers.size(); ++i) {
         const LayerExec &L = m->layers[i];
+        const Chain *chain = nullptr;
+        if (!layer_outs_host)
+            for (const auto &c : m->chains)
+                if (c.first == (int)i) chain = &c;
+        if (chain) {                                            // n x (depthwise 3x3 + pointwise 1x1) on a small feature map in one launch
+            uint8_t *dst = s.act[flip];
+            cudaError_t e = fused_chain_launch(chain->plan, cur, dst, (long long)n, m->num_sms, st, pdl);
+            if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("fused_chain_kernel launch failed: ") + cudaGetErrorString(e));
+            m->launches += 1;
+            m->launched[i] = "fused_chain_kernel";
+            for (size_t k = i + 1; k <= (size_t)chain->last; ++k) m->launched[k] = "";
+            pdl = use_pdl;
+            cur = dst;
+            flip ^= 1;
+            if (prof)
+                for (size_t k = i; k <= (size_t)chain->last; ++k) MF_CUDA(cudaEventRecord(prof[k + 1], st));
+            i = (size_t)chain->last;
+            continue;
+        }
         if ((int)i == m->tail_first && !layer_outs_host) {      // pool + conv + softmax in one launch
             TailArgs t = m->tail;
             t.in = cur; t.out = s.act[flip]; t.logits = d_logits; t.batch = (long long)n; t.pdl = pdl;
@@ -352,6 +381,80 @@ void plan_fc_tail(mf_model *m) {
     if (m->layers[(size_t)n - 1].kernel != Kernel::Softmax || sa.rows * sa.cols != m->layers[(size_t)j].fc.N) return;
     m->fc_tail_first = j;
     m->fc_tail_last = n - 1;
+}
+
+// Recognises runs of [depthwise_conv_2d 3x3 / s1 / SAME, 128 ch] -> [conv_2d 1x1, 128 -> 128] on one small feature map (both on
+// their fast kernels: int8, weight zero-points 0, accumulators within 2^22) and packs their static data for fused_chain_kernel.
+void plan_chains(const std::vector<LayerExec> &layers, BlobBuilder &bb, std::vector<Chain> &chains) {
+    const int n = (int)layers.size();
+    auto is_dw = [&](int i, int H, int W) {
+        const LayerExec &E = layers[(size_t)i];
+        const LayerSpec &L = E.spec;
+        return E.kernel == Kernel::DwConv3x3Rows && !E.big_acc && !L.is_u8 && L.Cin == kFusedC && L.Cout == kFusedC && L.KH == 3 && L.KW == 3 && L.sh == 1 &&
+               L.sw == 1 && L.pad == MF_PAD_SAME && L.H == H && L.W == W && L.OH == H && L.OW == W;
+    };
+    auto is_pw = [&](int i, int H, int W) {
+        const LayerExec &E = layers[(size_t)i];
+        const LayerSpec &L = E.spec;
+        return E.kernel == Kernel::ConvTcPointwise && !E.big_acc && !L.is_u8 && L.Cin == kFusedC && L.Cout == kFusedC && L.H == H && L.W == W;
+    };
+    for (int i = 0; i + 1 < n;) {
+        const LayerSpec &L0 = layers[(size_t)i].spec;
+        const int H = L0.H, W = L0.W;
+        int pairs = 0;
+        while (i + 2 * pairs + 1 < n && pairs < kFusedMaxPairs && is_dw(i + 2 * pairs, H, W) && is_pw(i + 2 * pairs + 1, H, W) &&
+               fused_chain_smem(pairs + 1, H, W) != 0)
+            ++pairs;
+        if (pairs < 2) { ++i; continue; }          // a single pair gains nothing over its two kernels
+        Chain c;
+        c.first = i; c.last = i + 2 * pairs - 1;
+        c.plan.n_pairs = pairs; c.plan.H = H; c.plan.W = W;
+        std::vector<uint8_t> wimg((size_t)pairs * 128 * 128), consts((size_t)pairs * kFusedConstBytes);
+        for (int l = 0; l < pairs; ++l) {
+            const LayerSpec &D = layers[(size_t)(i + 2 * l)].spec, &P = layers[(size_t)(i + 2 * l + 1)].spec;
+            auto consts_of = [](const LayerSpec &S, std::vector<float> &c0z, std::vector<float> &c1, std::vector<int32_t> &kcorr, bool dw) {
+                c0z.resize(128); c1.resize(128); kcorr.assign(128, 0);
+                for (int b = 0; b < 128; ++b) {
+                    c0z[(size_t)b] = (float)S.out_zp + S.c0[(size_t)b];                     // conv_2d.rs:94-95: the same single f32 add
+                    c1[(size_t)b] = S.c1[(size_t)b < S.c1.size() ? (size_t)b : 0];
+                    int32_t sum = 0;
+                    if (dw) for (int t = 0; t < 9; ++t) sum += (int8_t)S.w[(size_t)t * 128 + b];
+                    else for (int k = 0; k < 128; ++k) sum += (int8_t)S.w[(size_t)b * 128 + k];
+                    kcorr[(size_t)b] = S.in_zp * sum;
+                }
+            };
+            std::vector<float> dz, d1, pz, p1;
+            std::vector<int32_t> dk, pk;
+            consts_of(D, dz, d1, dk, true);
+            consts_of(P, pz, p1, pk, false);
+            fused_pack_pointwise_image(P.w.data(), wimg.data() + (size_t)l * 128 * 128);
+            fused_pack_consts(D.w.data(), dz.data(), d1.data(), pz.data(), p1.data(), pk.data(), consts.data() + (size_t)l * kFusedConstBytes);
+            c.plan.dw_zp[l] = D.in_zp;
+            c.plan.dw_lo[l] = (float)D.act_lo; c.plan.dw_hi[l] = (float)D.act_hi;
+            c.plan.pw_lo[l] = (float)P.act_lo; c.plan.pw_hi[l] = (float)P.act_hi;
+        }
+        std::string why;
+        if (!fused_chain_finalize(c.plan, &why)) { ++i; continue; }
+        c.o_wimg = bb.add(wimg.data(), wimg.size());
+        c.o_consts = bb.add(consts.data(), consts.size());
+        chains.push_back(c);
+        i = c.last + 1;
+    }
+}
+
+// after LayerExec::resolve: a layer that resolve() downgraded breaks its chain (it then runs layer by layer)
+void resolve_chains(const std::vector<LayerExec> &layers, std::vector<Chain> &chains, const uint8_t *d_blob) {
+    for (auto it = chains.begin(); it != chains.end();) {
+        bool ok = true;
+        for (int k = it->first; k <= it->last; ++k) {
+            const Kernel want = ((k - it->first) & 1) ? Kernel::ConvTcPointwise : Kernel::DwConv3x3Rows;
+            ok = ok && layers[(size_t)k].kernel == want;
+        }
+        if (!ok) { it = chains.erase(it); continue; }
+        it->plan.d_wimg = d_blob + it->o_wimg;
+        it->plan.d_consts = d_blob + it->o_consts;
+        ++it;
+    }
 }
 
 int need_device(const mf_model *m) {
@@ -554,6 +657,7 @@ int create_single(const uint8_t *buf, size_t len, const mf_options &o, bool uplo
             if (m->spec.layers[i].op == MF_OP_SOFTMAX) m->softmax_tail = (int)i;
             break;
         }
+    if (have_device && impl == 0 && !std::getenv("MF_NO_CHAIN_FUSE")) plan_chains(m->layers, bb, m->chains);
     m->blob_bytes = bb.bytes().size();
     m->launched.assign(m->layers.size(), "");
     if (have_device) {
@@ -565,6 +669,7 @@ int create_single(const uint8_t *buf, size_t len, const mf_options &o, bool uplo
         }
         for (auto &L : m->layers)
             if (!L.resolve(m->d_blob, &err)) return fail(MF_ERR_CUDA, err);
+        resolve_chains(m->layers, m->chains, m->d_blob);
         if (impl != 1 && !std::getenv("MF_NO_TAIL_FUSE")) { plan_tail(m.get()); plan_fc_tail(m.get()); }
         for (int k = 0; k < 2; ++k) {
             rc = alloc_slot(m.get(), m->slot[k]);
@@ -616,10 +721,10 @@ int broadcast_blob(mf_model *g) {
     for (size_t r = 0; r < G; ++r)
         for (size_t q = 0; q < r; ++q) distinct = distinct && g->replicas[r]->device != g->replicas[q]->device;
     if (nc.ok && distinct) {
-        std::vector<void *> comms(G, nullptr);
-        std::vector<int> devs(G);
+        void *comms[MF_MAX_DEVICES] = {};
+        int devs[MF_MAX_DEVICES] = {};
         for (size_t r = 0; r < G; ++r) devs[r] = g->replicas[r]->device;
-        bool ok = nc.comm_init_all(comms.data(), (int)G, devs.data()) == 0;
+        bool ok = nc.comm_init_all(comms, (int)G, devs) == 0;
         if (ok) {
             ok = nc.group_start() == 0;
             for (size_t r = 0; ok && r < G; ++r) {
@@ -840,6 +945,8 @@ int mf_model_layer_info(const mf_model *m, int i, mf_layer_info *o) {
     if (m->tail_first >= 0 && i >= m->tail_first && i <= m->tail_last && E.kernel != Kernel::None)
         kn = i == m->tail_first ? "tail_fused_kernel" : "(in tail_fused_kernel)";
     if (m->fc_tail_first >= 0 && i > m->fc_tail_first && i <= m->fc_tail_last && E.kernel != Kernel::None) kn = "(in fc_warp_kernel)";
+    for (const auto &c : m->chains)
+        if (i >= c.first && i <= c.last) kn = i == c.first ? "fused_chain_kernel" : "(in fused_chain_kernel)";
     std::snprintf(o->kernel, sizeof o->kernel, "%s", kn);
     return MF_OK;
 }
@@ -1154,6 +1261,67 @@ int mf_op_conv_2d(const mf_conv_desc *d, const void *in, void *out, size_t batch
     int rc = conv_spec_from_desc(d, L);
     if (rc) return rc;
     return run_single_layer(L, d->impl, in, out, batch);
+}
+
+// A sequence of conv_2d / depthwise_conv_2d operators, each consuming the previous one's output -- the straight-line chain the
+// macro emits (microflow-macros/src/lib.rs:198-201) restricted to convolutions.  fuse = 0: one kernel per operator;
+// fuse = 1: the whole sequence must be taken by ONE fused_chain_kernel launch (mf_fused.h), else MF_ERR_UNSUPPORTED_SHAPE.
+int mf_op_conv_chain(const mf_conv_desc *descs, int n_ops, const void *in, void *out, size_t batch, int fuse) {
+    int rc = check_device(nullptr);
+    if (rc) return rc;
+    if (!descs || n_ops < 1 || !in || !out) return fail(MF_ERR_INVALID_ARG, "null or empty operator list");
+    cudaDeviceProp prop{};
+    int dev = 0;
+    MF_CUDA(cudaGetDevice(&dev));
+    MF_CUDA(cudaGetDeviceProperties(&prop, dev));
+    std::vector<LayerExec> layers((size_t)n_ops);
+    BlobBuilder bb;
+    size_t max_elems = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        rc = conv_spec_from_desc(&descs[i], layers[(size_t)i].spec);
+        if (rc) return rc;
+        if (i && layers[(size_t)i].spec.in_elems != layers[(size_t)i - 1].spec.out_elems) return fail(MF_ERR_UNSUPPORTED_SHAPE, "operator input does not match the previous output");
+        layers[(size_t)i].plan(bb, 0, true);
+        max_elems = std::max(max_elems, std::max(layers[(size_t)i].spec.in_elems, layers[(size_t)i].spec.out_elems));
+    }
+    std::vector<Chain> chains;
+    if (fuse) plan_chains(layers, bb, chains);
+    uint8_t *d_blob = nullptr, *d_a = nullptr, *d_b = nullptr;
+    auto cleanup = [&] { cudaFree(d_blob); cudaFree(d_a); cudaFree(d_b); };
+    cudaError_t e = cudaSuccess;
+    std::string err, names;
+    do {
+        if ((e = cudaMalloc(&d_blob, bb.bytes().size() + 256)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(d_blob, bb.bytes().data(), bb.bytes().size(), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        for (auto &L : layers) L.resolve(d_blob, &err);
+        resolve_chains(layers, chains, d_blob);
+        if (fuse && (chains.size() != 1 || chains[0].first != 0 || chains[0].last != n_ops - 1)) {
+            cleanup();
+            return fail(MF_ERR_UNSUPPORTED_SHAPE, "the operator sequence is not one fusable chain of (depthwise 3x3 s1 SAME, 128 ch) -> (1x1 conv, 128 -> 128) pairs");
+        }
+        if ((e = cudaMalloc(&d_a, batch * max_elems + 256)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_b, batch * max_elems + 256)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(d_a, in, batch * layers[0].spec.in_elems, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        uint8_t *cur = d_a, *nxt = d_b;
+        if (fuse) {
+            e = fused_chain_launch(chains[0].plan, cur, nxt, (long long)batch, prop.multiProcessorCount, nullptr, 0);
+            names = "fused_chain_kernel";
+            std::swap(cur, nxt);
+        } else {
+            for (auto &L : layers) {
+                if ((e = L.run(cur, nxt, (long long)batch, prop.multiProcessorCount, nullptr, &err)) != cudaSuccess) break;
+                names += std::string(names.empty() ? "" : ",") + L.launched_name(cur, nxt, (long long)batch);
+                std::swap(cur, nxt);
+            }
+        }
+        if (e != cudaSuccess) break;
+        if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
+        e = cudaMemcpy(out, cur, batch * layers.back().spec.out_elems, cudaMemcpyDeviceToHost);
+    } while (false);
+    cleanup();
+    if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string("conv chain: ") + cudaGetErrorString(e) + " " + err);
+    g_err = names;   // lets tests see which kernels ran
+    return MF_OK;
 }
 
 // ---- persistent operator object: plan once, run on device-resident buffers (benchmarks, pipelines) ----------------

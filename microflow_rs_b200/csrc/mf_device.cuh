@@ -140,4 +140,34 @@ template <int K> __device__ __forceinline__ int sx8(uint32_t w) {
     return r;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// byte shuffles of the depthwise kernels (mf_kernels.cu, mf_fused.cu)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <uint32_t SEL> __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "n"(SEL));
+    return r;
+}
+// four words (one per column, 4 channels each; the 4th is ignored) -> per-channel (col0, col1, col2, don't-care) registers
+__device__ __forceinline__ void transpose_3x4(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t (&t)[4]) {
+    const uint32_t lo = prmt<0x5140>(v0, v1), hi = prmt<0x7362>(v0, v1);   // (v0.0 v1.0 v0.1 v1.1), (v0.2 v1.2 v0.3 v1.3)
+    t[0] = prmt<0x4410>(lo, v2);
+    t[1] = prmt<0x5532>(lo, v2);
+    t[2] = prmt<0x6610>(hi, v2);
+    t[3] = prmt<0x7732>(hi, v2);
+}
+__device__ __forceinline__ void transpose_4x4(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t (&t)[4]) {
+    const uint32_t lo01 = prmt<0x5140>(v0, v1), hi01 = prmt<0x7362>(v0, v1);
+    const uint32_t lo23 = prmt<0x5140>(v2, v3), hi23 = prmt<0x7362>(v2, v3);
+    t[0] = prmt<0x5410>(lo01, lo23);
+    t[1] = prmt<0x7632>(lo01, lo23);
+    t[2] = prmt<0x5410>(hi01, hi23);
+    t[3] = prmt<0x7632>(hi01, hi23);
+}
+
 }  // namespace mf

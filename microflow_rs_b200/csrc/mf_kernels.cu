@@ -434,24 +434,6 @@ __device__ __forceinline__ void sm_mbar_wait(uint32_t bar, uint32_t parity) {
 // Borders cost nothing in the row loop: each ring slot is [one row of in_zp][the sample][one row of in_zp], so rows -1 and
 // H are ordinary loads, a window column outside the image reads a zero-point word through a pointer whose per-row stride
 // is 0, and the accumulators start at -in_zp * sum(w).
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-template <uint32_t SEL> __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "n"(SEL));
-    return r;
-}
-// four words (one per column, 4 channels each; the 4th is ignored) -> per-channel (col0, col1, col2, don't-care) registers
-__device__ __forceinline__ void transpose_3x4(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t (&t)[4]) {
-    const uint32_t lo = prmt<0x5140>(v0, v1), hi = prmt<0x7362>(v0, v1);   // (v0.0 v1.0 v0.1 v1.1), (v0.2 v1.2 v0.3 v1.3)
-    t[0] = prmt<0x4410>(lo, v2);
-    t[1] = prmt<0x5532>(lo, v2);
-    t[2] = prmt<0x6610>(hi, v2);
-    t[3] = prmt<0x7732>(hi, v2);
-}
 // Slot layout (kDwHead bytes of header, then nbuf slots of buf_stride bytes, then kDwTail bytes):
 //   header: nbuf "sample landed" mbarriers at +0, nbuf "warps finished with this slot" counters at +64
 //   slot:   [one row of in_zp][the sample, filled by one cp.async.bulk][one row of in_zp]
@@ -617,14 +599,6 @@ __global__ void __launch_bounds__(kDwSmemThreads, MINB) dwconv3x3_smem_kernel(Co
 // border handling (zeroed weight bytes + per-thread correction) and epilogue as dwconv3x3_smem_kernel; CTAs are 96 or 128
 // threads (one strip of a 192-word-wide row is 96 pairs), 5 per SM.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void transpose_4x4(uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3, uint32_t (&t)[4]) {
-    const uint32_t lo01 = prmt<0x5140>(v0, v1), hi01 = prmt<0x7362>(v0, v1);
-    const uint32_t lo23 = prmt<0x5140>(v2, v3), hi23 = prmt<0x7362>(v2, v3);
-    t[0] = prmt<0x5410>(lo01, lo23);
-    t[1] = prmt<0x7632>(lo01, lo23);
-    t[2] = prmt<0x5410>(hi01, hi23);
-    t[3] = prmt<0x7632>(hi01, hi23);
-}
 constexpr int kDwPairMaxThreads = 128;
 template <bool FULL, int MINB>
 __global__ void __launch_bounds__(kDwPairMaxThreads, MINB) dwconv3x3_pair_kernel(ConvArgs a, uint32_t in_bytes, uint32_t buf_stride, int nbuf, int xwp, int nstrip,

@@ -10,6 +10,7 @@ if has tests; then
   timeout 500 python -m pytest tests/test_gpu_tc.py -q -m gpu 2>&1 | tail -25 > gpurun_out/t_tc.log
   timeout 700 python -m pytest tests/test_gpu_ops.py -q -m gpu 2>&1 | tail -40 > gpurun_out/t_ops.log
   timeout 900 python -m pytest tests/test_gpu_models.py -q -m gpu 2>&1 | tail -60 > gpurun_out/t_models.log
+  timeout 300 python -m pytest tests/test_gpu_multidevice.py -q -m gpu 2>&1 | tail -20 > gpurun_out/t_multi.log
   timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 fi
 if has bench; then
@@ -35,7 +36,7 @@ if has prof; then
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 5 -c 1 -f -o gpurun_out/prof_conv3x3 \
       python -m microflow_rs_b200._convbench 16 4 > gpurun_out/ncu_conv3x3.log 2>&1
 fi
-tail -n 4 gpurun_out/t_tc.log gpurun_out/t_ops.log gpurun_out/t_models.log gpurun_out/smoke.log 2>/dev/null
+tail -n 4 gpurun_out/t_tc.log gpurun_out/t_ops.log gpurun_out/t_models.log gpurun_out/t_multi.log gpurun_out/smoke.log 2>/dev/null
 for f in gpurun_out/bench_pd.json gpurun_out/bench_speech.json gpurun_out/bench_pd_chunk*.json gpurun_out/bench_ref.json; do
   [ -f "$f" ] && python - "$f" <<'PY'
 import json, sys
