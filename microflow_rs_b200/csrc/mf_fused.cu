@@ -2,7 +2,8 @@
 // pairs in ONE persistent kernel (see mf_fused.h for the why; reference chain:
 // microflow-macros/src/lib.rs:198-201, per-op semantics src/ops/depthwise_conv_2d.rs:56-101, conv_2d.rs:56-104).
 //
-// One CTA per SM, 512 threads = 2 TEAMS of 8 warps.  A team owns a UNIT of U samples (U * H * W <= 256 pixel rows) and takes it
+// One CTA per SM, 768 threads = 2 TEAMS of 12 warps (<= 80 registers per thread; with 8-warp teams the kernel sat at 62 % issue
+// utilisation on fixed-latency dependency stalls, profiles/r02a_fused_chain_v1.txt).  A team owns a UNIT of U samples (U * H * W <= 256 pixel rows) and takes it
 // through every layer of the chain without leaving the SM; the two teams run on different units, unsynchronised, so one team's
 // tensor-core latency and barrier waits are filled with the other's CUDA-core work.
 //
@@ -21,7 +22,7 @@
 //                kernel rows, pre-biased accumulators and the packed exact f32 epilogue of dwconv3x3_pair_kernel (mf_kernels.cu);
 //                rows -1 and H and window columns outside the image are the input zero-point (so kcorr = in_zp * sum(w) is uniform)
 //   pointwise    fence.proxy.async + team barrier; one thread issues 4 x tcgen05.mma (K = 32 each) per 128-row tile, commit -> mbarrier
-//   epilogue     warp = (TMEM lane quarter, tile): tcgen05.ld 32 lanes x 32 columns, requant4_biased with the pair's tables (broadcast
+//   epilogue     the three warps of a TMEM lane quarter share its (tile, 32-column chunk) jobs: tcgen05.ld 32 lanes x 32 columns, requant4_biased with the pair's tables (broadcast
 //                LDS.128), 16-byte stores into X -- or, for the last pair, 32-byte stores straight to HBM
 #include <cuda_runtime.h>
 
@@ -41,7 +42,7 @@ namespace {
 
 using namespace tcptx;
 
-constexpr int kTeams = 2, kTeamWarps = 8, kTeamThreads = 32 * kTeamWarps, kThreads = kTeams * kTeamThreads;
+constexpr int kTeams = 2;
 constexpr uint32_t kXPitch = 144;                 // bytes per pixel row of X after the first epilogue
 constexpr uint32_t kWImg = 128 * 128;             // one pointwise weight image
 constexpr uint32_t kATeam = 256 * 128;            // A operand of a team: two 128-row tiles
@@ -66,19 +67,20 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatil
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(kTeamThreads) : "memory"); }
+__device__ __forceinline__ void team_sync(int team, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(threads) : "memory"); }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <bool FULL>
-__global__ void __launch_bounds__(kThreads, 1) fused_chain_kernel(const __grid_constant__ FusedParams p) {
+template <bool FULL, int kTeamWarps>
+__global__ void __launch_bounds__(kTeams * 32 * kTeamWarps, 1) fused_chain_kernel(const __grid_constant__ FusedParams p) {
+    constexpr int kTeamThreads = 32 * kTeamWarps;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t s0 = smem_u32(smem);
     if ((s0 & 1023u) != 0) __trap();              // SWIZZLE_128B atoms need a 1024-byte aligned base
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler
-    const int team = warp >> 3, tw = warp & 7, tt = tid & (kTeamThreads - 1);
+    const int team = warp >= kTeamWarps ? 1 : 0, tw = warp - team * kTeamWarps, tt = tid - team * kTeamThreads;
     // barriers: [0] weights landed, [1 + t] unit input landed, [3 + t] tensor core done; TMEM base address behind them
     const uint32_t bar0 = s0 + p.off_bar;
     const uint32_t wbar = bar0, xbar = bar0 + 8u * (1 + team), mbar = bar0 + 8u * (3 + team);
@@ -162,8 +164,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_chain_kernel(const __grid_c
 #pragma unroll
                     for (int c = 0; c < 4; ++c) fresh[c] = kAccBias - zp * wsum[c];     // pre-biased accumulator (mf_device.cuh) minus in_zp * sum(w)
                 }
-                const float4 z = *reinterpret_cast<const float4 *>(cbuf + 9 * 32 + 4 * lane);
-                const float4 sc = *reinterpret_cast<const float4 *>(cbuf + 13 * 32 + 4 * lane);
                 const float lo = p.dw_lo[l], hi = p.dw_hi[l];
                 const int H = p.H, W = p.W;
                 const uint32_t rstep = (uint32_t)W * pitch;
@@ -175,24 +175,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_chain_kernel(const __grid_c
                     // shared address of (input row 0, window column c0); for c0 = -1 one pixel before the sample (never dereferenced)
                     uint32_t xr = sX + (uint32_t)((int)s * p.HW + c0) * pitch + lane4;
                     uint32_t orow = s * (uint32_t)p.HW + (uint32_t)j0;                  // A row of output (0, j0)
-                    int r = -1;
-                    auto take = [&](uint32_t (&t)[4]) {                                 // the next input row, transposed; zero-point outside the image
-                        if ((unsigned)r < (unsigned)H) {
-                            const uint32_t v0 = ok0 ? lds_u32(xr) : zpw;
-                            const uint32_t v1 = lds_u32(xr + pitch);
-                            const uint32_t v2 = ok2 ? lds_u32(xr + 2 * pitch) : zpw;
-                            const uint32_t v3 = ok3 ? lds_u32(xr + 3 * pitch) : zpw;
-                            xr += rstep;
-                            transpose_4x4(v0, v1, v2, v3, t);
-                        } else {
-                            t[0] = t[1] = t[2] = t[3] = zpw;
-                        }
-                        ++r;
+                    auto take = [&](uint32_t (&t)[4]) {                                 // the next input row, transposed; zero-point left / right of the image
+                        const uint32_t v0 = ok0 ? lds_u32(xr) : zpw;
+                        const uint32_t v1 = lds_u32(xr + pitch);
+                        const uint32_t v2 = ok2 ? lds_u32(xr + 2 * pitch) : zpw;
+                        const uint32_t v3 = ok3 ? lds_u32(xr + 3 * pitch) : zpw;
+                        xr += rstep;
+                        transpose_4x4(v0, v1, v2, v3, t);
                     };
                     struct Acc { int a[4], b[4]; };
-                    Acc init;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) { init.a[c] = fresh[c]; init.b[c] = fresh[c]; }
                     auto mac = [&](Acc &A, const uint32_t (&t)[4], int T) {
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
@@ -200,28 +191,41 @@ __global__ void __launch_bounds__(kThreads, 1) fused_chain_kernel(const __grid_c
                             A.b[c] = __dp4a((int)t[c], (int)wb[T][c], A.b[c]);
                         }
                     };
+                    auto open = [&](Acc &A, const uint32_t (&t)[4]) {                    // a new output row: accumulators start at `fresh`, kernel row 0
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            A.a[c] = __dp4a((int)t[c], (int)wa[0][c], fresh[c]);
+                            A.b[c] = __dp4a((int)t[c], (int)wb[0][c], fresh[c]);
+                        }
+                    };
                     auto store = [&](const Acc &A) {                                    // two pixels of the A operand (SWIZZLE_128B: 16-byte chunk ^= row & 7)
+                        const float4 z = *reinterpret_cast<const float4 *>(cbuf + 9 * 32 + 4 * lane);
+                        const float4 sc = *reinterpret_cast<const float4 *>(cbuf + 13 * 32 + 4 * lane);
                         const uint32_t y0 = requant4_biased<FULL>(A.a[0], A.a[1], A.a[2], A.a[3], z, sc, lo, hi);
                         const uint32_t y1 = requant4_biased<FULL>(A.b[0], A.b[1], A.b[2], A.b[3], z, sc, lo, hi);
                         sts_u32(a_lr + orow * 128u + ((a_lq ^ (orow & 7u)) << 4), y0);
                         if (ok2) sts_u32(a_lr + (orow + 1u) * 128u + ((a_lq ^ ((orow + 1u) & 7u)) << 4), y1);
                         orow += (uint32_t)W;
                     };
+                    // rows -1 and H are the zero-point: row -1 is kernel row 0 of output row 0, row H kernel row 2 of output row H - 1
+                    const uint32_t zt[4] = {zpw, zpw, zpw, zpw};
                     uint32_t t[4];
-                    Acc A = init, B = init, C = init;
-                    int left = H;
-                    take(t); mac(A, t, 0);
-                    take(t); mac(A, t, 1); mac(B, t, 0);
-                    while (true) {
-                        take(t); mac(A, t, 2); mac(B, t, 1); C = init; mac(C, t, 0); store(A); if (--left == 0) break;
-                        take(t); mac(B, t, 2); mac(C, t, 1); A = init; mac(A, t, 0); store(B); if (--left == 0) break;
-                        take(t); mac(C, t, 2); mac(A, t, 1); B = init; mac(B, t, 0); store(C); if (--left == 0) break;
+                    Acc A, B, C;
+                    open(A, zt);
+                    take(t); mac(A, t, 1); open(B, t);
+                    int left = H - 1;                                                    // output rows closed by a real input row
+                    while (left > 0) {
+                        take(t); mac(A, t, 2); mac(B, t, 1); open(C, t); store(A); if (--left == 0) { A = B; break; }
+                        take(t); mac(B, t, 2); mac(C, t, 1); open(A, t); store(B); if (--left == 0) { A = C; break; }
+                        take(t); mac(C, t, 2); mac(A, t, 1); open(B, t); store(C); if (--left == 0) break;
                     }
+                    mac(A, zt, 2);                                                       // the last output row: its kernel row 2 lies below the image
+                    store(A);
                 }
             }
             if (tt < kFusedPwWords / 4) reinterpret_cast<uint4 *>(cbuf + kFusedDwWords)[tt] = pwc;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // A was written through the generic proxy, the tensor core reads it through the async one
-            team_sync(team);
+            team_sync(team, kTeamThreads);
 
             // ================= pointwise 1x1: tcgen05.mma, A (smem) x W^T (smem) -> TMEM =================
             if (tt == 0) {
@@ -243,48 +247,47 @@ __global__ void __launch_bounds__(kThreads, 1) fused_chain_kernel(const __grid_c
                 const int ln = last ? 0 : l + 1;
                 if (tt < kFusedDwWords / 4) reinterpret_cast<uint4 *>(cbuf)[tt] = __ldg(reinterpret_cast<const uint4 *>(p.consts + (size_t)ln * kFusedConstBytes) + tt);
             }
-            mbar_wait(mbar, mph);
+            // one warp polls the mbarrier, the others wait at the team barrier (a hardware wait: no issue slots burnt on polling)
+            if (tw == 0) mbar_wait(mbar, mph);
             mph ^= 1u;
+            team_sync(team, kTeamThreads);
             tc_fence_after();
 
             // ================= epilogue: TMEM -> exact f32 requantize -> X (or HBM for the last pair) =================
             {
-                const uint32_t q = (uint32_t)tw & 3u, tile = (uint32_t)tw >> 2;
-                if ((int)tile < ntiles) {
+                const uint32_t q = (uint32_t)tw & 3u;                       // == warp % 4 (teams start at a multiple of 4 warps): the TMEM lane quarter
+                const float *tz = reinterpret_cast<const float *>(cbuf + kFusedDwWords), *ts = tz + 128;
+                const int *tk = reinterpret_cast<const int *>(ts + 128);
+                const float lo = p.pw_lo[l], hi = p.pw_hi[l];
+#pragma unroll 1
+                for (uint32_t job = (uint32_t)tw >> 2; job < (uint32_t)ntiles * 4u; job += kTeamWarps / 4) {
+                    const uint32_t tile = job >> 2, ch = job & 3u;
                     const uint32_t row = tile * 128u + q * 32u + (uint32_t)lane;
                     const bool valid = (int)row < rows;
-                    const uint32_t taddr = tmem_base + (uint32_t)team * 256u + tile * 128u + ((q * 32u) << 16);
-                    const float *tz = reinterpret_cast<const float *>(cbuf + kFusedDwWords), *ts = tz + 128;
-                    const int *tk = reinterpret_cast<const int *>(ts + 128);
-                    const float lo = p.pw_lo[l], hi = p.pw_hi[l];
-                    uint8_t *grow = p.out + ((size_t)first * p.HW + row) * 128u;
-                    const uint32_t xrow = sX + row * kXPitch;
-#pragma unroll 1
-                    for (uint32_t ch = 0; ch < 4; ++ch) {
-                        uint32_t r[32];
-                        tmem_ld32(taddr + ch * 32u, r);
-                        uint32_t w[8];
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + (uint32_t)team * 256u + tile * 128u + ((q * 32u) << 16) + ch * 32u, r);
+                    uint32_t w[8];
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            const float4 zz = *reinterpret_cast<const float4 *>(tz + ch * 32 + 4 * g);
-                            const float4 ss = *reinterpret_cast<const float4 *>(ts + ch * 32 + 4 * g);
-                            const int4 kk = *reinterpret_cast<const int4 *>(tk + ch * 32 + 4 * g);
-                            w[g] = requant4_biased<FULL>((int)r[4 * g] + kk.x, (int)r[4 * g + 1] + kk.y, (int)r[4 * g + 2] + kk.z, (int)r[4 * g + 3] + kk.w, zz, ss, lo, hi);
-                        }
-                        if (last) {
-                            if (valid)
-                                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(grow + ch * 32u), "r"(w[0]), "r"(w[1]), "r"(w[2]),
-                                             "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
-                                             : "memory");
-                        } else if (valid) {
-                            sts_v4(xrow + ch * 32u, w[0], w[1], w[2], w[3]);
-                            sts_v4(xrow + ch * 32u + 16u, w[4], w[5], w[6], w[7]);
-                        }
+                    for (int g = 0; g < 8; ++g) {
+                        const float4 zz = *reinterpret_cast<const float4 *>(tz + ch * 32 + 4 * g);
+                        const float4 ss = *reinterpret_cast<const float4 *>(ts + ch * 32 + 4 * g);
+                        const int4 kk = *reinterpret_cast<const int4 *>(tk + ch * 32 + 4 * g);
+                        w[g] = requant4_biased<FULL>((int)r[4 * g] + kk.x, (int)r[4 * g + 1] + kk.y, (int)r[4 * g + 2] + kk.z, (int)r[4 * g + 3] + kk.w, zz, ss, lo, hi);
+                    }
+                    if (last) {
+                        if (valid)
+                            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p.out + ((size_t)first * p.HW + row) * 128u + ch * 32u),
+                                         "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                                         : "memory");
+                    } else if (valid) {
+                        const uint32_t xrow = sX + row * kXPitch + ch * 32u;
+                        sts_v4(xrow, w[0], w[1], w[2], w[3]);
+                        sts_v4(xrow + 16u, w[4], w[5], w[6], w[7]);
                     }
                 }
             }
             tc_fence_before();
-            team_sync(team);        // X complete for the next depthwise; TMEM and A free for the next pointwise
+            team_sync(team, kTeamThreads);        // X complete for the next depthwise; TMEM and A free for the next pointwise
         }
     }
 
@@ -367,7 +370,11 @@ cudaError_t fused_chain_launch(const FusedChainPlan &pl, const uint8_t *in, uint
         p.dw_lo[l] = pl.dw_lo[l]; p.dw_hi[l] = pl.dw_hi[l]; p.pw_lo[l] = pl.pw_lo[l]; p.pw_hi[l] = pl.pw_hi[l];
     }
     using Fn = void (*)(const FusedParams);
-    Fn fn = pl.full_clamp ? fused_chain_kernel<true> : fused_chain_kernel<false>;
+    // warps per team: 8 (119 registers per thread) or 12 (80); MF_FUSED_TW selects for experiments
+    static const int env_tw = [] { const char *e = std::getenv("MF_FUSED_TW"); return e ? std::atoi(e) : 8; }();
+    const int tw = env_tw == 12 ? 12 : 8;
+    Fn fn = tw == 12 ? (pl.full_clamp ? fused_chain_kernel<true, 12> : fused_chain_kernel<false, 12>)
+                     : (pl.full_clamp ? fused_chain_kernel<true, 8> : fused_chain_kernel<false, 8>);
     static std::mutex mu;
     static std::vector<std::pair<int, Fn>> done;
     {
@@ -385,7 +392,7 @@ cudaError_t fused_chain_launch(const FusedChainPlan &pl, const uint8_t *in, uint
     }
     const long long ctas = (units + kTeams - 1) / kTeams;
     const unsigned grid = (unsigned)(ctas < num_sms ? ctas : num_sms);
-    return launch_pdl(fn, dim3(grid), dim3(kThreads), L.total, s, pdl, p);
+    return launch_pdl(fn, dim3(grid), dim3((unsigned)(kTeams * 32 * tw)), L.total, s, pdl, p);
 }
 
 }  // namespace mf
