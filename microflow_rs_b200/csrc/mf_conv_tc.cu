@@ -400,7 +400,7 @@ std::vector<uint8_t> conv_tc_pack_pointwise(const uint8_t *w, int Cout, int Cin,
     return m;
 }
 
-std::vector<int32_t> conv_tc_border_corr_3x3(const uint8_t *w, int Cout, int Cin, int in_zp, int H, int W) {
+std::vector<int32_t> conv_tc_border_corr_3x3(const uint8_t *w, int Cout, int Cin, int in_zp, int H, int W, bool is_u8) {
     (void)H; (void)W;
     std::vector<int32_t> t((size_t)9 * Cout, 0);
     for (int rcls = 0; rcls < 3; ++rcls)
@@ -412,7 +412,7 @@ std::vector<int32_t> conv_tc_border_corr_3x3(const uint8_t *w, int Cout, int Cin
                     for (int n = 0; n < 3; ++n) {
                         if ((ccls == 0 && n == 0) || (ccls == 2 && n == 2)) continue;
                         const uint8_t *f = w + (((size_t)o * 3 + m) * 3 + n) * Cin;
-                        for (int c = 0; c < Cin; ++c) s += (int8_t)f[c];
+                        for (int c = 0; c < Cin; ++c) s += is_u8 ? (int)f[c] : (int)(int8_t)f[c];
                     }
                 }
                 t[(size_t)(rcls * 3 + ccls) * Cout + o] = in_zp * s;
@@ -490,7 +490,7 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     ConvTcTables tab;
     std::memcpy(tab.c0z, p.h_c0z.data(), (size_t)p.N * 4);
     std::memcpy(tab.c1, p.h_c1.data(), (size_t)p.N * 4);
-    const bool packed_epilogue = p.lo == -128.f && p.hi == 127.f && !p.big_acc;   // == the kernel's XU && !BIG (MF_TC_XUG=0 clears it below)
+    const bool packed_epilogue = p.lo == -128.f && p.hi == 127.f && !p.big_acc && !p.is_u8;   // == the kernel's XU && !BIG (MF_TC_XUG=0 clears it below)
     std::memcpy(tab.corr, p.h_corr.data(), (size_t)p.ncls * p.N * 4);
     k.N = p.N; k.CB = p.CB; k.KH = p.KH; k.KW = p.KW; k.TW = p.TW; k.TH = p.TH;
     k.tw_log2 = 0;
@@ -506,7 +506,9 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     k.lo = p.lo; k.hi = p.hi;
     // instruction descriptor (cute::UMMA::InstrDescriptor): c_format S32 = 2 @4, a/b format INT8 = 1 @7/@10,
     // K-major A and B (bits 15, 16 = 0), n_dim = N >> 3 @17, m_dim = 128 >> 4 @24
-    k.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
+    // (uint8 tensors -- the reference's `T = u8` instantiation, microflow-macros/src/ops/conv_2d.rs:39-46 -- are a/b format 0)
+    const uint32_t fmt = p.is_u8 ? 0u : 1u;
+    k.idesc = (2u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
     k.stage_tx = (uint32_t)((p.TH + p.KH - 1) * box_w * 128);
     k.stage_bytes = p.patch ? ((k.stage_tx + 1023u) & ~1023u) : k.stage_tx;      // every stage base stays 1024-byte aligned (swizzle atom)
     k.patch = p.patch ? 1u : 0u;
@@ -521,7 +523,7 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
 
     // the F2I.S8 / I2F epilogue needs the full int8 clamp range (F2I.S8 saturation is the clamp); MF_TC_XUG=0 forces the XU-free one
     static const int env_xug = [] { const char *e = std::getenv("MF_TC_XUG"); return e ? std::atoi(e) : -1; }();
-    const bool xu = p.lo == -128.f && p.hi == 127.f && env_xug != 0;
+    const bool xu = p.lo == -128.f && p.hi == 127.f && env_xug != 0 && !p.is_u8;   // uint8 outputs take the clamp-based (XU-free) epilogue
     if (xu && packed_epilogue)   // pre-biased accumulators: the table entry is added, not subtracted (conv_tc_kernel, PACKED)
         for (int k = 0; k < p.ncls * p.N; ++k) tab.corr[k] = kAccBias - tab.corr[k];
     const bool linear = p.KH == 1 && p.KW == 1 && p.TW == 128 && p.TH == 1 && l.H == 1 && l.B == 1 && l.OH == 1 && p.ncls == 1 && l.OW < (1ll << 31) - 128;

@@ -46,6 +46,7 @@ struct ConvTcPlan {
     std::vector<int32_t> h_corr;       // [ncls][N]  in_zp * (sum of weights over the taps valid for that border class)
     float lo = -128.f, hi = 127.f;
     bool big_acc = false;              // |acc - corr| may exceed 2^22: use the general exact int->float in the epilogue
+    bool is_u8 = false;                // uint8 activations and weights: unsigned operand formats in the instruction descriptor
     alignas(64) unsigned char tmap_b[128];  // CUtensorMap of the weight matrix
 };
 
@@ -63,7 +64,7 @@ int conv_tc_pick_pack(int Cin, int Cout);
 // builds the block-diagonal weight matrix [P*Cout][P*Cin] from OHWI 1x1 filters [Cout][Cin]
 std::vector<uint8_t> conv_tc_pack_pointwise(const uint8_t *w, int Cout, int Cin, int P);
 // 3x3 border-class table [9][Cout]: class = 3*row_cls + col_cls, cls 0 = first row/col, 1 = interior, 2 = last
-std::vector<int32_t> conv_tc_border_corr_3x3(const uint8_t *w_ohwi, int Cout, int Cin, int in_zp, int H, int W);
+std::vector<int32_t> conv_tc_border_corr_3x3(const uint8_t *w_ohwi, int Cout, int Cin, int in_zp, int H, int W, bool is_u8 = false);
 
 bool conv_tc_available(std::string *why);      // driver entry point for cuTensorMapEncodeTiled present?
 // fills plan.tmap_b / smem_bytes / stages; returns false (with reason) if the shape cannot run on this kernel

@@ -140,6 +140,18 @@ template <int K> __device__ __forceinline__ int sx8(uint32_t w) {
     return r;
 }
 
+// zero-extended byte k of a packed word (uint8 tensors, `T = u8` of the reference's `Quantized` trait, src/quantize.rs:6-7)
+template <int K> __device__ __forceinline__ int zx8(uint32_t w) {
+    int r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0u), "r"((uint32_t)(0x4440 | K)));
+    return r;
+}
+template <bool U8, int K> __device__ __forceinline__ int ext8(uint32_t w) { return U8 ? zx8<K>(w) : sx8<K>(w); }
+// four byte products summed into acc, for int8 or uint8 operands
+template <bool U8> __device__ __forceinline__ int dot4(uint32_t a, uint32_t b, int acc) {
+    return U8 ? (int)__dp4a(a, b, (unsigned)acc) : __dp4a((int)a, (int)b, acc);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // byte shuffles of the depthwise kernels (mf_kernels.cu, mf_fused.cu)
 // ------------------------------------------------------------------------------------------------------------

@@ -66,14 +66,15 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
             else for (size_t k = 0; k < (size_t)taps * L.Cin; ++k) s += elem_i(L.w[(size_t)co * taps * L.Cin + k], L.is_u8);
             kcorr[(size_t)co] = L.in_zp * s;
         }
-        // can the corrected accumulator exceed 2^22 ?  It equals sum_valid (v - in_zp) * w whatever the kernel does with borders
-        // (zero-point padding, zero fill + border-class table, masked weights), and |v - in_zp| <= 255, so 255 * sum |w| bounds
-        // it rigorously.  Beyond 2^22 the kernels take the general exact int -> float conversion instead of the biased one.
+        // can the corrected accumulator exceed 2^22 ?  It equals sum_valid (v - in_zp) * (w - w_zp) whatever the kernel does with
+        // borders (zero-point padding, zero fill + border-class table, masked weights), and |v - in_zp| <= 255, so 255 * sum |w - w_zp|
+        // bounds it rigorously.  Beyond 2^22 the kernels take the general exact int -> float conversion instead of the biased one.
         big_acc = false;
         for (int co = 0; co < Cout; ++co) {
             long long sa = 0;
-            if (dw) for (int t = 0; t < taps; ++t) sa += std::abs(elem_i(L.w[(size_t)t * Cout + co], L.is_u8));
-            else for (size_t k = 0; k < (size_t)taps * L.Cin; ++k) sa += std::abs(elem_i(L.w[(size_t)co * taps * L.Cin + k], L.is_u8));
+            const int fz = wzp[(size_t)co];
+            if (dw) for (int t = 0; t < taps; ++t) sa += std::abs(elem_i(L.w[(size_t)t * Cout + co], L.is_u8) - fz);
+            else for (size_t k = 0; k < (size_t)taps * L.Cin; ++k) sa += std::abs(elem_i(L.w[(size_t)co * taps * L.Cin + k], L.is_u8) - fz);
             if (sa * 255 > (1ll << 22)) big_acc = true;
         }
         o_w = bb.add(L.w.data(), L.w.size());
@@ -87,7 +88,21 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
         const bool wz0 = std::all_of(L.w_zp.begin(), L.w_zp.end(), [](int32_t z) { return z == 0; });
         kernel = Kernel::ConvGeneric;
         if (impl == 1) { why_not_fast = "generic kernels forced"; return; }
-        if (L.is_u8 || !wz0) { why_not_fast = "uint8 or non-zero weight zero-point: generic kernel"; return; }
+        if (L.is_u8 || !wz0) {
+            // `T = u8` (microflow-macros/src/ops/conv_2d.rs:39-46) and general weight zero-points (the view-sum term, src/ops/conv_2d.rs:74-76,
+            // depthwise_conv_2d.rs:71-73): the SIMT fast kernels that implement the full formula, or -- uint8 with weight zero-points 0 --
+            // the tcgen05 path below with unsigned operand formats
+            if (dw) {
+                if (!big_acc && L.Cin == L.Cout && L.Cout % 4 == 0) kernel = Kernel::DwConvC4;
+                else why_not_fast = "uint8 / weight zero-point depthwise shape not covered by the fast kernel";
+                return;
+            }
+            if (!wz0) {
+                if (L.KH == 1 && L.KW == 1 && L.Cin % 4 == 0) kernel = Kernel::PwConvDp4a;
+                else why_not_fast = "non-zero weight zero-point on a KxK convolution: generic kernel";
+                return;
+            }
+        }
         if (dw) {
             if (big_acc) why_not_fast = "accumulator range beyond 2^22: generic kernel";
             else if (L.Cin == L.Cout && L.Cout % 4 == 0)
@@ -106,7 +121,7 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
                     tc_P = P;
                     tc.P = P; tc.N = P * L.Cout; tc.Cout = L.Cout; tc.C = P * L.Cin; tc.CB = tc.C / 128;
                     tc.KH = tc.KW = 1; tc.TW = 128; tc.TH = 1; tc.off_r = tc.off_c = 0; tc.ncls = 1;
-                    tc.lo = (float)L.act_lo; tc.hi = (float)L.act_hi; tc.big_acc = big_acc;
+                    tc.lo = (float)L.act_lo; tc.hi = (float)L.act_hi; tc.big_acc = big_acc; tc.is_u8 = L.is_u8;
                     std::vector<uint8_t> wm = conv_tc_pack_pointwise(L.w.data(), L.Cout, L.Cin, P);
                     std::vector<float> ez((size_t)tc.N), es((size_t)tc.N);
                     std::vector<int32_t> ec((size_t)tc.N);
@@ -133,8 +148,8 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
                     static const bool env_patch = [] { const char *e = std::getenv("MF_TC_PATCH"); return !e || std::atoi(e) != 0; }();
                     if (env_patch) { tc.patch = true; tc.TW = 8; tc.TH = 16; }
                 }
-                tc.lo = (float)L.act_lo; tc.hi = (float)L.act_hi; tc.big_acc = big_acc;
-                std::vector<int32_t> corr = conv_tc_border_corr_3x3(L.w.data(), L.Cout, L.Cin, L.in_zp, L.H, L.W);
+                tc.lo = (float)L.act_lo; tc.hi = (float)L.act_hi; tc.big_acc = big_acc; tc.is_u8 = L.is_u8;
+                std::vector<int32_t> corr = conv_tc_border_corr_3x3(L.w.data(), L.Cout, L.Cin, L.in_zp, L.H, L.W, L.is_u8);
                 o_tc_w = o_w;  // OHWI is already the [N][K_total] matrix
                 tc.h_c0z = c0z; tc.h_c1 = c1; tc.h_corr = corr;
                 kernel = Kernel::ConvTc3x3;
@@ -157,15 +172,15 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
         alg_bytes += weight_bytes;
         kernel = Kernel::FcGeneric;
         if (impl == 1) return;
-        if (!L.is_u8 && L.Cin % 16 == 0 && L.Cout <= 8) { kernel = Kernel::FcWarp; return; }
+        if (L.Cin % 16 == 0 && L.Cout <= 8) { kernel = Kernel::FcWarp; return; }     // int8 or uint8, any weight zero-point (row-sum term)
         // FullyConnected as the same tcgen05 GEMM as the pointwise convs: row = one sample (K bytes, K % 128 == 0), B = W [N][K].
         // With w_zp == 0 the reference's accumulator x.W - w_zp*rowsum - c2[j] + c3 (fully_connected.rs:71) is acc - c2[j]
         // (c3 = K*in_zp*w_zp = 0), i.e. exactly the conv epilogue with kcorr = c2; c1 is per-tensor and replicated.
-        if (impl == 0 && have_device && !L.is_u8 && L.w_zp[0] == 0 && L.c3 == 0 && L.Cin % 128 == 0 && L.Cout % 32 == 0 && L.Cout <= 256) {
+        if (impl == 0 && have_device && L.w_zp[0] == 0 && L.c3 == 0 && L.Cin % 128 == 0 && L.Cout % 32 == 0 && L.Cout <= 256) {
             long long big = 0;
             for (int j = 0; j < L.Cout; ++j) {
                 long long sa = 0;
-                for (int k = 0; k < L.Cin; ++k) sa += std::abs(elem_i(L.w[(size_t)j * L.Cin + k], false));
+                for (int k = 0; k < L.Cin; ++k) sa += std::abs(elem_i(L.w[(size_t)j * L.Cin + k], L.is_u8));
                 big = std::max(big, sa * 255);     // acc - c2[j] = sum (x - in_zp) * w  (w_zp == 0)
             }
             big_acc = big > (1ll << 22);
@@ -173,7 +188,7 @@ void LayerExec::plan(BlobBuilder &bb, int impl, bool have_device) {
             tc_P = 1;
             tc.P = 1; tc.N = L.Cout; tc.Cout = L.Cout; tc.C = L.Cin; tc.CB = L.Cin / 128;
             tc.KH = tc.KW = 1; tc.TW = 128; tc.TH = 1; tc.off_r = tc.off_c = 0; tc.ncls = 1;
-            tc.lo = (float)L.act_lo; tc.hi = (float)L.act_hi; tc.big_acc = big_acc;
+            tc.lo = (float)L.act_lo; tc.hi = (float)L.act_hi; tc.big_acc = big_acc; tc.is_u8 = L.is_u8;
             tc.h_c0z = c0z;
             tc.h_c1.assign((size_t)L.Cout, L.c1[0]);
             tc.h_corr = L.c2;
@@ -206,11 +221,13 @@ bool LayerExec::resolve(const uint8_t *d, std::string *err) {
         a.off_c = L.pad == MF_PAD_SAME ? (L.KW - 1) / 2 : 0;
         a.in_zp = L.in_zp; a.lo = (float)L.act_lo; a.hi = (float)L.act_hi; a.is_u8 = L.is_u8; a.depthwise = L.op == MF_OP_DEPTHWISE_CONV_2D;
         a.big_acc = big_acc;
+        a.wzp_nonzero = !std::all_of(L.w_zp.begin(), L.w_zp.end(), [](int32_t z) { return z == 0; });
         // plan() chose from the LayerSpec alone; the launch-side predicates (alignment, shared-memory budget, window geometry)
         // have the last word, so a shape they refuse runs on the generic kernel instead of failing at launch
         if (kernel == Kernel::PwConvDp4a && !pwconv_dp4a_eligible(a)) { kernel = Kernel::ConvGeneric; why_not_fast = "1x1 conv reads outside the input: generic kernel"; }
         if (kernel == Kernel::DwConvCin1 && !dwconv_cin1_eligible(a)) { kernel = Kernel::ConvGeneric; why_not_fast = "Cin=1 depthwise kernel too large for the fast kernel"; }
-        if ((kernel == Kernel::DwConvC4 || kernel == Kernel::DwConv3x3Rows) && !dwconv_c4_eligible(a)) { kernel = Kernel::ConvGeneric; why_not_fast = "depthwise shape refused by the fast kernel"; }
+        if (kernel == Kernel::DwConvC4 && !dwconv_c4_general_eligible(a)) { kernel = Kernel::ConvGeneric; why_not_fast = "depthwise shape refused by the fast kernel"; }
+        if (kernel == Kernel::DwConv3x3Rows && !dwconv_c4_eligible(a)) { kernel = Kernel::ConvGeneric; why_not_fast = "depthwise shape refused by the fast kernel"; }
         if (kernel == Kernel::ConvTcPointwise || kernel == Kernel::ConvTc3x3) {
             tc.d_wmat = at(o_tc_w);
             std::string why;

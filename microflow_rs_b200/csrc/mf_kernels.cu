@@ -242,7 +242,10 @@ static inline dim3 grid2(long long per_sample, int block, long long batch) {
 // output bytes and reads 128 contiguous input bytes per tap (stride 1).  Bytes are sign-extended with one PRMT each
 // and multiplied with IMAD (IDP.4A issues to the slow XU pipe on sm_100 and is avoided in every hot loop).
 // ------------------------------------------------------------------------------------------------
-template <int KH_T, int KW_T>
+// U8: uint8 tensors (zero-extended bytes).  WZP: non-zero weight zero-points -- with zero-point padding every term of the reference
+// formula (depthwise_conv_2d.rs:66-87) is uniform over the image: sum_valid (v - iz)(w - wz) = sum_all v'w - wz * sum_all v' - iz * sum_all w
+// + taps * iz * wz  (v' = v inside, iz outside), so the only extra work is the window sum S = sum_all v' per channel.
+template <int KH_T, int KW_T, bool U8, bool WZP>
 __global__ void __launch_bounds__(256) dwconv_c4_kernel(ConvArgs a, uint32_t words_per_sample, FastDiv fd_g, FastDiv fd_ow) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= words_per_sample) return;
@@ -253,12 +256,18 @@ __global__ void __launch_bounds__(256) dwconv_c4_kernel(ConvArgs a, uint32_t wor
     fd_ow.divmod(p, i, j);
     const uint32_t *ww = reinterpret_cast<const uint32_t *>(a.w);
     const uint32_t izw = (uint32_t)(a.in_zp & 0xff) * 0x01010101u;
-    const int4 kc = __ldg(reinterpret_cast<const int4 *>(a.kcorr) + g);
+    int4 kc = __ldg(reinterpret_cast<const int4 *>(a.kcorr) + g);
+    int4 wz = make_int4(0, 0, 0, 0);
+    if (WZP) {                                                    // fold the constant term taps * iz * wz into the correction
+        wz = __ldg(reinterpret_cast<const int4 *>(a.w_zp) + g);
+        const int t = KH * KW * a.in_zp;
+        kc.x -= t * wz.x; kc.y -= t * wz.y; kc.z -= t * wz.z; kc.w -= t * wz.w;
+    }
     const float4 z = __ldg(reinterpret_cast<const float4 *>(a.c0z) + g);
     const float4 s = __ldg(reinterpret_cast<const float4 *>(a.c1) + g);
     for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
         const uint32_t *inw = reinterpret_cast<const uint32_t *>(a.in) + (size_t)b * a.H * a.W * G;
-        int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+        int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
         for (int m = 0; m < KH; ++m) {
             const int r = a.sh * (int)i + m - a.off_r;
@@ -269,27 +278,41 @@ __global__ void __launch_bounds__(256) dwconv_c4_kernel(ConvArgs a, uint32_t wor
                 const bool ok = rok && (unsigned)c < (unsigned)a.W;
                 const uint32_t v = ok ? __ldg(inw + ((size_t)r * a.W + c) * G + g) : izw;
                 const uint32_t wv = __ldg(ww + (size_t)(m * KW + n) * G + g);
-                acc0 += sx8<0>(v) * sx8<0>(wv);
-                acc1 += sx8<1>(v) * sx8<1>(wv);
-                acc2 += sx8<2>(v) * sx8<2>(wv);
-                acc3 += sx8<3>(v) * sx8<3>(wv);
+                const int v0 = ext8<U8, 0>(v), v1 = ext8<U8, 1>(v), v2 = ext8<U8, 2>(v), v3 = ext8<U8, 3>(v);
+                acc0 += v0 * ext8<U8, 0>(wv);
+                acc1 += v1 * ext8<U8, 1>(wv);
+                acc2 += v2 * ext8<U8, 2>(wv);
+                acc3 += v3 * ext8<U8, 3>(wv);
+                if (WZP) { s0 += v0; s1 += v1; s2 += v2; s3 += v3; }
             }
         }
+        if (WZP) { acc0 -= wz.x * s0; acc1 -= wz.y * s1; acc2 -= wz.z * s2; acc3 -= wz.w * s3; }
         reinterpret_cast<uint32_t *>(a.out)[(size_t)b * words_per_sample + idx] =
             pack4(requant_nx<false>(acc0 - kc.x, z.x, s.x, a.lo, a.hi), requant_nx<false>(acc1 - kc.y, z.y, s.y, a.lo, a.hi),
                   requant_nx<false>(acc2 - kc.z, z.z, s.z, a.lo, a.hi), requant_nx<false>(acc3 - kc.w, z.w, s.w, a.lo, a.hi));
     }
 }
 
-bool dwconv_c4_eligible(const ConvArgs &a) {
-    return a.depthwise && !a.is_u8 && a.Cin == a.Cout && (a.Cout % 4) == 0 && a.kcorr != nullptr && !a.big_acc;
+// any depthwise shape with Cin == Cout, C % 4 == 0 and accumulators within 2^22: int8 or uint8, any weight zero-points
+bool dwconv_c4_general_eligible(const ConvArgs &a) {
+    return a.depthwise && a.Cin == a.Cout && (a.Cout % 4) == 0 && a.kcorr != nullptr && a.w_zp != nullptr && !a.big_acc;
 }
+// the int8 / weight-zero-point-0 subset every other depthwise fast kernel builds on
+bool dwconv_c4_eligible(const ConvArgs &a) { return dwconv_c4_general_eligible(a) && !a.is_u8 && !a.wzp_nonzero; }
 cudaError_t launch_dwconv_c4(const ConvArgs &a, cudaStream_t s) {
     const long long per = (long long)a.OH * a.OW * (a.Cout / 4);
     if (per <= 0 || a.batch <= 0) return cudaSuccess;
     const FastDiv fg((uint32_t)(a.Cout / 4)), fow((uint32_t)a.OW);
-    if (a.KH == 3 && a.KW == 3) dwconv_c4_kernel<3, 3><<<grid2(per, 256, a.batch), 256, 0, s>>>(a, (uint32_t)per, fg, fow);
-    else dwconv_c4_kernel<0, 0><<<grid2(per, 256, a.batch), 256, 0, s>>>(a, (uint32_t)per, fg, fow);
+    const dim3 grid = grid2(per, 256, a.batch);
+    const bool k33 = a.KH == 3 && a.KW == 3;
+#define MF_C4(U, Z)                                                                                          \
+    do {                                                                                                     \
+        if (k33) dwconv_c4_kernel<3, 3, U, Z><<<grid, 256, 0, s>>>(a, (uint32_t)per, fg, fow);               \
+        else dwconv_c4_kernel<0, 0, U, Z><<<grid, 256, 0, s>>>(a, (uint32_t)per, fg, fow);                   \
+    } while (0)
+    if (a.is_u8) { if (a.wzp_nonzero) MF_C4(true, true); else MF_C4(true, false); }
+    else { if (a.wzp_nonzero) MF_C4(false, true); else MF_C4(false, false); }
+#undef MF_C4
     return cudaGetLastError();
 }
 
@@ -1279,6 +1302,7 @@ cudaError_t launch_dwconv_cin1(const ConvArgs &a, cudaStream_t s) {
 // 1x1 conv on CUDA cores (shapes the tcgen05 GEMM does not take, e.g. person_detect's final 256 -> 2 layer):
 // int8, w_zp == 0, Cin % 4 == 0.  One thread = up to 4 output channels of one pixel; dp4a over the input channels.
 // ------------------------------------------------------------------------------------------------
+template <bool U8, bool WZP>
 __global__ void __launch_bounds__(256) pwconv_dp4a_kernel(ConvArgs a, uint32_t items_per_sample, FastDiv fd_g, FastDiv fd_ow) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= items_per_sample) return;
@@ -1292,32 +1316,46 @@ __global__ void __launch_bounds__(256) pwconv_dp4a_kernel(ConvArgs a, uint32_t i
     const uint32_t *w1 = w0 + (nco > 1 ? K4 : 0), *w2 = w0 + (nco > 2 ? 2 * K4 : 0), *w3 = w0 + (nco > 3 ? 3 * K4 : 0);
     for (long long b = blockIdx.y; b < a.batch; b += gridDim.y) {
         const uint32_t *x = reinterpret_cast<const uint32_t *>(a.in) + (((size_t)b * a.H + (size_t)a.sh * i) * a.W + (size_t)a.sw * j) * K4;
-        int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;
+        int acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, vsum = 0;
 #pragma unroll 4
         for (int k = 0; k < K4; ++k) {
-            const int v = (int)__ldg(x + k);
-            acc0 = __dp4a(v, (int)__ldg(w0 + k), acc0);
-            acc1 = __dp4a(v, (int)__ldg(w1 + k), acc1);
-            acc2 = __dp4a(v, (int)__ldg(w2 + k), acc2);
-            acc3 = __dp4a(v, (int)__ldg(w3 + k), acc3);
+            const uint32_t v = __ldg(x + k);
+            acc0 = dot4<U8>(v, __ldg(w0 + k), acc0);
+            acc1 = dot4<U8>(v, __ldg(w1 + k), acc1);
+            acc2 = dot4<U8>(v, __ldg(w2 + k), acc2);
+            acc3 = dot4<U8>(v, __ldg(w3 + k), acc3);
+            if (WZP) vsum = dot4<U8>(v, 0x01010101u, vsum);              // conv_2d.rs:74-76: the view sum, once per pixel
         }
         const int accs[4] = {acc0, acc1, acc2, acc3};
         uint8_t *o = a.out + ((size_t)b * a.OH * a.OW + p) * a.Cout + co;
-        for (int u = 0; u < nco; ++u) o[u] = (uint8_t)requant_nx<true>(accs[u] - a.kcorr[co + u], a.c0z[co + u], a.c1[co + u], a.lo, a.hi);
+        for (int u = 0; u < nco; ++u) {
+            int t = accs[u] - a.kcorr[co + u];
+            if (WZP) { const int fz = a.w_zp[co + u]; t += fz * (a.Cin * a.in_zp - vsum); }     // - fz * sum(v) + len * Cin * iz * fz  (len = 1)
+            o[u] = (uint8_t)requant_nx<true>(t, a.c0z[co + u], a.c1[co + u], a.lo, a.hi);
+        }
     }
 }
 
 bool pwconv_dp4a_eligible(const ConvArgs &a) {
     // the kernel reads in[(sh*i)*W + sw*j] unchecked: every output position must map inside the input (a model whose declared
-    // output is larger than the strided input would need the reference's padding semantics -> generic kernel)
-    return !a.depthwise && !a.is_u8 && a.KH == 1 && a.KW == 1 && (a.Cin % 4) == 0 && a.kcorr != nullptr && (long long)a.sh * (a.OH - 1) < a.H &&
+    // output is larger than the strided input would need the reference's padding semantics -> generic kernel).  int8 or uint8, any
+    // weight zero-points.
+    return !a.depthwise && a.KH == 1 && a.KW == 1 && (a.Cin % 4) == 0 && a.kcorr != nullptr && a.w_zp != nullptr && (long long)a.sh * (a.OH - 1) < a.H &&
            (long long)a.sw * (a.OW - 1) < a.W;
 }
 cudaError_t launch_pwconv_dp4a(const ConvArgs &a, cudaStream_t s) {
     const int G = (a.Cout + 3) / 4;
     const long long per = (long long)a.OH * a.OW * G;
     if (per <= 0 || a.batch <= 0) return cudaSuccess;
-    pwconv_dp4a_kernel<<<grid2(per, 256, a.batch), 256, 0, s>>>(a, (uint32_t)per, FastDiv((uint32_t)G), FastDiv((uint32_t)a.OW));
+    const dim3 grid = grid2(per, 256, a.batch);
+    const FastDiv fg((uint32_t)G), fow((uint32_t)a.OW);
+    if (a.is_u8) {
+        if (a.wzp_nonzero) pwconv_dp4a_kernel<true, true><<<grid, 256, 0, s>>>(a, (uint32_t)per, fg, fow);
+        else pwconv_dp4a_kernel<true, false><<<grid, 256, 0, s>>>(a, (uint32_t)per, fg, fow);
+    } else {
+        if (a.wzp_nonzero) pwconv_dp4a_kernel<false, true><<<grid, 256, 0, s>>>(a, (uint32_t)per, fg, fow);
+        else pwconv_dp4a_kernel<false, false><<<grid, 256, 0, s>>>(a, (uint32_t)per, fg, fow);
+    }
     return cudaGetLastError();
 }
 
@@ -1325,7 +1363,7 @@ cudaError_t launch_pwconv_dp4a(const ConvArgs &a, cudaStream_t s) {
 // FAST: fully connected with few outputs (speech: 4000 -> 4): one warp per sample, 128-bit loads, dp4a,
 // shuffle reduction.  Pure bandwidth: K bytes per sample.
 // ================================================================================================
-template <int N_T>
+template <int N_T, bool U8>
 __global__ void __launch_bounds__(256) fc_warp_kernel(FcArgs a) {
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -1340,14 +1378,14 @@ __global__ void __launch_bounds__(256) fc_warp_kernel(FcArgs a) {
     int rowsum = 0;
     for (int t = lane; t < chunks; t += 32) {
         const int4 v = __ldg(x + t);
-        rowsum = __dp4a(v.x, 0x01010101, rowsum); rowsum = __dp4a(v.y, 0x01010101, rowsum);
-        rowsum = __dp4a(v.z, 0x01010101, rowsum); rowsum = __dp4a(v.w, 0x01010101, rowsum);
+        rowsum = dot4<U8>(v.x, 0x01010101u, rowsum); rowsum = dot4<U8>(v.y, 0x01010101u, rowsum);
+        rowsum = dot4<U8>(v.z, 0x01010101u, rowsum); rowsum = dot4<U8>(v.w, 0x01010101u, rowsum);
 #pragma unroll
         for (int j = 0; j < N_T; ++j) {
             if (j < a.N) {
                 const int4 w = __ldg(reinterpret_cast<const int4 *>(a.w + (size_t)j * a.K) + t);
-                acc[j] = __dp4a(v.x, w.x, acc[j]); acc[j] = __dp4a(v.y, w.y, acc[j]);
-                acc[j] = __dp4a(v.z, w.z, acc[j]); acc[j] = __dp4a(v.w, w.w, acc[j]);
+                acc[j] = dot4<U8>(v.x, w.x, acc[j]); acc[j] = dot4<U8>(v.y, w.y, acc[j]);
+                acc[j] = dot4<U8>(v.z, w.z, acc[j]); acc[j] = dot4<U8>(v.w, w.w, acc[j]);
             }
         }
     }
@@ -1462,12 +1500,16 @@ cudaError_t launch_tail_fused(const TailArgs &a, cudaStream_t s) {
     }
 }
 
-bool fc_warp_eligible(const FcArgs &a) { return !a.is_u8 && (a.K % 16) == 0 && a.N >= 1 && a.N <= 8; }
+bool fc_warp_eligible(const FcArgs &a) { return (a.K % 16) == 0 && a.N >= 1 && a.N <= 8; }     // int8 or uint8, any weight zero-point
 cudaError_t launch_fc_warp(const FcArgs &a, cudaStream_t s) {
     if (a.batch <= 0) return cudaSuccess;
     const unsigned grid = grid_for(a.batch * 32, 256);
-    if (a.N <= 4) return launch_pdl(fc_warp_kernel<4>, dim3(grid), dim3(256), 0, s, a.pdl, a);
-    return launch_pdl(fc_warp_kernel<8>, dim3(grid), dim3(256), 0, s, a.pdl, a);
+    if (a.is_u8) {
+        if (a.N <= 4) return launch_pdl(fc_warp_kernel<4, true>, dim3(grid), dim3(256), 0, s, a.pdl, a);
+        return launch_pdl(fc_warp_kernel<8, true>, dim3(grid), dim3(256), 0, s, a.pdl, a);
+    }
+    if (a.N <= 4) return launch_pdl(fc_warp_kernel<4, false>, dim3(grid), dim3(256), 0, s, a.pdl, a);
+    return launch_pdl(fc_warp_kernel<8, false>, dim3(grid), dim3(256), 0, s, a.pdl, a);
 }
 
 }  // namespace mf

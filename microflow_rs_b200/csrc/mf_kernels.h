@@ -58,6 +58,7 @@ struct ConvArgs {
     int in_zp = 0;
     float lo = -128.f, hi = 127.f;
     int is_u8 = 0, depthwise = 0;
+    int wzp_nonzero = 0;            // some weight zero-point != 0 (the general formula with the view-sum term)
     int big_acc = 0;                // 1 if |acc - kcorr| can exceed 2^22 (selects the general exact int->float)
     long long batch = 0;
     int pdl = 0;                    // launch with programmatic stream serialization (see launch_pdl); smem / tcgen05 kernels only
@@ -139,7 +140,8 @@ cudaError_t launch_dequantize(const uint8_t *in, float *out, size_t n, float sca
 cudaError_t launch_layout_transpose(const uint8_t *src, uint8_t *dst, long long batch, int R, int C, int elem, cudaStream_t s);
 
 // ---- SIMT fast kernels (int8, weight zero-point 0): coalesced NHWC, dp4a -------------------------------
-bool dwconv_c4_eligible(const ConvArgs &a);      // depthwise, Cin == Cout, C % 4 == 0
+bool dwconv_c4_eligible(const ConvArgs &a);      // depthwise, Cin == Cout, C % 4 == 0, int8, weight zero-points 0
+bool dwconv_c4_general_eligible(const ConvArgs &a);   // the same kernel also takes uint8 and non-zero weight zero-points
 cudaError_t launch_dwconv_c4(const ConvArgs &a, cudaStream_t s);
 bool dwconv3x3_rows_eligible(const ConvArgs &a); // + 3x3, stride 1x1 or 2x2: sliding 3x3 window down a column strip
 cudaError_t launch_dwconv3x3_rows(const ConvArgs &a, cudaStream_t s);

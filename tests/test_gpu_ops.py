@@ -200,6 +200,64 @@ def test_conv_fast_simt_vs_oracle(case):
     np.testing.assert_array_equal(got_g, want)
 
 
+FAST_GENERAL_CASES = [
+    # uint8 tensors (`T = u8`, microflow-macros/src/ops/conv_2d.rs:39-46) and non-zero weight zero-points (the view-sum term,
+    # src/ops/conv_2d.rs:74-76, depthwise_conv_2d.rs:71-73) on the FAST kernels: impl=2 refuses the generic kernel.
+    # B, H, W, Cin, Cout, KH, KW, sh, sw, pad, act, dw, dtype, wzp0, kernel
+    (3, 12, 12, 8, 8, 3, 3, 1, 1, "same", "relu6", True, np.uint8, False, "dwconv_c4"),
+    (2, 7, 9, 12, 12, 5, 3, 2, 1, "same", "relu", True, np.int8, False, "dwconv_c4"),
+    (300, 6, 6, 128, 128, 3, 3, 1, 1, "same", "relu6", True, np.uint8, True, "dwconv_c4"),
+    (2, 9, 7, 4, 4, 3, 3, 1, 1, "valid", "none", True, np.int8, False, "dwconv_c4"),
+    (2, 4, 4, 16, 7, 1, 1, 1, 1, "same", "relu", False, np.int8, False, "pwconv_dp4a"),
+    (3, 12, 12, 8, 16, 1, 1, 1, 1, "same", "relu6", False, np.uint8, False, "pwconv_dp4a"),
+    (2, 6, 6, 8, 4, 1, 1, 2, 2, "same", "relu", False, np.uint8, False, "pwconv_dp4a"),
+    (2, 5, 5, 12, 20, 1, 1, 1, 1, "same", "none", False, np.uint8, True, "pwconv_dp4a"),
+    (3, 24, 24, 32, 32, 1, 1, 1, 1, "same", "relu6", False, np.uint8, True, "conv_tc"),     # tcgen05 with unsigned operand formats, packed pixels
+    (9, 6, 6, 128, 128, 1, 1, 1, 1, "same", "relu", False, np.uint8, True, "conv_tc"),
+    (5, 3, 3, 256, 256, 1, 1, 1, 1, "same", "none", False, np.uint8, True, "conv_tc"),       # two 128-byte channel blocks
+    (2, 9, 21, 128, 64, 3, 3, 1, 1, "same", "relu6", False, np.uint8, True, "conv_tc"),      # 3x3 implicit GEMM, zero-filled borders + class table
+]
+
+
+@pytest.mark.parametrize("case", FAST_GENERAL_CASES)
+def test_uint8_and_weight_zero_points_on_fast_kernels(case):
+    import re
+    B, H, W, Cin, Cout, KH, KW, sh, sw, pad, act, dw, dtype, wzp0, kname = case
+    c = _conv_case(rng(zlib.crc32(repr(case).encode())), B, H, W, Cin, Cout, KH, KW, sh, sw, pad, act, dw, dtype, wzp0)
+    if kname == "conv_tc":                      # keep the requantized values inside the output range for a meaningful comparison
+        c["c1"] = (c["c1"] / 4).astype(np.float32)
+    nchk = min(B, 6)
+    got = mf.ops.conv_2d(c["x"], c["in_zp"], c["w"], c["wzp"], c["out_scale"], c["out_zp"], c["act"], c["pad"], c["strides"], c["c0"], c["c1"], c["out_hw"],
+                         depthwise=c["dw"], impl=2)
+    assert re.search(kname, mf.ops.last_kernel), mf.ops.last_kernel
+    want = np.stack([oracle.conv_2d(c["x"][b], c["in_zp"], c["w"], c["wzp"], c["out_scale"], c["out_zp"], c["act"], c["pad"], c["strides"], c["c0"],
+                                    c["c1"], c["out_hw"], depthwise=c["dw"]) for b in range(nchk)])
+    np.testing.assert_array_equal(got[:nchk], want)
+    ref = mf.ops.conv_2d(c["x"], c["in_zp"], c["w"], c["wzp"], c["out_scale"], c["out_zp"], c["act"], c["pad"], c["strides"], c["c0"], c["c1"], c["out_hw"],
+                         depthwise=c["dw"], impl=1)
+    np.testing.assert_array_equal(got, ref)
+    assert 0.01 < np.mean((got != got.flat[0])), "degenerate output"
+
+
+@pytest.mark.parametrize("K,N,B,wzp,dtype,kname", [(48, 3, 40, 9, np.uint8, "fc_warp"), (64, 8, 6, -7, np.int8, "fc_warp"), (4000, 4, 9, 200, np.uint8, "fc_warp"),
+                                                    (256, 64, 129, 0, np.uint8, "conv_tc"), (128, 32, 300, 0, np.uint8, "conv_tc")])
+def test_fully_connected_uint8_and_weight_zero_point_on_fast_kernels(K, N, B, wzp, dtype, kname):
+    r = rng(K * 7 + N)
+    lo, hi = (0, 256) if dtype == np.uint8 else (-128, 128)
+    x = r.integers(lo, hi, (B, K)).astype(dtype)
+    w = r.integers(lo, hi, (N, K)).astype(dtype)
+    in_zp = int(r.integers(lo, hi))
+    c0 = r.uniform(-10, 10, N).astype(np.float32)
+    c1 = np.float32(1.0 / (K * 60.0))
+    c2 = (w.astype(np.int32).sum(1) * in_zp).astype(np.int32)
+    c3 = K * in_zp * wzp
+    out_zp = 100 if dtype == np.uint8 else 3
+    got = mf.ops.fully_connected(x, w, wzp, 0.1, out_zp, "relu", c0, c1, c2, c3, impl=2)
+    assert kname in mf.ops.last_kernel, mf.ops.last_kernel
+    want = oracle.fully_connected(x, w, wzp, 0.1, out_zp, "relu", c0, c1, c2, c3)
+    np.testing.assert_array_equal(got, want)
+
+
 def test_requant_saturation_and_large_accumulators():
     """Accumulators beyond 2^24 (i32->f32 rounding), saturation at both ends, ties."""
     r = rng(7)
