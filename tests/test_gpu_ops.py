@@ -226,6 +226,9 @@ def test_uint8_and_weight_zero_points_on_fast_kernels(case):
     c = _conv_case(rng(zlib.crc32(repr(case).encode())), B, H, W, Cin, Cout, KH, KW, sh, sw, pad, act, dw, dtype, wzp0)
     if kname == "conv_tc":                      # keep the requantized values inside the output range for a meaningful comparison
         c["c1"] = (c["c1"] / 4).astype(np.float32)
+    if dtype == np.uint8 and wzp0:              # unsigned weights with zero-point 0 are all positive: large accumulators
+        c["c1"] = (c["c1"] / 24).astype(np.float32)
+        c["in_zp"] = 128
     nchk = min(B, 6)
     got = mf.ops.conv_2d(c["x"], c["in_zp"], c["w"], c["wzp"], c["out_scale"], c["out_zp"], c["act"], c["pad"], c["strides"], c["c0"], c["c1"], c["out_hw"],
                          depthwise=c["dw"], impl=2)
