@@ -23,7 +23,7 @@ import numpy as np
 
 from . import _build
 
-__all__ = ["model", "Model", "ConvOp", "ops", "MicroflowError", "lib", "build", "device_count", "PinnedBuffer"]
+__all__ = ["model", "Model", "ConvOp", "ops", "MicroflowError", "lib", "build", "device_count", "PinnedBuffer", "features_from_bmp"]
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libmicroflow_cuda.so"
@@ -95,7 +95,7 @@ ABI_SYMBOLS = [
     "mf_predict", "mf_predict_quantized", "mf_predict_many", "mf_predict_many_quantized", "mf_predict_many_quantized_async", "mf_predict_many_logits", "mf_predict_many_device",
     "mf_predict_trace", "mf_model_synchronize", "mf_model_set_profiling", "mf_model_layer_times_ms", "mf_model_launch_count", "mf_model_blob",
     "mf_host_alloc", "mf_host_free", "mf_op_conv_2d", "mf_op_conv_2d_create", "mf_op_run_device", "mf_op_kernel_name", "mf_op_destroy", "mf_op_fully_connected", "mf_op_average_pool_2d", "mf_op_softmax", "mf_op_quantize",
-    "mf_op_dequantize", "mf_op_layout_transpose", "mf_model_layer_launched", "mf_model_devices", "mf_model_weight_broadcast", "mf_predict_many_device_on", "mf_op_conv_chain",
+    "mf_op_dequantize", "mf_op_layout_transpose", "mf_model_layer_launched", "mf_model_devices", "mf_model_weight_broadcast", "mf_predict_many_device_on", "mf_op_conv_chain", "mf_features_from_bmp_gray8", "mf_predict_many_bmp",
 ]
 
 _lib = None
@@ -151,6 +151,8 @@ def lib():
         L.mf_host_free.argtypes = [C.c_void_p]
         L.mf_device_count.argtypes = [C.POINTER(C.c_int)]
         L.mf_op_conv_2d.argtypes = [C.POINTER(_ConvDesc), C.c_void_p, C.c_void_p, C.c_size_t]
+        L.mf_features_from_bmp_gray8.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.mf_predict_many_bmp.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t, C.c_void_p]
         L.mf_op_conv_chain.argtypes = [C.POINTER(_ConvDesc), C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
         L.mf_op_conv_2d_create.argtypes = [C.POINTER(_ConvDesc), C.POINTER(C.c_void_p)]
         L.mf_op_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -352,6 +354,15 @@ class Model:
         _check(lib().mf_predict_many_logits(self._h, xs.ctypes.data, n, outq.ctypes.data, lp))
         return outq, logits
 
+    def predict_many_bmp(self, images):
+        """images: a list of BMP files as bytes (8-bit gray, the model's input size) -> staged and run as one batch."""
+        n = len(images)
+        arr = (C.c_char_p * n)(*images)
+        lens = (C.c_size_t * n)(*[len(b) for b in images])
+        out = np.zeros((n, self.out_elems), np.float32)
+        _check(lib().mf_predict_many_bmp(self._h, arr, lens, n, out.ctypes.data))
+        return out
+
     def predict_many_device(self, d_in_ptr, n, d_out_f32_ptr=None, d_out_q_ptr=None, stream=None):
         """Device-resident buffers given as raw pointers (e.g. torch.Tensor.data_ptr()); asynchronous."""
         _check(lib().mf_predict_many_device(self._h, C.c_void_p(d_in_ptr), n, C.c_void_p(d_out_f32_ptr or 0), C.c_void_p(d_out_q_ptr or 0),
@@ -445,6 +456,15 @@ class ConvOp:
             self.close()
         except Exception:
             pass
+
+
+def features_from_bmp(data):
+    """samples/person.bmp -> the reference's `features::PERSON` tensor (samples/features/person_detect.rs): int8 [H, W, 1], top row first."""
+    h, w = C.c_int32(0), C.c_int32(0)
+    _check(lib().mf_features_from_bmp_gray8(data, len(data), None, 0, C.byref(h), C.byref(w)))
+    out = np.zeros((h.value, w.value, 1), np.int8)
+    _check(lib().mf_features_from_bmp_gray8(data, len(data), out.ctypes.data, out.size, C.byref(h), C.byref(w)))
+    return out
 
 
 def model(path, **kw):

@@ -1174,6 +1174,34 @@ int mf_model_blob(const mf_model *m, void **d_ptr, size_t *bytes) {
     return MF_OK;
 }
 
+// ---- host staging of the reference's sample formats ------------------------------------------------
+int mf_features_from_bmp_gray8(const void *bmp, size_t len, void *out, size_t cap, int32_t *height, int32_t *width) {
+    std::string err;
+    int h = 0, w = 0;
+    int rc = features_from_bmp_gray8((const uint8_t *)bmp, len, (uint8_t *)out, out ? cap : 0, &h, &w, err);
+    if (height) *height = h;
+    if (width) *width = w;
+    if (rc != MF_OK && !(rc == MF_ERR_INVALID_ARG && !out && h > 0)) return fail(rc, err);      // out == NULL: a size query
+    return MF_OK;
+}
+int mf_predict_many_bmp(mf_model *m, const void *const *bmps, const size_t *lens, size_t n, float *out) {
+    if (!m || !bmps || !lens || !out) return fail(MF_ERR_INVALID_ARG, "null argument");
+    const mf_model *p = primary(m);
+    if (p->spec.in_rank != 4 || p->spec.in_dims[3] != 1 || p->spec.is_u8_in) return fail(MF_ERR_UNSUPPORTED_SHAPE, "the model does not take one-channel int8 images");
+    const size_t ie = p->spec.in_elems;
+    std::vector<uint8_t> staged(n * ie);
+    for (size_t k = 0; k < n; ++k) {
+        std::string err;
+        int h = 0, w = 0;
+        int rc = features_from_bmp_gray8((const uint8_t *)bmps[k], lens[k], staged.data() + k * ie, ie, &h, &w, err);
+        if (rc) return fail(rc, "image " + std::to_string(k) + ": " + err);
+        if (h != p->spec.in_dims[1] || w != p->spec.in_dims[2]) return fail(MF_ERR_UNSUPPORTED_SHAPE, "image " + std::to_string(k) + " is not " +
+                                                                                std::to_string(p->spec.in_dims[1]) + "x" + std::to_string(p->spec.in_dims[2]));
+    }
+    if (p->layout == MF_LAYOUT_NALGEBRA) return fail(MF_ERR_INVALID_ARG, "mf_predict_many_bmp stages NHWC inputs: create the model with MF_LAYOUT_NHWC");
+    return predict_host_any(m, staged.data(), nullptr, n, out, nullptr, nullptr);
+}
+
 int mf_host_alloc(void **p, size_t bytes) {
     if (!p) return fail(MF_ERR_INVALID_ARG, "null pointer");
     int rc = check_device(nullptr);

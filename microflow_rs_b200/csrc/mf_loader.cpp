@@ -197,6 +197,35 @@ float libm_expf(float x) {
     return k == 0 ? y : scalbn_f(y, k);
 }
 
+int features_from_bmp_gray8(const uint8_t *b, size_t len, uint8_t *out, size_t cap, int *height, int *width, std::string &err) {
+    auto u16 = [&](size_t o) { return (uint32_t)b[o] | ((uint32_t)b[o + 1] << 8); };
+    auto u32 = [&](size_t o) { return u16(o) | (u16(o + 2) << 16); };
+    if (!b || len < 54 || b[0] != 'B' || b[1] != 'M') { err = "not a BMP file"; return MF_ERR_INVALID_ARG; }
+    const uint32_t off = u32(10), hsz = u32(14);
+    const int32_t w = (int32_t)u32(18), hraw = (int32_t)u32(22);
+    const uint32_t planes = u16(26), bpp = u16(28), comp = u32(30);
+    if (hsz < 40 || planes != 1 || bpp != 8 || comp != 0) { err = "only uncompressed 8-bit BMP images are supported"; return MF_ERR_UNSUPPORTED_TYPE; }
+    const int32_t h = hraw < 0 ? -hraw : hraw;
+    if (w <= 0 || h <= 0 || w > 16384 || h > 16384) { err = "bad BMP dimensions"; return MF_ERR_INVALID_ARG; }
+    const size_t pitch = ((size_t)w + 3) & ~(size_t)3;                      // rows are padded to 4 bytes
+    if ((size_t)off + pitch * (size_t)h > len) { err = "truncated BMP pixel array"; return MF_ERR_INVALID_ARG; }
+    uint32_t ncol = u32(46);
+    if (ncol == 0) ncol = 256;
+    if (14 + (size_t)hsz + 4 * (size_t)ncol > off || ncol > 256) { err = "bad BMP palette"; return MF_ERR_INVALID_ARG; }
+    for (uint32_t k = 0; k < ncol; ++k) {                                   // gray identity palette: index == intensity
+        const uint8_t *e = b + 14 + hsz + 4 * (size_t)k;
+        if (e[0] != k || e[1] != k || e[2] != k) { err = "BMP palette is not the identity gray ramp"; return MF_ERR_UNSUPPORTED_TYPE; }
+    }
+    if (height) *height = h;
+    if (width) *width = w;
+    if ((size_t)w * (size_t)h > cap) { err = "output buffer too small for the image"; return MF_ERR_INVALID_ARG; }
+    for (int32_t r = 0; r < h; ++r) {
+        const int32_t src = hraw < 0 ? r : h - 1 - r;                        // bottom-up storage -> top row first
+        std::memcpy(out + (size_t)r * w, b + off + pitch * (size_t)src, (size_t)w);
+    }
+    return MF_OK;
+}
+
 int quantize_scalar(float x, float scale, int zp, bool is_u8) {  // src/quantize.rs:16-18
     return sat_cast(roundf(x / scale + (float)zp), is_u8);
 }

@@ -43,6 +43,11 @@ struct ModelSpec {
 // Returns MF_OK or the mf_status that corresponds to the reference's compile-time diagnostic.
 int parse_tflite(const uint8_t *buf, size_t len, ModelSpec &out, std::string &err);
 
+// Host staging of the reference's image sample format (samples/person.bmp -> the const PERSON of samples/features/person_detect.rs):
+// an uncompressed 8-bit BMP with the identity gray palette; the feature tensor is the pixel bytes read as int8, top row first
+// (BMP stores its rows bottom-up unless the height is negative).  Returns MF_OK or MF_ERR_INVALID_ARG / MF_ERR_UNSUPPORTED_TYPE.
+int features_from_bmp_gray8(const uint8_t *bmp, size_t len, uint8_t *out, size_t cap, int *height, int *width, std::string &err);
+
 // Scalar semantics shared by host-side preprocessing (bit-exact restatements).
 float libm_expf(float x);                                   // Rust libm 0.2 expf (musl e_expf.c algorithm)
 int quantize_scalar(float x, float scale, int zp, bool is_u8);  // src/quantize.rs:16-18

@@ -205,6 +205,8 @@ extern "C" {
     pub fn mf_model_devices(m: *const mf_model, devices: *mut i32, cap: c_int) -> c_int;
     pub fn mf_model_weight_broadcast(m: *const mf_model) -> *const c_char;
     pub fn mf_model_blob(m: *const mf_model, d_ptr: *mut *mut c_void, bytes: *mut usize) -> c_int;
+    pub fn mf_features_from_bmp_gray8(bmp: *const c_void, len: usize, out: *mut c_void, cap: usize, height: *mut i32, width: *mut i32) -> c_int;
+    pub fn mf_predict_many_bmp(m: *mut mf_model, bmps: *const *const c_void, lens: *const usize, n: usize, out_f32: *mut f32) -> c_int;
     pub fn mf_host_alloc(p: *mut *mut c_void, bytes: usize) -> c_int;
     pub fn mf_host_free(p: *mut c_void) -> c_int;
     // ---- per-operator hooks (microflow::ops::*, src/ops/mod.rs:8-13)

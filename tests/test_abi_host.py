@@ -183,3 +183,17 @@ def test_device_list_options_are_validated_without_a_gpu():
     m = mf.Model(MODELS / "sine.tflite", flags=mf.FLAG_HOST_ONLY, devices=[0, 1, 2])
     assert m.devices == [] and m.launched_kernels() == [""] * len(m.layers)
     m.close()
+
+
+def test_bmp_staging_reproduces_the_reference_features(samples):
+    """samples/person.bmp and no_person.bmp (byte-identical copies under tests/golden/) -> exactly the int8 tensors the reference ships as
+    features::PERSON / NO_PERSON (samples/features/person_detect.rs:5,104).  Host-side staging: needs no GPU."""
+    from conftest import GOLDEN
+    for f, key in (("person.bmp", "PERSON"), ("no_person.bmp", "NO_PERSON")):
+        got = mf.features_from_bmp((GOLDEN / f).read_bytes())
+        assert got.shape == (96, 96, 1) and got.dtype == np.int8
+        np.testing.assert_array_equal(got.reshape(-1), np.asarray(samples[key]).reshape(-1))
+    with pytest.raises(mf.MicroflowError):
+        mf.features_from_bmp(b"BM" + b"\0" * 20)
+    with pytest.raises(mf.MicroflowError):
+        mf.features_from_bmp((GOLDEN / "person.bmp").read_bytes()[:5000])       # truncated pixel array

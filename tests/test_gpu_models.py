@@ -217,3 +217,11 @@ def test_device_resident_full_batch_splits_into_two_streams(gpu_models, ora):
             m.predict_many_device(d_in.data_ptr(), n, d_out.data_ptr(), None, st.cuda_stream)
         got = d_out.cpu().numpy()                            # ordered behind the calls on the same stream
     np.testing.assert_array_equal(got, want)
+
+
+def test_predict_from_bmp_samples(gpu_models):
+    """The step before the path: the reference's image samples as files -> staged -> person_detect, same outputs as its
+    precomputed feature tensors give (examples/person_detect.rs:27-28 classes)."""
+    from conftest import GOLDEN
+    out = gpu_models["person_detect"].predict_many_bmp([(GOLDEN / "person.bmp").read_bytes(), (GOLDEN / "no_person.bmp").read_bytes()])
+    np.testing.assert_array_equal(out, f32([[0.26953125, 0.73046875], [0.6171875, 0.3828125]]))
