@@ -190,7 +190,7 @@ int mf_model_blob(const mf_model *m, void **d_ptr, size_t *bytes);
 
 /* ---- host staging of the reference's sample formats: the step before the path (samples/person.bmp -> samples/features/person_detect.rs) */
 /* An uncompressed 8-bit BMP with the identity gray palette -> `height * width` int8 features, top row first (the pixel bytes read as
- * int8; BMP rows are stored bottom-up).  out == NULL only reports the dimensions.  The speech frontend (samples/*.wav ->
+ * int8; BMP rows are stored bottom-up).  out == NULL only reports the dimensions.  The speech frontend (the .wav samples ->
  * samples/features/speech.rs) is TensorFlow Lite Micro's audio frontend, which the reference does not contain: not provided. */
 int mf_features_from_bmp_gray8(const void *bmp, size_t len, void *out, size_t cap, int32_t *height, int32_t *width);
 /* n BMP images of the model's input size -> staged into one NHWC batch -> mf_predict_many_quantized */

@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -814,6 +815,57 @@ int group_predict_many(mf_model *g, const void *in_q, const float *in_f32, size_
     const size_t le = p->softmax_tail >= 0 ? p->layers[(size_t)p->softmax_tail].spec.in_elems : 0;
     struct Res { int rc = 0; std::string err; };
     auto res = std::make_shared<std::vector<Res>>(G);
+    // Large host-resident batches: the host -> device links of a box are not equally fast once several GPUs copy at the same time
+    // (pairs of GPUs share an uplink: profiles/r02c_h2d_sweep_8gpu.txt measured 21-37 GB/s per GPU with eight copying), and with equal
+    // shards the slowest link sets the time of the call.  So the range is cut into contiguous 2048-sample chunks that the replicas'
+    // host threads claim from a shared counter: a GPU on a faster link takes more of them.  Every chunk still lands at its own offset
+    // of the caller's buffers, so the result is the same row for row; with equal links this degenerates to equal contiguous
+    // shards.  MF_SHARD_DYNAMIC=0 keeps the static split [r * ceil(n / G), ...) below (always used for smaller calls).
+    static const bool env_dyn = [] { const char *e = std::getenv("MF_SHARD_DYNAMIC"); return !e || std::atoi(e) != 0; }();
+    constexpr size_t kDynChunk = 2048;
+    if (env_dyn && n >= G * 2 * kDynChunk) {
+        auto next = std::make_shared<std::atomic<size_t>>(0);
+        const size_t nchunks = (n + kDynChunk - 1) / kDynChunk;
+        for (size_t r = 0; r < G; ++r) {
+            mf_model *rep = g->replicas[r];
+            g->workers[r]->post([=] {
+                int rc = MF_OK;
+                size_t k = 0;
+                for (;;) {
+                    const size_t c = next->fetch_add(1);
+                    if (c >= nchunks) break;
+                    const size_t lo = c * kDynChunk, cn = std::min(kDynChunk, n - lo);
+                    const size_t slot = rep->slot_rr & 1;            // the stream slot predict_many_host is about to use for this chunk
+                    rc = predict_many_host(rep, in_q ? (const uint8_t *)in_q + lo * ie : nullptr, in_f32 ? in_f32 + lo * ie : nullptr, cn,
+                                           out_f32 ? out_f32 + lo * oe : nullptr, out_q ? (uint8_t *)out_q + lo * oe : nullptr,
+                                           logits ? (uint8_t *)logits + lo * le : nullptr, /*wait=*/false);
+                    if (rc) break;
+                    // two chunks in flight per GPU: before claiming another one, wait for the chunk enqueued before this one
+                    if (k >= 1 && (cudaSetDevice(rep->device) != cudaSuccess || cudaStreamSynchronize(rep->slot[slot ^ 1].stream) != cudaSuccess)) {
+                        rc = fail(MF_ERR_CUDA, "cudaStreamSynchronize failed in the multi-device chunk loop");
+                        break;
+                    }
+                    ++k;
+                }
+                if (!rc && wait && (cudaSetDevice(rep->device) != cudaSuccess || cudaStreamSynchronize(rep->slot[0].stream) != cudaSuccess ||
+                                    cudaStreamSynchronize(rep->slot[1].stream) != cudaSuccess))
+                    rc = fail(MF_ERR_CUDA, "cudaStreamSynchronize failed at the end of a multi-device call");
+                if (rc) {
+                    (*res)[r].rc = rc;
+                    (*res)[r].err = g_err;
+                    if (!wait) {
+                        std::lock_guard<std::mutex> l(g->group_mu);
+                        if (!g->deferred_rc) { g->deferred_rc = rc; g->deferred_err = g_err; }
+                    }
+                }
+            });
+        }
+        if (!wait) return MF_OK;
+        for (auto &w : g->workers) w->drain();
+        for (size_t r = 0; r < G; ++r)
+            if ((*res)[r].rc) return fail((*res)[r].rc, "device " + std::to_string(g->replicas[r]->device) + ": " + (*res)[r].err);
+        return MF_OK;
+    }
     for (size_t r = 0; r < G; ++r) {
         size_t lo, hi;
         shard_range(n, r, G, lo, hi);

@@ -48,8 +48,15 @@ for k in range(2):
 g.synchronize()
 ref = one.predict_many_quantized(xs)
 res["async"] = bool(np.array_equal(outs[0].array, ref) and np.array_equal(outs[1].array, ref))
+# large host-resident calls: contiguous 2048-sample chunks claimed dynamically by the devices' host threads (same rows, same order)
+nb = len(devices) * 2 * 2048 + 37
+big = np.concatenate([xs] * (nb // n + 1))[:nb]
+res["dynamic_chunks"] = bool(np.array_equal(g.predict_many_quantized(big), one.predict_many_quantized(big)))
+qb, lb = g.predict_many_logits(big)
+q1b, l1b = one.predict_many_logits(big)
+res["dynamic_chunks_logits"] = bool(np.array_equal(qb, q1b) and np.array_equal(lb, l1b))
 res["launches"] = g.launch_count()
-res["ok"] = all(res[k] for k in ("rows_equal_1gpu", "last_shard_equals_oracle", "one_sample", "tiny_batches", "async"))
+res["ok"] = all(res[k] for k in ("rows_equal_1gpu", "last_shard_equals_oracle", "one_sample", "tiny_batches", "async", "dynamic_chunks", "dynamic_chunks_logits"))
 g.close(); one.close()
 print(json.dumps(res))
 """
