@@ -547,7 +547,9 @@ int predict_small_graph(mf_model *m, const void *in_q, const float *in_f32, size
 }
 
 // host-buffer batched path: chunks alternate between two streams so H2D(c+1) overlaps compute(c) and D2H(c-1)
-int predict_many_host(mf_model *m, const void *in_q, const float *in_f32, size_t n, float *out_f32, void *out_q, void *logits, bool wait = true) {
+// single_piece: the whole call is ONE piece on ONE stream slot (the multi-device chunk loop pipelines its chunks itself)
+int predict_many_host(mf_model *m, const void *in_q, const float *in_f32, size_t n, float *out_f32, void *out_q, void *logits, bool wait = true,
+                      bool single_piece = false) {
     int rc = need_device(m);
     if (rc) return rc;
     if ((!in_q && !in_f32) || (!out_f32 && !out_q)) return fail(MF_ERR_INVALID_ARG, "null input or output buffer");
@@ -568,6 +570,7 @@ int predict_many_host(mf_model *m, const void *in_q, const float *in_f32, size_t
     static const int env_piece = [] { const char *e = std::getenv("MF_HOST_PIECE"); return e ? std::atoi(e) : 0; }();
     const size_t cap = env_piece > 0 ? (size_t)env_piece : (wait ? 2048 : 4096);
     if (piece > cap) piece = cap;
+    if (single_piece) piece = std::min(m->chunk, n);
     size_t ci = m->slot_rr;
     for (size_t off = 0; off < n; off += piece, ++ci) {
         Slot &s = m->slot[ci & 1];
@@ -838,7 +841,7 @@ int group_predict_many(mf_model *g, const void *in_q, const float *in_f32, size_
                     const size_t slot = rep->slot_rr & 1;            // the stream slot predict_many_host is about to use for this chunk
                     rc = predict_many_host(rep, in_q ? (const uint8_t *)in_q + lo * ie : nullptr, in_f32 ? in_f32 + lo * ie : nullptr, cn,
                                            out_f32 ? out_f32 + lo * oe : nullptr, out_q ? (uint8_t *)out_q + lo * oe : nullptr,
-                                           logits ? (uint8_t *)logits + lo * le : nullptr, /*wait=*/false);
+                                           logits ? (uint8_t *)logits + lo * le : nullptr, /*wait=*/false, /*single_piece=*/true);
                     if (rc) break;
                     // two chunks in flight per GPU: before claiming another one, wait for the chunk enqueued before this one
                     if (k >= 1 && (cudaSetDevice(rep->device) != cudaSuccess || cudaStreamSynchronize(rep->slot[slot ^ 1].stream) != cudaSuccess)) {
