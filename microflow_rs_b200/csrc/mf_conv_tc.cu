@@ -336,6 +336,197 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
+// 3x3 convolution on CTA PAIRS (tcgen05.mma.cta_group::2)
+// ------------------------------------------------------------------------------------------------
+// Why: the one-CTA M128 x N128 x K32 int8 instruction reads 4 KB of A and 4 KB of B from shared memory every 66 clocks -- 124 of the
+// 128 B/clk the shared-memory port delivers (tools/ubench/mma_i8.cu: 4 423 TOP/s MMA-only) -- so every TMA write and epilogue table
+// load steals tensor-core time; the kernel above stops at 60 % of that ceiling.  A pair of CTAs on one TPC shares the B operand:
+// each keeps the weights of HALF of the output channels (72 KB instead of 147 KB: six pipeline stages instead of three), one thread of
+// the even CTA issues M256 x N128 x K32 instructions that run on both SMs' tensor cores, and each SM reads 4 KB of A + 2 KB of B per
+// instruction.  Everything else is the one-CTA kernel's: single-patch A staging by TMA (every tap a descriptor offset), zero-filled
+// borders + per-class correction table, 16 epilogue warps per CTA with the exact f32 requantize.
+//   barriers the LEADER waits on are fed by both CTAs: full[s] (TMA transaction bytes of both patches, cp.async.bulk.tensor
+//   .cta_group::2 with the leader's mbarrier), bfull (both weight halves), tempty[a] (2 x 16 epilogue warps, the odd CTA's by
+//   mapa + remote arrive); completions are multicast: tcgen05.commit.cta_group::2...multicast::cluster on empty[s] and tfull[a].
+template <bool BIG, bool XU>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ ConvTcTables tab,
+                    const ConvTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    const uint32_t NH = (uint32_t)p.N >> 1;                                   // output channels whose weights this CTA holds
+    const uint32_t bblk = NH * 128u;                                          // one tap's weight block: [N/2][128 B]
+    uint8_t *sB = smem;
+    uint8_t *sA = sB + 9u * bblk;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + (size_t)p.stages * p.stage_bytes);
+    float *s_c0z = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(bars) + 256);
+    float *s_c1 = s_c0z + p.N;
+    int32_t *s_corr = reinterpret_cast<int32_t *>(s_c1 + p.N);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 9);
+
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](uint32_t s) { return bar0 + 8u * (kMaxStages + s); };
+    const uint32_t bfull_bar = bar0 + 8u * (2 * kMaxStages);
+    auto tfull_bar = [&](uint32_t a) { return bar0 + 8u * (2 * kMaxStages + 1 + a); };
+    auto tempty_bar = [&](uint32_t a) { return bar0 + 8u * (2 * kMaxStages + 5 + a); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                                  // 0 = leader (issues the MMAs)
+    const uint32_t npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+    const uint32_t ntiles = (uint32_t)p.num_tiles;
+
+    if (warp == kWarpTma && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_b)) : "memory");
+    }
+    if (warp == kWarpMma && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+        mbar_init(bfull_bar, 2);
+        for (uint32_t a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kWarpAlloc) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    if (warp < kEpiWarps) {
+        for (int k = threadIdx.x; k < p.N; k += 32 * kEpiWarps) { s_c0z[k] = tab.c0z[k]; s_c1[k] = tab.c1[k]; }
+        for (int k = threadIdx.x; k < p.ncls * p.N; k += 32 * kEpiWarps) s_corr[k] = tab.corr[k];
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                      // both CTAs' barriers exist before any remote arrive / transaction
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+
+    // tile of this CTA in round t: 2 * t + rank; the odd CTA of the last pair may have none (it then recomputes the last tile and
+    // stores nothing, so that the pair's barrier protocol stays symmetric)
+    auto tile_of = [&](uint32_t t, bool &valid) {
+        const uint32_t mine = 2u * t + rank;
+        valid = mine < ntiles;
+        return valid ? mine : ntiles - 1u;
+    };
+
+    if (warp == kWarpTma) {
+        if (lane == 0) {
+            // ===== TMA producer (both CTAs; transaction bytes are counted on the leader's barriers) =====
+            const uint32_t l_bfull = mapa_rank(bfull_bar, 0);
+            mbar_expect_tx_cluster(l_bfull, 9u * bblk);
+            for (uint32_t kb = 0; kb < 9; ++kb) tma_load_2d_pair(smem_u32(sB + (size_t)kb * bblk), &tmap_b, l_bfull, (int)(kb * 128), (int)(rank * NH));
+            pdl_wait();
+            uint32_t s = 0, ph = 0;
+            for (uint32_t t = pair; 2u * t < ntiles; t += npairs) {
+                bool valid;
+                const uint32_t tile = tile_of(t, valid);
+                uint32_t b, rem, ty, tx;
+                p.fd_img.divmod(tile, b, rem);
+                p.fd_tx.divmod(rem, ty, tx);
+                mbar_wait(empty_bar(s), ph ^ 1);
+                const uint32_t l_full = mapa_rank(full_bar(s), 0);
+                mbar_expect_tx_cluster(l_full, p.stage_tx);
+                tma_load_4d_pair(smem_u32(sA + (size_t)s * p.stage_bytes), &tmap_a, l_full, 0, (int)tx * p.TW - p.off_c, (int)ty * p.TH - p.off_r, (int)b);
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == kWarpMma) {
+        if (lane == 0 && rank == 0) {
+            // ===== MMA issuer (leader CTA only) =====
+            mbar_wait(bfull_bar, 0);
+            tc_fence_after();
+            uint32_t s = 0, ph = 0, it = 0;
+            const uint64_t desc_hi = make_desc(0);
+            const uint64_t desc_a = make_desc(0, p.patch_w * 128u);
+            const uint32_t a0 = smem_u32(sA) >> 4, b0 = smem_u32(sB) >> 4;
+            const uint32_t stage16 = p.stage_bytes >> 4, bblk16 = bblk >> 4;
+            for (uint32_t t = pair; 2u * t < ntiles; t += npairs, ++it) {
+                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+                mbar_wait(tempty_bar(acc), aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.N;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint64_t adesc = desc_a | (uint64_t)(a0 + s * stage16);
+                const uint64_t bdesc = desc_hi | (uint64_t)b0;
+                uint32_t accumulate = 0;
+#pragma unroll
+                for (int m = 0; m < 3; ++m)
+#pragma unroll
+                    for (int n = 0; n < 3; ++n)
+#pragma unroll
+                        for (uint32_t ks = 0; ks < 4; ++ks) {
+                            tc_mma_i8_pair(d_tmem, adesc + (uint64_t)(((uint32_t)m * p.patch_w + (uint32_t)n) * 8u + 2 * ks),
+                                           bdesc + (uint64_t)((uint32_t)(m * 3 + n) * bblk16 + 2 * ks), p.idesc, accumulate);
+                            accumulate = 1;
+                        }
+                tc_commit_pair(empty_bar(s));            // both CTAs' slot s is free once these MMAs retire
+                if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
+                tc_commit_pair(tfull_bar(acc));          // both CTAs' accumulator halves are complete
+            }
+        }
+    } else if (warp < kEpiWarps) {
+        // ===== epilogue (both CTAs, each on its own 128 accumulator rows = its own tile) =====
+        const uint32_t q = (uint32_t)(warp & 3);
+        const int cg = warp >> 2;
+        const int row = (int)(q * 32 + lane);
+        const int rr = row >> p.tw_log2, rc = row & (p.TW - 1);
+        pdl_wait();
+        uint32_t it = 0;
+        for (uint32_t t = pair; 2u * t < ntiles; t += npairs, ++it) {
+            const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+            bool tvalid;
+            const uint32_t tile = tile_of(t, tvalid);
+            uint32_t b, rem, ty, tx;
+            p.fd_img.divmod(tile, b, rem);
+            p.fd_tx.divmod(rem, ty, tx);
+            const long long oy = (long long)ty * p.TH + rr, ox = (long long)tx * p.TW + rc;
+            const bool valid = tvalid && oy < p.OH && ox < p.OW;
+            const int cls = 3 * (oy == 0 ? 0 : (oy == p.OH - 1 ? 2 : 1)) + (ox == 0 ? 0 : (ox == p.OW - 1 ? 2 : 1));
+            const int32_t *corr = s_corr + cls * p.N;
+            uint8_t *orow = p.out + (((long long)b * p.OH + oy) * p.OW + ox) * p.N;
+            mbar_wait(tfull_bar(acc), aph);
+            tc_fence_after();
+            const uint32_t t_base = tmem_base + acc * (uint32_t)p.N + ((q * 32u) << 16);
+            for (int c0 = 32 * cg; c0 < p.N; c0 += 128) {
+                uint32_t r[32];
+                tmem_ld32(t_base + (uint32_t)c0, r);
+                uint32_t w[8];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const float4 z = *reinterpret_cast<const float4 *>(s_c0z + c0 + 4 * g);
+                    const float4 sc = *reinterpret_cast<const float4 *>(s_c1 + c0 + 4 * g);
+                    const int4 kc = *reinterpret_cast<const int4 *>(corr + c0 + 4 * g);
+                    if (XU && !BIG) {
+                        w[g] = requant4_biased<true>((int)r[4 * g] + kc.x, (int)r[4 * g + 1] + kc.y, (int)r[4 * g + 2] + kc.z, (int)r[4 * g + 3] + kc.w, z, sc, p.lo, p.hi);
+                    } else if (XU) {
+                        w[g] = requant4_i2f((int)r[4 * g] - kc.x, (int)r[4 * g + 1] - kc.y, (int)r[4 * g + 2] - kc.z, (int)r[4 * g + 3] - kc.w, z, sc);
+                    } else {
+                        w[g] = pack4(requant_nx<BIG>((int)r[4 * g] - kc.x, z.x, sc.x, p.lo, p.hi), requant_nx<BIG>((int)r[4 * g + 1] - kc.y, z.y, sc.y, p.lo, p.hi),
+                                     requant_nx<BIG>((int)r[4 * g + 2] - kc.z, z.z, sc.z, p.lo, p.hi), requant_nx<BIG>((int)r[4 * g + 3] - kc.w, z.w, sc.w, p.lo, p.hi));
+                    }
+                }
+                if (valid)
+                    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow + c0), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                                 : "memory");
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));      // the leader's MMA thread counts both CTAs' epilogue warps
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                      // no CTA of the pair leaves (or frees TMEM) while the other may still signal it
+    if (warp == kWarpAlloc) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -445,6 +636,24 @@ bool conv_tc_finalize_plan(ConvTcPlan &p, std::string *why) {
     if (!encode_map(&m, p.d_wmat, 2, dims, strides, box, why)) return false;
     static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
     std::memcpy(p.tmap_b, &m, sizeof m);
+    // CTA-pair variant of the 3x3 kernel: one 128-byte channel block, single-patch staging, the weights split by output channel
+    p.pair_ok = false;
+    if (p.KH == 3 && p.KW == 3 && p.CB == 1 && p.patch && p.ncls == 9 && p.N % 64 == 0) {
+        const size_t b_half = (size_t)9 * (p.N / 2) * 128;
+        const size_t stage = (((size_t)(p.TH + 2) * (p.TW + 2) * 128) + 1023) & ~(size_t)1023;
+        const size_t fixed = b_half + 256 + (size_t)p.N * 8 + (size_t)9 * p.N * 4;
+        int st = 0;
+        for (int k = kMaxStages; k >= 2; --k)
+            if (fixed + stage * k <= kSmemLimit) { st = k; break; }
+        cuuint32_t box_h[2] = {128, (cuuint32_t)(p.N / 2)};
+        CUtensorMap mh;
+        if (st && encode_map(&mh, p.d_wmat, 2, dims, strides, box_h, nullptr)) {
+            std::memcpy(p.tmap_b_half, &mh, sizeof mh);
+            p.pair_ok = true;
+            p.pair_stages = st;
+            p.pair_smem_bytes = fixed + stage * st;
+        }
+    }
     return true;
 }
 
@@ -565,6 +774,36 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
             if (e != cudaSuccess) return e;
             attr_done.emplace_back(dev, fn);
         }
+    }
+    // 3x3 layers on CTA pairs (conv3x3_pair_kernel) with MF_TC_PAIR=1.  Measured equal to the one-CTA kernel on BASELINE config 5
+    // (0.0900 vs 0.0894 ms at batch 16, profiles/r02d_conv3x3_experiments.txt): the layer is bound by its epilogue, not by the
+    // shared-memory reads the pair halves -- so the simpler kernel stays the default and this one is kept, tested, for layers whose
+    // weights do not fit one SM (Cout = 256: 288 KB) and as the basis of the next step named in DESIGN.md.
+    static const int env_pair = [] { const char *e = std::getenv("MF_TC_PAIR"); return e ? std::atoi(e) : 0; }();
+    if (env_pair && shape == 1 && p.pair_ok && p.patch && k.num_tiles >= 2 && num_sms >= 2) {
+        KernelFn pf = p.big_acc ? (xu ? conv3x3_pair_kernel<true, true> : conv3x3_pair_kernel<true, false>)
+                                : (xu ? conv3x3_pair_kernel<false, true> : conv3x3_pair_kernel<false, false>);
+        CUtensorMap tbh;
+        std::memcpy(&tbh, p.tmap_b_half, sizeof tbh);
+        ConvTcParams kp = k;
+        kp.stages = p.pair_stages;
+        kp.idesc = (2u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.N >> 3) << 17) | ((256u >> 4) << 24);     // M = 256 across the pair
+        {
+            int dev = 0;
+            cudaError_t e = cudaGetDevice(&dev);
+            if (e != cudaSuccess) return e;
+            std::lock_guard<std::mutex> lock(attr_mu);
+            bool have = false;
+            for (auto &f : attr_done) have = have || (f.first == dev && f.second == pf);
+            if (!have) {
+                e = cudaFuncSetAttribute(pf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
+                if (e != cudaSuccess) return e;
+                attr_done.emplace_back(dev, pf);
+            }
+        }
+        const long long pairs_needed = (k.num_tiles + 1) / 2;
+        long long ctas = 2 * (pairs_needed < num_sms / 2 ? pairs_needed : num_sms / 2);
+        return launch_pdl(pf, dim3((unsigned)ctas), dim3(kThreads), p.pair_smem_bytes, s, l.pdl, ta, tbh, tab, kp);
     }
     const unsigned grid = (unsigned)(k.num_tiles < num_sms ? k.num_tiles : num_sms);
     return launch_pdl(fn, dim3(grid), dim3(kThreads), p.smem_bytes, s, l.pdl, ta, tb, tab, k);

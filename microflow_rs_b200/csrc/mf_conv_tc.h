@@ -48,6 +48,12 @@ struct ConvTcPlan {
     bool big_acc = false;              // |acc - corr| may exceed 2^22: use the general exact int->float in the epilogue
     bool is_u8 = false;                // uint8 activations and weights: unsigned operand formats in the instruction descriptor
     alignas(64) unsigned char tmap_b[128];  // CUtensorMap of the weight matrix
+    // 3x3 layers with Cin == 128 and Cout % 64 == 0 can run on CTA PAIRS (conv3x3_pair_kernel: tcgen05.mma.cta_group::2, M = 256):
+    // each CTA of the pair keeps HALF of the output channels' weights (box {128, N/2}) and reads A + B/2 per instruction
+    bool pair_ok = false;
+    int pair_stages = 0;
+    size_t pair_smem_bytes = 0;
+    alignas(64) unsigned char tmap_b_half[128];
 };
 
 struct ConvTcLaunch {

@@ -23,15 +23,18 @@ __device__ __forceinline__ void mma_i8(uint32_t d, uint64_t a, uint64_t b, uint3
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 
-template <int N>
-__global__ void __launch_bounds__(128, 1) mma_kernel(int iters, long long *cycles) {
+// LD_WARPS > 0: that many extra warps (4 per TMEM lane quarter) read the accumulators with tcgen05.ld.32x32b.x32 in a loop while the
+// MMAs run -- does epilogue-style TMEM traffic slow the tensor pipe (and how fast are the loads under MMA load)?
+template <int N, int LD_WARPS>
+__global__ void __launch_bounds__(128 + 32 * LD_WARPS, 1) mma_kernel(int iters, long long *cycles, unsigned *sink, unsigned long long *ld_count) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar[4];
+    __shared__ uint64_t bar[8];
     __shared__ uint32_t tmem_slot;
     uint8_t *sA = smem, *sB = smem + 16384;
     for (int i = threadIdx.x; i < (16384 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x01010101u * (uint32_t)(i & 3);
     const uint32_t bar_a = smem_u32(&bar[0]);
     if (threadIdx.x == 0) {
+        reinterpret_cast<volatile unsigned *>(&bar[3])[4] = 0;
         for (int k = 0; k < 4; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a + 8 * k) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -64,39 +67,69 @@ __global__ void __launch_bounds__(128, 1) mma_kernel(int iters, long long *cycle
         }
         for (int b = iters >= 2 ? iters - 2 : 0; b < iters; ++b) wait_batch(b);
         cycles[blockIdx.x] = clock64() - t0;
+        reinterpret_cast<volatile unsigned *>(&bar[3])[4] = 1;
+    }
+    if (LD_WARPS > 0 && threadIdx.x >= 128) {
+        const unsigned q = (threadIdx.x >> 5) & 3;
+        volatile unsigned *flag = reinterpret_cast<volatile unsigned *>(&bar[3]) + 4;   // set by thread 0 when it is done (spare shared word)
+        unsigned acc = 0;
+        unsigned long long n = 0;
+        while (*flag == 0) {
+            unsigned r[32];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                           "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+                           "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                         : "r"(tmem + ((q * 32u) << 16) + (unsigned)((n & 3) * 32))
+                         : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < 32; ++k) acc ^= r[k];
+            ++n;
+        }
+        if (acc == 0x12345u) sink[0] = acc;
+        if ((threadIdx.x & 31) == 0) atomicAdd(ld_count, n);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
-template <int N> static void run(int iters, int sms) {
+template <int N, int LD_WARPS> static void run(int iters, int sms) {
     long long *cyc;
+    unsigned *sink;
+    unsigned long long *ldc;
     cudaMalloc(&cyc, sms * sizeof(long long));
+    cudaMalloc(&sink, 4);
+    cudaMalloc(&ldc, 8);
     const size_t smem = 16384 + (size_t)N * 128;
-    cudaFuncSetAttribute(mma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(mma_kernel<N, LD_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    mma_kernel<N><<<sms, 128, smem>>>(iters / 8 + 1, cyc);
+    mma_kernel<N, LD_WARPS><<<sms, 128 + 32 * LD_WARPS, smem>>>(iters / 8 + 1, cyc, sink, ldc);
     cudaDeviceSynchronize();
     float best = 1e30f;
+    unsigned long long loads = 0;
     for (int rep = 0; rep < 5; ++rep) {
+        cudaMemset(ldc, 0, 8);
         cudaEventRecord(e0);
-        mma_kernel<N><<<sms, 128, smem>>>(iters, cyc);
+        mma_kernel<N, LD_WARPS><<<sms, 128 + 32 * LD_WARPS, smem>>>(iters, cyc, sink, ldc);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms;
         cudaEventElapsedTime(&ms, e0, e1);
-        if (ms < best) best = ms;
+        if (ms < best) { best = ms; cudaMemcpy(&loads, ldc, 8, cudaMemcpyDeviceToHost); }
     }
     cudaError_t e = cudaDeviceSynchronize();
     long long c0 = 0;
     cudaMemcpy(&c0, cyc, sizeof c0, cudaMemcpyDeviceToHost);
     const double ops = 2.0 * 128.0 * N * 32.0 * 64.0 * iters * sms;
-    printf("tcgen05.mma.cta_group::1.kind::i8 M128 N%-3d K32: %8.3f ms for %d x 64 instructions/SM on %d SMs -> %8.1f TOP/s  (%.1f clk per instruction on SM 0, %s)\n", N,
-           best, iters, sms, ops / (best * 1e-3) / 1e12, (double)c0 / (64.0 * iters), cudaGetErrorString(e));
-    cudaFree(cyc);
+    printf("tcgen05.mma.cta_group::1.kind::i8 M128 N%-3d K32, %2d warps of tcgen05.ld: %8.3f ms -> %8.1f TOP/s  (%.1f clk per MMA on SM 0", N, LD_WARPS, best,
+           ops / (best * 1e-3) / 1e12, (double)c0 / (64.0 * iters));
+    if (LD_WARPS) printf("; %.1f clk per 32x32 tcgen05.ld per warp", (double)c0 * LD_WARPS / ((double)loads / sms));
+    printf(", %s)\n", cudaGetErrorString(e));
+    cudaFree(cyc); cudaFree(sink); cudaFree(ldc);
 }
 
 int main(int argc, char **argv) {
@@ -104,8 +137,10 @@ int main(int argc, char **argv) {
     cudaDeviceProp p;
     cudaGetDeviceProperties(&p, 0);
     printf("%s, %d SMs, SM clock max %d MHz\n", p.name, p.multiProcessorCount, p.clockRate / 1000);
-    run<64>(iters, p.multiProcessorCount);
-    run<128>(iters, p.multiProcessorCount);
-    run<256>(iters, p.multiProcessorCount);
+    run<64, 0>(iters, p.multiProcessorCount);
+    run<128, 0>(iters, p.multiProcessorCount);
+    run<256, 0>(iters, p.multiProcessorCount);
+    run<128, 4>(iters, p.multiProcessorCount);
+    run<128, 16>(iters, p.multiProcessorCount);
     return 0;
 }
