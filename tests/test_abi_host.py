@@ -143,7 +143,7 @@ def test_sass_epilogues_are_never_contracted_into_fma():
     into FFMA2 even under -fmad=false, so the machine code of every conv / depthwise / fully-connected kernel is
     checked: no FFMA, no FFMA2.  (The pool, softmax, quantize and classifier-tail kernels contain FFMAs inside __fdiv_rn.)"""
     funcs = _sass_by_function()
-    hot = {n: body for n, body in funcs.items() if re.search(r"conv_tc_kernel|dwconv|pwconv|conv_generic|fc_generic|layout_transpose", n)}
+    hot = {n: body for n, body in funcs.items() if re.search(r"conv_tc_kernel|conv3x3_pair_kernel|fused_chain_kernel|dwconv|pwconv|conv_generic|fc_generic|layout_transpose", n)}
     assert len(hot) >= 20, sorted(funcs)
     for name, body in hot.items():
         bad = [ln for ln in body if re.search(r"\bFFMA2?\b", ln)]
@@ -158,6 +158,10 @@ def test_sass_shows_the_blackwell_paths():
     tc = [t for n, t in text.items() if "conv_tc_kernel" in n]
     assert tc and all("UTCIMMA" in t and "UTMALDG" in t and "LDTM" in t for t in tc)
     assert any("STG.E.ENL2.256" in t for t in tc)
+    pair = [t for n, t in text.items() if re.search(r"(?<!dw)conv3x3_pair_kernel", n)]
+    assert pair and all("UTCIMMA.2CTA" in t and "UTMALDG" in t and "LDTM" in t for t in pair)          # tcgen05.mma.cta_group::2 on CTA pairs
+    chain = [t for n, t in text.items() if "fused_chain_kernel" in n]
+    assert chain and all("UTCIMMA" in t and "UBLKCP" in t and "LDTM" in t and "IDP.4A" in t and "FADD2" in t for t in chain)
     dw = [t for n, t in text.items() if re.search(r"dwconv3x3_(smem|pair)_kernel|dwconv_cin1_smem_kernel", n)]
     assert dw and all("UBLKCP" in t and "IDP.4A" in t and "FADD2" in t for t in dw)
 

@@ -10,8 +10,9 @@ pytestmark = pytest.mark.gpu
 HERE = Path(__file__).resolve().parent
 
 
-def _run(which):
-    p = subprocess.run([sys.executable, str(HERE / "tc_check.py"), which], capture_output=True, text=True, timeout=300)
+def _run(which, env=None):
+    import os
+    p = subprocess.run([sys.executable, str(HERE / "tc_check.py"), which], capture_output=True, text=True, timeout=300, env=dict(os.environ, **(env or {})))
     lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
     assert lines, f"no result (rc={p.returncode})\nstdout:\n{p.stdout[-2000:]}\nstderr:\n{p.stderr[-3000:]}"
     res = json.loads(lines[-1])
@@ -24,6 +25,12 @@ def test_tc_pointwise_packed_gemm():
 
 def test_tc_conv3x3_implicit_gemm():
     _run("conv3x3")
+
+
+def test_tc_conv3x3_on_cta_pairs():
+    """MF_TC_PAIR=1: the same shapes through conv3x3_pair_kernel (thread-block clusters of 2, tcgen05.mma.cta_group::2, weights split by
+    output channel between the two CTAs); tc_check asserts that the eligible shapes really ran on it."""
+    _run("conv3x3", env={"MF_TC_PAIR": "1"})
 
 
 def test_config5_full_size_image_vs_oracle():
