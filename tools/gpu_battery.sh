@@ -11,6 +11,7 @@ if has tests; then
   timeout 700 python -m pytest tests/test_gpu_ops.py -q -m gpu 2>&1 | tail -40 > gpurun_out/t_ops.log
   timeout 900 python -m pytest tests/test_gpu_models.py -q -m gpu 2>&1 | tail -60 > gpurun_out/t_models.log
   timeout 300 python -m pytest tests/test_gpu_multidevice.py -q -m gpu 2>&1 | tail -20 > gpurun_out/t_multi.log
+  timeout 900 python -m pytest tests/test_gpu_fused.py -q -m gpu 2>&1 | tail -20 > gpurun_out/t_fused.log
   timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 fi
 if has bench; then
@@ -19,7 +20,7 @@ if has bench; then
   for c in 1024 2048 8192; do
     timeout 200 python bench.py --steps 10 --warmup 3 --chunk $c --no-cpu-baseline --no-conv2d > gpurun_out/bench_pd_chunk$c.json 2>> gpurun_out/bench_pd.err
   done
-  timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+  timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 fi
 if has prof; then
   timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
@@ -33,10 +34,12 @@ if has prof; then
       python tools/layer_bench.py 8192 L6_pw32_32 > gpurun_out/ncu_tc.log 2>&1
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 10 -c 1 -f -o gpurun_out/prof_tc_pw128 \
       python tools/layer_bench.py 8192 L14_pw128 > gpurun_out/ncu_tc128.log 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:fused_chain -s 3 -c 1 -f -o gpurun_out/prof_fused \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-conv2d > gpurun_out/ncu_fused.log 2>&1
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 5 -c 1 -f -o gpurun_out/prof_conv3x3 \
       python -m microflow_rs_b200._convbench 16 4 > gpurun_out/ncu_conv3x3.log 2>&1
 fi
-tail -n 4 gpurun_out/t_tc.log gpurun_out/t_ops.log gpurun_out/t_models.log gpurun_out/t_multi.log gpurun_out/smoke.log 2>/dev/null
+tail -n 4 gpurun_out/t_tc.log gpurun_out/t_ops.log gpurun_out/t_models.log gpurun_out/t_multi.log gpurun_out/t_fused.log gpurun_out/smoke.log 2>/dev/null
 for f in gpurun_out/bench_pd.json gpurun_out/bench_speech.json gpurun_out/bench_pd_chunk*.json gpurun_out/bench_ref.json; do
   [ -f "$f" ] && python - "$f" <<'PY'
 import json, sys

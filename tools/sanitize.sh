@@ -20,6 +20,27 @@ for name, n in (("person_detect", 300), ("speech", 40), ("sine", 70)):
     g = mf.Model(MODELS / f"{name}.tflite", flags=mf.FLAG_FORCE_GENERIC)
     assert np.array_equal(g.predict_many_quantized(xs[:16]), a[:16]), name
     m.close(); g.close()
+# fused low-resolution chain at a batch with partial units, the CTA-pair 3x3 kernel, a two-replica multi-device model
+import os
+r = np.random.default_rng(1)
+sys.path.insert(0, str(ROOT / "tests"))
+import fused_check
+layers = fused_check.make_chain(r, 6, 6, 5)
+x = r.integers(-128, 128, (23, 6, 6, 128)).astype(np.int8)
+assert np.array_equal(mf.ops.conv_chain(x, layers, fuse=True), mf.ops.conv_chain(x, layers, fuse=False))
+os.environ["MF_TC_PAIR"] = "1"
+x3 = r.integers(-128, 128, (2, 24, 16, 128)).astype(np.int8)
+w3 = r.integers(-128, 128, (128, 3, 3, 128)).astype(np.int8)
+c1 = (r.uniform(0.2, 2.0, 128) / 40000.0).astype(np.float32); c0 = r.uniform(-20, 20, 128).astype(np.float32)
+a3 = mf.ops.conv_2d(x3, -128, w3, [0], 0.0235294, -128, "relu6", "same", (1, 1), c0, c1, (24, 16), impl=0)
+assert "conv3x3_pair_kernel" in mf.ops.last_kernel, mf.ops.last_kernel
+assert np.array_equal(a3, mf.ops.conv_2d(x3, -128, w3, [0], 0.0235294, -128, "relu6", "same", (1, 1), c0, c1, (24, 16), impl=1))
+os.environ["MF_ALLOW_DUPLICATE_DEVICES"] = "1"
+g = mf.Model(MODELS / "speech.tflite", devices=[0, 0])
+one = mf.Model(MODELS / "speech.tflite")
+xs = splitmix_bytes(9, 300 * g.in_elems).reshape(300, -1)
+assert np.array_equal(g.predict_many_quantized(xs), one.predict_many_quantized(xs))
+g.close(); one.close()
 print("workload ok")
 PY
 for tool in memcheck racecheck synccheck; do
