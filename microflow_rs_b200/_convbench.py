@@ -37,10 +37,19 @@ def run(torch, w, c0, c1, in_zp, out_zp, out_scale, H, W, batch, steps, warmup, 
     ops = 2.0 * fast.macs * batch
     tops = ops / (ms * 1e-3) / 1e12
     peak = 2.0 * peaks["bf16_tflops"]
+    traffic = None
+    try:   # dram__bytes_read + write of one launch at batch 16 from the committed ncu capture (profiles/r02e_conv3x3.txt)
+        import json
+        from pathlib import Path
+        traffic = json.loads((Path(__file__).resolve().parent.parent / "profiles" / "traffic_latest.json").read_text()).get("conv_tc_kernel(3x3)") if batch == 16 else None
+    except Exception:
+        traffic = None
+    mma_only = 4423.0   # tools/ubench/mma_i8.cu on this pool's B200: tcgen05.mma kind::i8 M128 N128 K32 back to back, no TMA, no epilogue (profiles/r02d)
     res.update({"ms_per_launch": ms, "images_per_s": batch / (ms * 1e-3),
-                "roofline": {"bound": "tensor", "achieved": tops, "peak": peak, "unit": "TOP/s", "frac": tops / peak, "traffic": None,
-                             "peak_source": "2 x measured cuBLAS bf16 burst TFLOP/s (tcgen05 kind::i8 issues 2x the bf16 MAC rate); nominal dense int8 is 4500",
-                             "frac_of_nominal_4500": tops / 4500.0},
+                "roofline": {"bound": "tensor", "achieved": tops, "peak": peak, "unit": "TOP/s", "frac": tops / peak, "traffic": traffic,
+                             "peak_source": "2 x measured cuBLAS bf16 burst TFLOP/s (tcgen05 kind::i8 issues 2x the bf16 MAC rate); nominal dense int8 is 4500; "
+                                            "the MMA-only ceiling of this instruction shape measured by tools/ubench/mma_i8.cu is 4423 TOP/s",
+                             "frac_of_nominal_4500": tops / 4500.0, "frac_of_mma_only_ceiling_4423": tops / mma_only},
                 "l2": f"input+output per launch {(x[0].numel() + y.numel()) / 1e6:.0f} MB > 126 MB L2; inputs alternate between 2 buffers",
                 "algorithmic_bytes_per_launch": int(x[0].numel() + y.numel() + fast.weight_bytes)})
     fast.close()
