@@ -541,6 +541,16 @@ def main():
             g["bytes"] += (L["bytes"] - L["weight_bytes"]) * batch * args.steps + L["weight_bytes"] * args.steps
             g["macs"] += L["macs"] * batch * args.steps
             g["launches"] += 0 if inside else 1
+            # compulsory traffic of a launch: what enters it and what leaves it (for a fused launch the tensors between its layers never
+            # reach HBM; for a one-layer launch this equals the algorithmic figure minus nothing)
+            in_b = int(np.prod(L["in_shape"])) if L["in_shape"] else 0
+            if not inside:
+                g.setdefault("comp", 0)
+                g["comp"] += (in_b + L["out_elems"]) * batch * args.steps
+                g["_last_out"] = L["out_elems"]
+            else:
+                g["comp"] += (L["out_elems"] - g["_last_out"]) * batch * args.steps     # the launch's output is its LAST layer's output
+                g["_last_out"] = L["out_elems"]
         total_layer_ms = sum(g["ms"] for g in groups.values()) or 1.0
         dom_name, dom = max(groups.items(), key=lambda kv: kv[1]["ms"])
         achieved = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
@@ -560,6 +570,7 @@ def main():
                     "note": "achieved = algorithmic bytes (layer input+output per sample x batch + weights once per launch) of this kernel's layers / its summed "
                             "CUDA-event time inside the timed region"}
         kernels = {k: {"ms_per_step": g["ms"] / args.steps, "share": g["ms"] / total_layer_ms, "GBps": g["bytes"] / (g["ms"] * 1e-3) / 1e9 if g["ms"] > 0 else None,
+                       "compulsory_GBps": g.get("comp", 0) / (g["ms"] * 1e-3) / 1e9 if g["ms"] > 0 else None,
                        "TOPS": 2 * g["macs"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else None} for k, g in groups.items()}
         line = {
             "metric": f"inferences/s {wl} int8", "value": value, "unit": "inferences/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
