@@ -201,3 +201,48 @@ def test_bmp_staging_reproduces_the_reference_features(samples):
         mf.features_from_bmp(b"BM" + b"\0" * 20)
     with pytest.raises(mf.MicroflowError):
         mf.features_from_bmp((GOLDEN / "person.bmp").read_bytes()[:5000])       # truncated pixel array
+
+
+def _patched_model(name, old_shape, new_shape, which=0):
+    """Returns the .tflite bytes with one int32 shape vector replaced (flatbuffer vector = length word + elements)."""
+    data = bytearray((MODELS / f"{name}.tflite").read_bytes())
+    pat = np.array([len(old_shape)] + list(old_shape), np.int32).tobytes()
+    hits = [i for i in range(len(data) - len(pat)) if data[i:i + len(pat)] == pat]
+    assert len(hits) > which, (name, old_shape, hits)
+    data[hits[which] + 4: hits[which] + 4 + 4 * len(new_shape)] = np.array(new_shape, np.int32).tobytes()
+    return bytes(data)
+
+
+def test_loader_rejects_batched_and_overflowing_shapes():
+    """The reference's ops take Tensor4D<T, 1, ...> (BATCHES = 1, src/ops/conv_2d.rs:40): a model whose op tensors carry a batch dimension
+    other than 1 would not type-check there and must not be silently mis-strided here; dimensions are untrusted, so products that
+    overflow are refused instead of wrapping to a small element count."""
+    # layer 0's output / layer 1's input [1,48,48,8] -> batch 2: element counts no longer chain, or the batch check fires
+    for which in (0, 1):
+        with pytest.raises(mf.MicroflowError) as e:
+            mf.Model(_patched_model("person_detect", [1, 48, 48, 8], [2, 48, 48, 8], which), flags=mf.FLAG_HOST_ONLY)
+        assert e.value.status in (7, 2), e.value
+    # the model input [1,96,96,1] -> batch 2 with layer 0 declaring the same: must be refused as an unsupported shape
+    with pytest.raises(mf.MicroflowError) as e:
+        mf.Model(_patched_model("person_detect", [1, 96, 96, 1], [2, 96, 96, 1]), flags=mf.FLAG_HOST_ONLY)
+    assert e.value.status == 7, e.value
+    # absurd dimensions: 2^31-1 squared overflows any size_t product check that is not done step by step
+    with pytest.raises(mf.MicroflowError) as e:
+        mf.Model(_patched_model("person_detect", [1, 96, 96, 1], [1, 2147483647, 2147483647, 1]), flags=mf.FLAG_HOST_ONLY)
+    assert e.value.status == 7, e.value
+    with pytest.raises(mf.MicroflowError):
+        mf.Model(_patched_model("person_detect", [1, 96, 96, 1], [1, -96, 96, 1]), flags=mf.FLAG_HOST_ONLY)
+
+
+def test_python_mirror_validates_caller_supplied_output_arrays():
+    """A wrong-sized, wrong-typed or non-contiguous `out=` must be refused before its raw pointer reaches the C side."""
+    m = mf.Model(MODELS / "sine.tflite", flags=mf.FLAG_HOST_ONLY)
+    xs = np.zeros((4, 1), np.int8)
+    for bad in (np.zeros((3, 1), np.float32), np.zeros((4, 1), np.float64), np.zeros((4, 2), np.float32)[:, ::2]):
+        with pytest.raises(ValueError):
+            m.predict_many_quantized(xs, out=bad)
+        with pytest.raises(ValueError):
+            m.predict_many_quantized_async(xs, bad)
+    with pytest.raises(ValueError):
+        m.predict_many_quantized_async(np.zeros((4, 1), np.float32), np.zeros((4, 1), np.float32))
+    m.close()
