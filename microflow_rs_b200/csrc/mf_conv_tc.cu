@@ -59,7 +59,7 @@ constexpr uint32_t kSmemLimit = 232448;  // 227 KB usable per CTA on sm_100
 // (A fourth mode -- kTabGroup for the 3x3 kernel with the eight non-interior border classes kept in shared memory as deltas -- removed
 // the epilogue's 32 % share of the L1/shared data pipe and was still slower, 0.138 vs 0.103 ms on BASELINE config 5; it is not kept:
 // profiles/r01j_conv3x3_experiments.txt.)
-enum { kTabSmem = 0, kTabGroup = 1, kTabPeriod = 2 };
+enum { kTabSmem = 0, kTabGroup = 1, kTabPeriod = 2, kTabGroupPB = 3, kTabPeriodPB = 4 };   // PB: + pre-biased accumulators in TMEM (below)
 struct ConvTcTables {
     float c0z[256];
     float c1[256];
@@ -84,10 +84,11 @@ struct ConvTcParams {
 // KH_T/KW_T/CB_T != 0: compile-time loop bounds, so the single MMA-issuing thread spends ~3 scalar instructions per MMA
 // (descriptor = base + constant); XU = F2I.S8 / I2F epilogue (needs the full int8 clamp range) instead of the XU-free one;
 // TAB = how the epilogue reads its per-channel tables (above).
-template <bool BIG, bool XU, int KH_T, int KW_T, int CB_T, int TAB>
+template <bool BIG, bool XU, int KH_T, int KW_T, int CB_T, int TABM>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ ConvTcTables tab,
                const ConvTcParams p) {
+    constexpr int TAB = TABM == kTabGroupPB ? kTabGroup : (TABM == kTabPeriodPB ? kTabPeriod : TABM);
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();   // SWIZZLE_128B atoms need a 1024-byte aligned base
     uint8_t *sB = smem;
@@ -110,6 +111,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // the 1x1 instantiations are only launched on a single row of (packed) pixels (TW = 128, H = B = 1; conv_tc_launch checks):
     // a tile index is its x coordinate and there are no border classes
     constexpr bool LINEAR = KH_T == 1 && KW_T == 1;
+    // Pre-biased accumulators in TMEM (constant-operand table modes of the packed pointwise GEMM): every epilogue warp owns fixed
+    // accumulator columns whose correction kAccBias - kcorr[column] is the same for every tile, so it keeps those 32 words in
+    // registers and writes them back into TMEM (one tcgen05.st) right after reading an accumulator; the MMAs of the next tile then
+    // ACCUMULATE onto them and the epilogue needs neither the integer add per value nor the table operand for it.
+    constexpr bool PREBIAS = (TABM == kTabPeriodPB || TABM == kTabGroupPB) && XU && !BIG;
 
     if (warp == kWarpTma && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
@@ -171,10 +177,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (a0 + (uint32_t)p.stages * stage16 >= (1u << 14) || b0 + p.nkb * bblk16 >= (1u << 14)) __trap();     // descriptor start field would overflow
             for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const uint32_t acc = it & 1, aph = (it >> 1) & 1;
-                mbar_wait(tempty_bar(acc), aph ^ 1);
+                mbar_wait(tempty_bar(acc), PREBIAS ? aph : (aph ^ 1));     // PREBIAS: phase 0 of each buffer is the epilogue warps' initial fill
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.N;
-                uint32_t accumulate = 0;
+                uint32_t accumulate = PREBIAS ? 1 : 0;
                 if (p.patch) {
                     // one stage per channel block holds the whole patch: tap (m, n) starts (m * patch_w + n) pixel rows into it and
                     // the 8-row groups of the tile (TW == 8: one tile row each) are patch_w rows apart (SBO)
@@ -231,6 +237,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int row = (int)(q * 32 + lane);
             const int rr = row >> p.tw_log2, rc = row & (p.TW - 1);
             const float lo = p.lo, hi = p.hi;
+            uint32_t kkr[32];
+            if (PREBIAS) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) kkr[j] = (uint32_t)tab.corr[(TAB == kTabPeriod ? 0 : 32 * CG) + j];
+                for (uint32_t a = 0; a < 2; ++a) {                  // both accumulator buffers start out holding the correction
+                    for (int c0 = 32 * cg; c0 < p.N; c0 += (TAB == kTabGroup ? 1 << 20 : 128)) tmem_st32(tmem_base + a * (uint32_t)p.N + ((q * 32u) << 16) + (uint32_t)c0, kkr);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(tempty_bar(0)); mbar_arrive(tempty_bar(1)); }
+            }
             pdl_wait();       // stores must not overtake the previous kernel's reads of the ping-pong buffer
             uint32_t it = 0;
             // LINEAR: this thread's row and output pointer advance by a constant per tile (no multiplies in the tile loop)
@@ -268,6 +286,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 for (int c0 = 32 * cg; c0 < p.N; c0 += (ONE_CHUNK ? 1 << 20 : 128)) {
                     uint32_t r[32];
                     tmem_ld32(t_base + (uint32_t)c0, r);
+                    if (PREBIAS) tmem_st32(t_base + (uint32_t)c0, kkr);     // re-arm the accumulator for the tile after next
                     uint32_t w[8];
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
@@ -288,7 +307,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             for (int u = 0; u < 4; ++u) {
                                 // kTabPeriod: the tables repeat every 32 columns; kTabGroup: N <= 128, this warp's only chunk is 32 * CG
                                 const int n = (TAB == kTabPeriod ? 0 : 32 * CG) + 4 * g + u;
-                                zz[u] = tab.c0z[n]; ss[u] = tab.c1[n]; kk[u] = tab.corr[n];
+                                zz[u] = tab.c0z[n]; ss[u] = tab.c1[n]; kk[u] = PREBIAS ? 0 : tab.corr[n];
                             }
                         }
                         if (PACKED) {
@@ -310,6 +329,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                      "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                                      : "memory");
                 }
+                if (PREBIAS) tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -756,8 +776,10 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     static const int env_tab = [] { const char *e = std::getenv("MF_TC_TAB"); return e ? std::atoi(e) : -1; }();
     if (shape == 2 && xu && !p.big_acc && p.ncls == 1 && env_tab != kTabSmem) {
         const bool periodic = p.Cout > 0 && 32 % p.Cout == 0 && p.N % p.Cout == 0 && p.P * p.Cout == p.N;
-        if (periodic && env_tab != kTabGroup) fn = conv_tc_kernel<false, true, 1, 1, 1, kTabPeriod>;
-        else if (p.N <= 128) fn = conv_tc_kernel<false, true, 1, 1, 1, kTabGroup>;
+        // MF_TC_PREBIAS=1: accumulators pre-biased in TMEM by the epilogue warps (see PREBIAS in the kernel)
+        static const bool env_pb = [] { const char *e = std::getenv("MF_TC_PREBIAS"); return e && std::atoi(e) != 0; }();
+        if (periodic && env_tab != kTabGroup) fn = env_pb ? conv_tc_kernel<false, true, 1, 1, 1, kTabPeriodPB> : conv_tc_kernel<false, true, 1, 1, 1, kTabPeriod>;
+        else if (p.N <= 128) fn = env_pb ? conv_tc_kernel<false, true, 1, 1, 1, kTabGroupPB> : conv_tc_kernel<false, true, 1, 1, 1, kTabGroup>;
     }
     // the opt-in to > 48 KB of dynamic shared memory is per device (context): remember it per (device, kernel)
     static std::mutex attr_mu;
