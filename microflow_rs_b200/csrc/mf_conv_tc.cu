@@ -75,6 +75,7 @@ struct ConvTcParams {
     float lo, hi;
     uint32_t idesc, stage_bytes, b_block_bytes, tmem_cols, nkb;
     uint32_t stage_tx;          // bytes one stage's TMA load delivers (== stage_bytes unless the stage is padded to 1024)
+    int out_u8;                 // outputs are uint8 (F2IP.U8 in the general epilogue)
     uint32_t patch, patch_w;    // single-patch mode (ConvTcPlan::patch) and its patch width TW + KW - 1 in pixels
 };
 
@@ -316,11 +317,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         } else if (XU) {        // any accumulator magnitude: I2F, then the same packed adds
                             w[g] = requant4_i2f((int)r[4 * g] - kk[0], (int)r[4 * g + 1] - kk[1], (int)r[4 * g + 2] - kk[2], (int)r[4 * g + 3] - kk[3],
                                                 make_float4(zz[0], zz[1], zz[2], zz[3]), make_float4(ss[0], ss[1], ss[2], ss[3]));
-                        } else {
-                            int y[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) y[u] = requant_nx<BIG>((int)r[4 * g + u] - kk[u], zz[u], ss[u], lo, hi);
-                            w[g] = pack4(y[0], y[1], y[2], y[3]);
+                        } else {                // any clamp range, int8 or uint8 outputs
+                            w[g] = requant4_clamp<BIG>((int)r[4 * g] - kk[0], (int)r[4 * g + 1] - kk[1], (int)r[4 * g + 2] - kk[2], (int)r[4 * g + 3] - kk[3],
+                                                       make_float4(zz[0], zz[1], zz[2], zz[3]), make_float4(ss[0], ss[1], ss[2], ss[3]), lo, hi, p.out_u8 != 0);
                         }
                     }
                     if (valid)     // the thread's 32 output bytes = one aligned 32-byte sector: a single 256-bit store (STG.256), so L2 sees
@@ -522,8 +521,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     } else if (XU) {
                         w[g] = requant4_i2f((int)r[4 * g] - kc.x, (int)r[4 * g + 1] - kc.y, (int)r[4 * g + 2] - kc.z, (int)r[4 * g + 3] - kc.w, z, sc);
                     } else {
-                        w[g] = pack4(requant_nx<BIG>((int)r[4 * g] - kc.x, z.x, sc.x, p.lo, p.hi), requant_nx<BIG>((int)r[4 * g + 1] - kc.y, z.y, sc.y, p.lo, p.hi),
-                                     requant_nx<BIG>((int)r[4 * g + 2] - kc.z, z.z, sc.z, p.lo, p.hi), requant_nx<BIG>((int)r[4 * g + 3] - kc.w, z.w, sc.w, p.lo, p.hi));
+                        w[g] = requant4_clamp<BIG>((int)r[4 * g] - kc.x, (int)r[4 * g + 1] - kc.y, (int)r[4 * g + 2] - kc.z, (int)r[4 * g + 3] - kc.w, z, sc, p.lo, p.hi, p.out_u8 != 0);
                     }
                 }
                 if (valid)
@@ -741,6 +739,7 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     k.stage_tx = (uint32_t)((p.TH + p.KH - 1) * box_w * 128);
     k.stage_bytes = p.patch ? ((k.stage_tx + 1023u) & ~1023u) : k.stage_tx;      // every stage base stays 1024-byte aligned (swizzle atom)
     k.patch = p.patch ? 1u : 0u;
+    k.out_u8 = p.is_u8 ? 1 : 0;
     k.patch_w = (uint32_t)(p.TW + p.KW - 1);
     k.b_block_bytes = (uint32_t)(p.N * 128);
     k.nkb = (uint32_t)(p.KH * p.KW * p.CB);

@@ -92,7 +92,8 @@ template <bool FULL> __device__ __forceinline__ int requant_xu(int acc, float c0
 //   * the two epilogue adds are packed FADD2 (add.rn.f32x2: two independent IEEE RN adds, one issue slot).  The multiply
 //     stays scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false (checked in SASS),
 //     which would round once instead of twice and break bit-exactness; FMUL + FADD2 is never contracted.
-//   4 values: 2 FADD2 + 4 FMUL + 2 FADD2 + 4 LOP3 + 2 FADD2 + 4 F2I.S8 + 3 PRMT = 21 issue slots (was 27).
+//   4 values: 2 FADD2 + 4 FMUL + 2 FADD2 + 4 LOP3 + 2 FADD2 + 2 F2IP.S8.F32 (f2i_pack4 below) = 16 issue slots and no XU-pipe
+//   instruction (round 1: 4 F2I.S8 + 3 PRMT in place of the 2 F2IP = 21 slots and 32 XU clocks).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kAccBias = 0x4B400000;   // bits of 1.5 * 2^23 = 12582912.0f
 
@@ -109,19 +110,38 @@ template <bool FULL> __device__ __forceinline__ int round_sat_s8(float s, float 
     asm("cvt.rzi.sat.s8.f32 %0, %1;" : "=r"(y) : "f"(s));      // trunc, saturate to int8, NaN -> 0 (Rust's `as i8`)
     return y;
 }
-// two pre-biased accumulators -> two values in [lo, hi]
-template <bool FULL> __device__ __forceinline__ void requant2_biased(int a0, int a1, float z0, float z1, float s0, float s1, float lo, float hi, int &y0, int &y1) {
+// Four floats -> four saturated bytes in one word (byte k = value k): trunc toward zero, saturate, NaN -> 0 -- bit for bit what four
+// cvt.rzi.sat.s8.f32 (F2I.S8) and three PRMT produce (checked over all 2^32 float patterns, tools/ubench/f2ip.cu).  ptxas fuses each
+// {cvt.rzi.s32.f32 x2, cvt.pack.sat.s8.s32.b32} into ONE F2IP.S8.F32.TRUNC.NTZ, which does not run on the quarter-rate XU pipe:
+// 2 issue slots per four values instead of 4 F2I.S8 (8 clocks each per sub-partition) + 3 PRMT (tests/test_abi_host.py pins the SASS).
+template <bool U8 = false> __device__ __forceinline__ uint32_t f2i_pack4(float a, float b, float c, float d) {
+    int ia, ib, ic, id;
+    uint32_t hi, r;
+    asm("cvt.rzi.s32.f32 %0, %1;" : "=r"(ia) : "f"(a));
+    asm("cvt.rzi.s32.f32 %0, %1;" : "=r"(ib) : "f"(b));
+    asm("cvt.rzi.s32.f32 %0, %1;" : "=r"(ic) : "f"(c));
+    asm("cvt.rzi.s32.f32 %0, %1;" : "=r"(id) : "f"(d));
+    if (U8) {
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(id), "r"(ic), "r"(0));
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(ib), "r"(ia), "r"(hi));
+    } else {
+        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(id), "r"(ic), "r"(0));
+        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(ib), "r"(ia), "r"(hi));
+    }
+    return r;
+}
+// two pre-biased accumulators -> two rounded values (still float; the caller converts four at a time with f2i_pack4)
+template <bool FULL> __device__ __forceinline__ float2 requant2_biased_f(int a0, int a1, float z0, float z1, float s0, float s1, float lo, float hi) {
     const float2 f = fadd2(make_float2(__int_as_float(a0), __int_as_float(a1)), make_float2(-12582912.0f, -12582912.0f));
     const float2 t = fadd2(make_float2(z0, z1), make_float2(__fmul_rn(s0, f.x), __fmul_rn(s1, f.y)));
-    const float2 r = fadd2(t, make_float2(round_bias(t.x), round_bias(t.y)));
-    y0 = round_sat_s8<FULL>(r.x, lo, hi);
-    y1 = round_sat_s8<FULL>(r.y, lo, hi);
+    float2 r = fadd2(t, make_float2(round_bias(t.x), round_bias(t.y)));
+    if (!FULL) { r.x = fminf(fmaxf(r.x, lo), hi); r.y = fminf(fmaxf(r.y, lo), hi); }
+    return r;
 }
 template <bool FULL> __device__ __forceinline__ uint32_t requant4_biased(int a0, int a1, int a2, int a3, float4 z, float4 s, float lo, float hi) {
-    int y0, y1, y2, y3;
-    requant2_biased<FULL>(a0, a1, z.x, z.y, s.x, s.y, lo, hi, y0, y1);
-    requant2_biased<FULL>(a2, a3, z.z, z.w, s.z, s.w, lo, hi, y2, y3);
-    return pack4(y0, y1, y2, y3);
+    const float2 r01 = requant2_biased_f<FULL>(a0, a1, z.x, z.y, s.x, s.y, lo, hi);
+    const float2 r23 = requant2_biased_f<FULL>(a2, a3, z.z, z.w, s.z, s.w, lo, hi);
+    return f2i_pack4(r01.x, r01.y, r23.x, r23.y);
 }
 
 // same packed adds for accumulators of any magnitude (I2F on the XU pipe instead of the bias trick); full int8 clamp only
@@ -130,7 +150,21 @@ __device__ __forceinline__ uint32_t requant4_i2f(int a0, int a1, int a2, int a3,
     const float2 t23 = fadd2(make_float2(z.z, z.w), make_float2(__fmul_rn(s.z, __int2float_rn(a2)), __fmul_rn(s.w, __int2float_rn(a3))));
     const float2 r01 = fadd2(t01, make_float2(round_bias(t01.x), round_bias(t01.y)));
     const float2 r23 = fadd2(t23, make_float2(round_bias(t23.x), round_bias(t23.y)));
-    return pack4(round_sat_s8<true>(r01.x, 0.f, 0.f), round_sat_s8<true>(r01.y, 0.f, 0.f), round_sat_s8<true>(r23.x, 0.f, 0.f), round_sat_s8<true>(r23.y, 0.f, 0.f));
+    return f2i_pack4(r01.x, r01.y, r23.x, r23.y);
+}
+
+// general form: any clamp range [lo, hi] inside the output type's range, int8 or uint8 outputs (u8 is a warp-uniform run-time flag),
+// accumulators of any magnitude (BIG: I2F on the now otherwise idle XU pipe; else the exact bias trick).  Same arithmetic as requant():
+// t = c0z + c1 * f32(acc); s = t + copysign(0.49999997, t); clamp; truncate.  ~8 issue slots per value less than requant_nx + pack4.
+template <bool BIG> __device__ __forceinline__ uint32_t requant4_clamp(int a0, int a1, int a2, int a3, float4 z, float4 s, float lo, float hi, bool u8) {
+    const float f0 = BIG ? __int2float_rn(a0) : i2f_exact<false>(a0), f1 = BIG ? __int2float_rn(a1) : i2f_exact<false>(a1);
+    const float f2 = BIG ? __int2float_rn(a2) : i2f_exact<false>(a2), f3 = BIG ? __int2float_rn(a3) : i2f_exact<false>(a3);
+    const float2 t01 = fadd2(make_float2(z.x, z.y), make_float2(__fmul_rn(s.x, f0), __fmul_rn(s.y, f1)));
+    const float2 t23 = fadd2(make_float2(z.z, z.w), make_float2(__fmul_rn(s.z, f2), __fmul_rn(s.w, f3)));
+    const float2 r01 = fadd2(t01, make_float2(round_bias(t01.x), round_bias(t01.y)));
+    const float2 r23 = fadd2(t23, make_float2(round_bias(t23.x), round_bias(t23.y)));
+    const float c0 = fminf(fmaxf(r01.x, lo), hi), c1 = fminf(fmaxf(r01.y, lo), hi), c2 = fminf(fmaxf(r23.x, lo), hi), c3 = fminf(fmaxf(r23.y, lo), hi);
+    return u8 ? f2i_pack4<true>(c0, c1, c2, c3) : f2i_pack4<false>(c0, c1, c2, c3);
 }
 
 // sign-extended byte k of a packed word: one PRMT (selector msb = replicate the sign of the selected byte)

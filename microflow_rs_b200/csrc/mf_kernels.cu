@@ -288,8 +288,7 @@ __global__ void __launch_bounds__(256) dwconv_c4_kernel(ConvArgs a, uint32_t wor
         }
         if (WZP) { acc0 -= wz.x * s0; acc1 -= wz.y * s1; acc2 -= wz.z * s2; acc3 -= wz.w * s3; }
         reinterpret_cast<uint32_t *>(a.out)[(size_t)b * words_per_sample + idx] =
-            pack4(requant_nx<false>(acc0 - kc.x, z.x, s.x, a.lo, a.hi), requant_nx<false>(acc1 - kc.y, z.y, s.y, a.lo, a.hi),
-                  requant_nx<false>(acc2 - kc.z, z.z, s.z, a.lo, a.hi), requant_nx<false>(acc3 - kc.w, z.w, s.w, a.lo, a.hi));
+            requant4_clamp<false>(acc0 - kc.x, acc1 - kc.y, acc2 - kc.z, acc3 - kc.w, z, s, a.lo, a.hi, U8);
     }
 }
 
@@ -397,6 +396,8 @@ __global__ void __launch_bounds__(128, 4) dwconv3x3_rows_kernel(ConvArgs a, uint
                 s += r2[k] * wi[6][k]; s += r2[4 + k] * wi[7][k]; s += r2[8 + k] * wi[8][k];
                 acc[k] = s;
             }
+            if (XU >= 4) *o = requant4_i2f(acc[0] - kc.x, acc[1] - kc.y, acc[2] - kc.z, acc[3] - kc.w, z, sc);      // full int8 clamp: I2F + packed F2IP
+            else
             *o = pack4(XU > 0 ? requant_xu<true>(acc[0] - kc.x, z.x, sc.x, lo, hi) : requant_nx<false>(acc[0] - kc.x, z.x, sc.x, lo, hi),
                        XU > 1 ? requant_xu<true>(acc[1] - kc.y, z.y, sc.y, lo, hi) : requant_nx<false>(acc[1] - kc.y, z.y, sc.y, lo, hi),
                        XU > 2 ? requant_xu<true>(acc[2] - kc.z, z.z, sc.z, lo, hi) : requant_nx<false>(acc[2] - kc.z, z.z, sc.z, lo, hi),

@@ -166,6 +166,21 @@ def test_sass_shows_the_blackwell_paths():
     assert dw and all("UBLKCP" in t and "IDP.4A" in t and "FADD2" in t for t in dw)
 
 
+def test_sass_packed_float_to_int8_conversion():
+    """f2i_pack4 (mf_device.cuh) relies on ptxas fusing {cvt.rzi.s32.f32 x2, cvt.pack.sat.s8.s32} into ONE F2IP.S8.F32.TRUNC.NTZ (two
+    values per instruction, not on the quarter-rate XU pipe).  If a toolchain stops doing that the epilogues silently fall back to
+    F2I.S32 + I2IP (five times the cost): pin it.  No XU-epilogue kernel may contain the old F2I.S8 either."""
+    funcs = _sass_by_function()
+    text = {n: "\n".join(b) for n, b in funcs.items()}
+    hot = {n: t for n, t in text.items()
+           if re.search(r"fused_chain_kernel|dwconv3x3_(smem|pair)_kernel|dwconv_cin1_(smem|taps)_kernel", n)
+           or re.search(r"(conv_tc_kernel|(?<!dw)conv3x3_pair_kernel)ILb[01]ELb1E", n)}      # XU = true instantiations
+    assert len(hot) >= 30, sorted(text)
+    for n, t in hot.items():
+        assert "F2IP.S8.F32.TRUNC.NTZ" in t, n
+        assert "F2I.S8" not in t and "I2IP" not in t, n
+
+
 def test_device_list_options_are_validated_without_a_gpu():
     """ABI 3: mf_options.n_devices / devices[].  A 20-byte ABI-2 struct (no device list) is still accepted; a list longer than
     MF_MAX_DEVICES is refused; with MF_FLAG_HOST_ONLY (parse + preprocess only) the device list is not consulted."""
