@@ -27,6 +27,8 @@ def run(torch, w, c0, c1, in_zp, out_zp, out_scale, H, W, batch, steps, warmup, 
     for i in range(warmup):
         fast.run_device(x[i & 1].data_ptr(), y.data_ptr(), batch, st)
     torch.cuda.synchronize()
+    from . import lib
+    res["kernel"] = lib().mf_op_kernel_name(fast._h).decode()      # what the launches above really ran (CTA-pair or one-CTA kernel)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
@@ -41,7 +43,7 @@ def run(torch, w, c0, c1, in_zp, out_zp, out_scale, H, W, batch, steps, warmup, 
     try:   # dram__bytes_read + write of one launch at batch 16 from the committed ncu capture (profiles/r02e_conv3x3.txt)
         import json
         from pathlib import Path
-        traffic = json.loads((Path(__file__).resolve().parent.parent / "profiles" / "traffic_latest.json").read_text()).get("conv_tc_kernel(3x3)") if batch == 16 else None
+        traffic = json.loads((Path(__file__).resolve().parent.parent / "profiles" / "traffic_latest.json").read_text()).get(res["kernel"]) if batch == 16 else None
     except Exception:
         traffic = None
     mma_only = 4423.0   # tools/ubench/mma_i8.cu on this pool's B200: tcgen05.mma kind::i8 M128 N128 K32 back to back, no TMA, no epilogue (profiles/r02d)

@@ -1412,6 +1412,7 @@ struct mf_op {
     LayerExec exec;
     uint8_t *d_blob = nullptr;
     int num_sms = 148;
+    const char *launched = nullptr;     // the kernel the most recent mf_op_run_device launched (static string)
 };
 
 int mf_op_conv_2d_create(const mf_conv_desc *d, mf_op **out) {
@@ -1444,9 +1445,10 @@ int mf_op_run_device(mf_op *op, const void *d_in, void *d_out, size_t batch, voi
     std::string err;
     cudaError_t e = op->exec.run((const uint8_t *)d_in, (uint8_t *)d_out, (long long)batch, op->num_sms, (cudaStream_t)stream, &err);
     if (e != cudaSuccess) return fail(MF_ERR_CUDA, std::string(kernel_name(op->exec.kernel)) + ": " + cudaGetErrorString(e) + " " + err);
+    op->launched = op->exec.launched_name((const uint8_t *)d_in, (uint8_t *)d_out, (long long)batch);
     return MF_OK;
 }
-const char *mf_op_kernel_name(const mf_op *op) { return op ? kernel_name(op->exec.kernel) : ""; }
+const char *mf_op_kernel_name(const mf_op *op) { return op ? (op->launched ? op->launched : kernel_name(op->exec.kernel)) : ""; }
 void mf_op_destroy(mf_op *op) {
     if (!op) return;
     if (op->d_blob) cudaFree(op->d_blob);

@@ -75,6 +75,7 @@ struct ConvTcParams {
     float lo, hi;
     uint32_t idesc, stage_bytes, b_block_bytes, tmem_cols, nkb;
     uint32_t stage_tx;          // bytes one stage's TMA load delivers (== stage_bytes unless the stage is padded to 1024)
+    int early;                  // release the accumulator right after tcgen05.ld (MF_TC_EARLY, default 1)
     int out_u8;                 // outputs are uint8 (F2IP.U8 in the general epilogue)
     uint32_t patch, patch_w;    // single-patch mode (ConvTcPlan::patch) and its patch width TW + KW - 1 in pixels
 };
@@ -143,7 +144,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     pdl_trigger();
 
     if (warp == kWarpTma) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== TMA producer =====
             mbar_expect_tx(bfull_bar, p.nkb * p.b_block_bytes);
             for (uint32_t kb = 0; kb < p.nkb; ++kb) tma_load_2d(smem_u32(sB + (size_t)kb * p.b_block_bytes), &tmap_b, bfull_bar, (int)(kb * 128), 0);
@@ -166,7 +167,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
         }
     } else if (warp == kWarpMma) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== MMA issuer =====
             mbar_wait(bfull_bar, 0);
             tc_fence_after();
@@ -288,6 +289,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     uint32_t r[32];
                     tmem_ld32(t_base + (uint32_t)c0, r);
                     if (PREBIAS) tmem_st32(t_base + (uint32_t)c0, kkr);     // re-arm the accumulator for the tile after next
+                    if (!PREBIAS && p.early && (ONE_CHUNK || c0 + 128 >= p.N)) {
+                        // the warp's last chunk of this accumulator is in registers: hand the buffer back BEFORE the math and the stores
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    }
                     uint32_t w[8];
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
@@ -329,9 +336,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                      : "memory");
                 }
                 if (PREBIAS) tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(acc));
+                if (PREBIAS || !p.early) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                }
             }
         };
         if (TAB == kTabGroup) {
@@ -429,7 +438,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     };
 
     if (warp == kWarpTma) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== TMA producer (both CTAs; transaction bytes are counted on the leader's barriers) =====
             const uint32_t l_bfull = mapa_rank(bfull_bar, 0);
             mbar_expect_tx_cluster(l_bfull, 9u * bblk);
@@ -450,7 +459,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
         }
     } else if (warp == kWarpMma) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0 && elect_one()) {
             // ===== MMA issuer (leader CTA only) =====
             mbar_wait(bfull_bar, 0);
             tc_fence_after();
@@ -510,6 +519,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             for (int c0 = 32 * cg; c0 < p.N; c0 += 128) {
                 uint32_t r[32];
                 tmem_ld32(t_base + (uint32_t)c0, r);
+                if (p.early && c0 + 128 >= p.N) {          // the accumulator is in registers: release it before the math (as in conv_tc_kernel)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));
+                }
                 uint32_t w[8];
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
@@ -529,9 +543,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                  "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                                  : "memory");
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));      // the leader's MMA thread counts both CTAs' epilogue warps
+            if (!p.early) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(acc), 0));      // the leader's MMA thread counts both CTAs' epilogue warps
+            }
         }
     }
 
@@ -740,6 +756,8 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     k.stage_bytes = p.patch ? ((k.stage_tx + 1023u) & ~1023u) : k.stage_tx;      // every stage base stays 1024-byte aligned (swizzle atom)
     k.patch = p.patch ? 1u : 0u;
     k.out_u8 = p.is_u8 ? 1 : 0;
+    static const int env_early = [] { const char *e = std::getenv("MF_TC_EARLY"); return e ? std::atoi(e) : 1; }();
+    k.early = env_early;
     k.patch_w = (uint32_t)(p.TW + p.KW - 1);
     k.b_block_bytes = (uint32_t)(p.N * 128);
     k.nkb = (uint32_t)(p.KH * p.KW * p.CB);
@@ -796,11 +814,11 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
             attr_done.emplace_back(dev, fn);
         }
     }
-    // 3x3 layers on CTA pairs (conv3x3_pair_kernel) with MF_TC_PAIR=1.  Measured equal to the one-CTA kernel on BASELINE config 5
-    // (0.0900 vs 0.0894 ms at batch 16, profiles/r02d_conv3x3_experiments.txt): the layer is bound by its epilogue, not by the
-    // shared-memory reads the pair halves -- so the simpler kernel stays the default and this one is kept, tested, for layers whose
-    // weights do not fit one SM (Cout = 256: 288 KB) and as the basis of the next step named in DESIGN.md.
-    static const int env_pair = [] { const char *e = std::getenv("MF_TC_PAIR"); return e ? std::atoi(e) : 0; }();
+    // 3x3 layers run on CTA pairs (conv3x3_pair_kernel) unless MF_TC_PAIR=0.  Until the MMA issue loop was fixed (elect_one) and the
+    // accumulators were released right after tcgen05.ld, the pair kernel only equalled the one-CTA kernel (0.0900 vs 0.0894 ms on
+    // BASELINE config 5); now its halved B-operand traffic and six pipeline stages show: 0.0819 vs 0.0879 ms at batch 16, 0.156 vs
+    // 0.168 ms at batch 32 (profiles/r02g_conv3x3_experiments.txt).  The one-CTA kernel remains for odd shapes and single tiles.
+    static const int env_pair = [] { const char *e = std::getenv("MF_TC_PAIR"); return e ? std::atoi(e) : 1; }();
     if (env_pair && shape == 1 && p.pair_ok && p.patch && k.num_tiles >= 2 && num_sms >= 2) {
         KernelFn pf = p.big_acc ? (xu ? conv3x3_pair_kernel<true, true> : conv3x3_pair_kernel<true, false>)
                                 : (xu ? conv3x3_pair_kernel<false, true> : conv3x3_pair_kernel<false, false>);

@@ -279,7 +279,7 @@ const char *LayerExec::launched_name(const uint8_t *in, uint8_t *out, long long 
         if (!no_smem && kernel == Kernel::DwConvCin1 && dwconv_cin1_taps_eligible(a)) return "dwconv_cin1_taps_kernel";
     }
     if (kernel == Kernel::ConvTc3x3) {
-        static const bool pair = [] { const char *e = std::getenv("MF_TC_PAIR"); return e && std::atoi(e) != 0; }();
+        static const bool pair = [] { const char *e = std::getenv("MF_TC_PAIR"); return !e || std::atoi(e) != 0; }();
         if (pair && tc.pair_ok && tc.patch && (long long)batch * ((spec.OH + tc.TH - 1) / tc.TH) * ((spec.OW + tc.TW - 1) / tc.TW) >= 2) return "conv3x3_pair_kernel";
     }
     return kernel_name(kernel);

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kTeams * 32 * kTeamWarps, 1) fused_chain_kerne
             team_sync(team, kTeamThreads);
 
             // ================= pointwise 1x1: tcgen05.mma, A (smem) x W^T (smem) -> TMEM =================
-            if (tt == 0) {
+            if (tw == 0 && elect_one()) {     // elect.sync, not `tt == 0`: the MMAs are then issued back to back (mf_tc_ptx.cuh)
                 if (last && u + ustride < p.n_units) request_unit(u + ustride);   // X is free: the last depthwise of this unit has read it
                 if (!weights_ready) { mbar_wait(wbar, 0); weights_ready = true; }
                 tc_fence_after();

@@ -21,6 +21,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // Bounded wait: a protocol bug must trap (launch failure) instead of hanging the GPU.  try_wait suspends the thread in
 // hardware for up to the hinted time, so waiting warps do not burn issue slots that the working warps need.
+// One thread of the (converged) warp, chosen by elect.sync.  Unlike `lane == 0`, the compiler knows the elected region runs on a single
+// thread, so tcgen05.mma / cp.async.bulk.tensor (uniform-register operands) are emitted straight, not wrapped in a per-instruction
+// ELECT / BRA.U.ANY serialisation loop (~10 SASS instructions per MMA with lane == 0: the MMA issue rate then bounds a K = 1152 tile).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spins = 0;; ++spins) {

@@ -53,7 +53,7 @@ def main():
             got = mf.ops.conv_2d(x, in_zp, w, [0], 0.0235294, -128, act, "same", (1, 1), c0, c1, (H, W), impl=0)
             kern = mf.ops.last_kernel
             import os
-            pair_expected = os.environ.get("MF_TC_PAIR") == "1" and Cin == 128 and Cout % 64 == 0 and B * (-(-H // 16)) * (-(-W // 8)) >= 2
+            pair_expected = os.environ.get("MF_TC_PAIR", "1") != "0" and Cin == 128 and Cout % 64 == 0 and B * (-(-H // 16)) * (-(-W // 8)) >= 2
             if ("conv3x3_pair_kernel" in kern) != pair_expected or ("conv_tc" not in kern and "conv3x3_pair" not in kern):
                 res["error"] = f"shape {(B, H, W, Cin, Cout)} ran on {kern}"
                 print(json.dumps(res)); return

@@ -24,11 +24,12 @@ def test_tc_pointwise_packed_gemm():
 
 
 def test_tc_conv3x3_implicit_gemm():
-    _run("conv3x3")
+    """The one-CTA 3x3 kernel (MF_TC_PAIR=0; the default runs eligible shapes on CTA pairs, next test)."""
+    _run("conv3x3", env={"MF_TC_PAIR": "0"})
 
 
 def test_tc_conv3x3_on_cta_pairs():
-    """MF_TC_PAIR=1: the same shapes through conv3x3_pair_kernel (thread-block clusters of 2, tcgen05.mma.cta_group::2, weights split by
+    """Default (MF_TC_PAIR=1): the same shapes through conv3x3_pair_kernel (thread-block clusters of 2, tcgen05.mma.cta_group::2, weights split by
     output channel between the two CTAs); tc_check asserts that the eligible shapes really ran on it."""
     _run("conv3x3", env={"MF_TC_PAIR": "1"})
 
@@ -56,7 +57,7 @@ def test_config5_full_size_image_vs_oracle():
     c0 = r.uniform(-4, 4, C).astype(np.float32)
     x = splitmix_bytes(seed + 1, H * W * C).reshape(1, H, W, C)
     got = mf.ops.conv_2d(x, -128, w, [0], 0.0235294, -128, "relu6", "same", (1, 1), c0, c1, (H, W), impl=0)
-    assert "conv_tc_kernel" in mf.ops.last_kernel
+    assert "conv3x3_pair_kernel" in mf.ops.last_kernel or "conv_tc_kernel" in mf.ops.last_kernel
     strips = [(a, min(H, a + 16)) for a in range(0, H, 16)]
 
     def strip(ab):

@@ -36,7 +36,9 @@ if has prof; then
       python tools/layer_bench.py 8192 L14_pw128 > gpurun_out/ncu_tc128.log 2>&1
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:fused_chain -s 3 -c 1 -f -o gpurun_out/prof_fused \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-conv2d > gpurun_out/ncu_fused.log 2>&1
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 5 -c 1 -f -o gpurun_out/prof_conv3x3 \
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv3x3_pair -s 5 -c 1 -f -o gpurun_out/prof_conv3x3_pair \
+      python -m microflow_rs_b200._convbench 16 4 > gpurun_out/ncu_conv3x3_pair.log 2>&1
+  MF_TC_PAIR=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 5 -c 1 -f -o gpurun_out/prof_conv3x3 \
       python -m microflow_rs_b200._convbench 16 4 > gpurun_out/ncu_conv3x3.log 2>&1
 fi
 tail -n 4 gpurun_out/t_tc.log gpurun_out/t_ops.log gpurun_out/t_models.log gpurun_out/t_multi.log gpurun_out/t_fused.log gpurun_out/smoke.log 2>/dev/null

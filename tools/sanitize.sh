@@ -35,6 +35,11 @@ c1 = (r.uniform(0.2, 2.0, 128) / 40000.0).astype(np.float32); c0 = r.uniform(-20
 a3 = mf.ops.conv_2d(x3, -128, w3, [0], 0.0235294, -128, "relu6", "same", (1, 1), c0, c1, (24, 16), impl=0)
 assert "conv3x3_pair_kernel" in mf.ops.last_kernel, mf.ops.last_kernel
 assert np.array_equal(a3, mf.ops.conv_2d(x3, -128, w3, [0], 0.0235294, -128, "relu6", "same", (1, 1), c0, c1, (24, 16), impl=1))
+# the one-CTA 3x3 kernel (Cout = 32 is not splittable over a CTA pair)
+w4 = r.integers(-128, 128, (32, 3, 3, 128)).astype(np.int8)
+a4 = mf.ops.conv_2d(x3, -128, w4, [0], 0.0235294, -128, "relu6", "same", (1, 1), c0[:32], c1[:32], (24, 16), impl=0)
+assert "conv_tc_kernel" in mf.ops.last_kernel, mf.ops.last_kernel
+assert np.array_equal(a4, mf.ops.conv_2d(x3, -128, w4, [0], 0.0235294, -128, "relu6", "same", (1, 1), c0[:32], c1[:32], (24, 16), impl=1))
 os.environ["MF_ALLOW_DUPLICATE_DEVICES"] = "1"
 g = mf.Model(MODELS / "speech.tflite", devices=[0, 0])
 one = mf.Model(MODELS / "speech.tflite")

@@ -11,10 +11,10 @@
 #include <cstdlib>
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr) {     // K-major, SWIZZLE_128B, SBO = 1024 (see mf_tc_ptx.cuh)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo = 1024) {     // K-major, SWIZZLE_128B, SBO = 1024 (see mf_tc_ptx.cuh)
     uint64_t d = (uint64_t)((addr >> 4) & 0x3FFFu);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)(sbo >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
@@ -26,12 +26,12 @@ __device__ __forceinline__ void mma_i8(uint32_t d, uint64_t a, uint64_t b, uint3
 // LD_WARPS > 0: that many extra warps (4 per TMEM lane quarter) read the accumulators with tcgen05.ld.32x32b.x32 in a loop while the
 // MMAs run -- does epilogue-style TMEM traffic slow the tensor pipe (and how fast are the loads under MMA load)?
 template <int N, int LD_WARPS>
-__global__ void __launch_bounds__(128 + 32 * LD_WARPS, 1) mma_kernel(int iters, long long *cycles, unsigned *sink, unsigned long long *ld_count) {
+__global__ void __launch_bounds__(128 + 32 * LD_WARPS, 1) mma_kernel(int iters, long long *cycles, unsigned *sink, unsigned long long *ld_count, uint32_t a_off, uint32_t sbo, int chain) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar[8];
     __shared__ uint32_t tmem_slot;
-    uint8_t *sA = smem, *sB = smem + 16384;
-    for (int i = threadIdx.x; i < (16384 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x01010101u * (uint32_t)(i & 3);
+    uint8_t *sA = smem, *sB = smem + 32768;      // A region 32 KB: room for shifted / strided views
+    for (int i = threadIdx.x; i < (32768 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x01010101u * (uint32_t)(i & 3);
     const uint32_t bar_a = smem_u32(&bar[0]);
     if (threadIdx.x == 0) {
         reinterpret_cast<volatile unsigned *>(&bar[3])[4] = 0;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(128 + 32 * LD_WARPS, 1) mma_kernel(int iters, 
     const uint32_t tmem = tmem_slot;
     if (threadIdx.x == 0) {
         const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-        const uint64_t da = make_desc(smem_u32(sA)), db = make_desc(smem_u32(sB));
+        const uint64_t da = make_desc(smem_u32(sA) + a_off, sbo), db = make_desc(smem_u32(sB));
         // batch `it` of 64 instructions commits to barrier it & 3 (phase (it >> 2) & 1); batch it - 2 is awaited before batch it + 1 is
         // issued, so three batches are in flight and a barrier never completes a phase that has not been waited for
         auto wait_batch = [&](int b) {
@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(128 + 32 * LD_WARPS, 1) mma_kernel(int iters, 
         const long long t0 = clock64();
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
-            for (int k = 0; k < 64; ++k) mma_i8(tmem + (uint32_t)((k >> 2) & 1) * N, da + 2 * (k & 3), db + 2 * (k & 3), idesc, (uint32_t)(k & 3));
+            for (int k = 0; k < 64; ++k)       // chain: all 64 MMAs of a batch accumulate into ONE accumulator (a long K loop), else 4 per accumulator
+                mma_i8(tmem + (uint32_t)(chain ? (it & 1) : ((k >> 2) & 1)) * N, da + 2 * (k & 3), db + 2 * (k & 3), idesc, chain ? (uint32_t)(k != 0) : (uint32_t)(k & 3));
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_a + 8u * (uint32_t)(it & 3)) : "memory");
             if (it >= 2) wait_batch(it - 2);
         }
@@ -95,26 +96,26 @@ __global__ void __launch_bounds__(128 + 32 * LD_WARPS, 1) mma_kernel(int iters, 
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
-template <int N, int LD_WARPS> static void run(int iters, int sms) {
+template <int N, int LD_WARPS> static void run(int iters, int sms, uint32_t a_off = 0, uint32_t sbo = 1024, int chain = 0) {
     long long *cyc;
     unsigned *sink;
     unsigned long long *ldc;
     cudaMalloc(&cyc, sms * sizeof(long long));
     cudaMalloc(&sink, 4);
     cudaMalloc(&ldc, 8);
-    const size_t smem = 16384 + (size_t)N * 128;
+    const size_t smem = 32768 + (size_t)N * 128;
     cudaFuncSetAttribute(mma_kernel<N, LD_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    mma_kernel<N, LD_WARPS><<<sms, 128 + 32 * LD_WARPS, smem>>>(iters / 8 + 1, cyc, sink, ldc);
+    mma_kernel<N, LD_WARPS><<<sms, 128 + 32 * LD_WARPS, smem>>>(iters / 8 + 1, cyc, sink, ldc, a_off, sbo, chain);
     cudaDeviceSynchronize();
     float best = 1e30f;
     unsigned long long loads = 0;
     for (int rep = 0; rep < 5; ++rep) {
         cudaMemset(ldc, 0, 8);
         cudaEventRecord(e0);
-        mma_kernel<N, LD_WARPS><<<sms, 128 + 32 * LD_WARPS, smem>>>(iters, cyc, sink, ldc);
+        mma_kernel<N, LD_WARPS><<<sms, 128 + 32 * LD_WARPS, smem>>>(iters, cyc, sink, ldc, a_off, sbo, chain);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms;
@@ -125,7 +126,7 @@ template <int N, int LD_WARPS> static void run(int iters, int sms) {
     long long c0 = 0;
     cudaMemcpy(&c0, cyc, sizeof c0, cudaMemcpyDeviceToHost);
     const double ops = 2.0 * 128.0 * N * 32.0 * 64.0 * iters * sms;
-    printf("tcgen05.mma.cta_group::1.kind::i8 M128 N%-3d K32, %2d warps of tcgen05.ld: %8.3f ms -> %8.1f TOP/s  (%.1f clk per MMA on SM 0", N, LD_WARPS, best,
+    printf("tcgen05.mma.cta_group::1.kind::i8 M128 N%-3d K32, %2d warps of tcgen05.ld, A start +%u B, SBO %u%s: %8.3f ms -> %8.1f TOP/s  (%.1f clk per MMA on SM 0", N, LD_WARPS, a_off, sbo, chain ? ", one accumulator per 64" : "", best,
            ops / (best * 1e-3) / 1e12, (double)c0 / (64.0 * iters));
     if (LD_WARPS) printf("; %.1f clk per 32x32 tcgen05.ld per warp", (double)c0 * LD_WARPS / ((double)loads / sms));
     printf(", %s)\n", cudaGetErrorString(e));
@@ -142,5 +143,10 @@ int main(int argc, char **argv) {
     run<256, 0>(iters, p.multiProcessorCount);
     run<128, 4>(iters, p.multiProcessorCount);
     run<128, 16>(iters, p.multiProcessorCount);
+    // the 3x3 kernel's single-patch A views: 8-row groups patch_w * 128 B apart, tap (m, n) starts (m * patch_w + n) * 128 B into the patch
+    run<128, 0>(iters, p.multiProcessorCount, 0, 1024, 1);
+    run<128, 0>(iters, p.multiProcessorCount, 128, 1024, 0);
+    run<128, 0>(iters, p.multiProcessorCount, 0, 1280, 0);
+    run<128, 0>(iters, p.multiProcessorCount, 1280 + 256, 1280, 1);
     return 0;
 }
