@@ -203,7 +203,7 @@ def conv2d_roofline(torch, mf, peaks, steps, warmup, batch=16):
     # drive the op through a one-layer engine object (private helper of the package keeps device buffers resident)
     from microflow_rs_b200 import _convbench
     return _convbench.run(torch, w, c0, c1, in_zp=-128, out_zp=-128, out_scale=0.0235294, H=H, W=W, batch=batch, steps=steps, warmup=warmup,
-                          peaks=peaks, seed=seed)
+                          peaks=peaks, seed=seed, clock_sampler=ClockSampler(torch.cuda.current_device()))
 
 
 def verify_ranks(dist, torch, m, wl, rank, world, batch):

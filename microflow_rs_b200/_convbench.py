@@ -5,7 +5,7 @@ import numpy as np
 from . import ConvOp
 
 
-def run(torch, w, c0, c1, in_zp, out_zp, out_scale, H, W, batch, steps, warmup, peaks, seed):
+def run(torch, w, c0, c1, in_zp, out_zp, out_scale, H, W, batch, steps, warmup, peaks, seed, clock_sampler=None):
     Cout, _, _, Cin = w.shape
     fast = ConvOp((H, W, Cin), in_zp, w, [0], out_scale, out_zp, "relu6", "same", (1, 1), c0, c1, (H, W), impl=0)
     res = {"workload": f"synthetic Conv2D {H}x{W}x{Cin}->{Cout} k3 s1 SAME int8 ReLU6, batch {batch} (BASELINE configs[4])", "kernel": fast.kernel}
@@ -36,6 +36,25 @@ def run(torch, w, c0, c1, in_zp, out_zp, out_scale, H, W, batch, steps, warmup, 
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    # SM clock under THIS kernel: the timed region is a millisecond, so sample NVML over ~0.3 s of the same launches right after it.
+    # (The 3x3 kernel keeps tensor pipe, TMA and HBM busy at once and runs power-capped well below the 1965 MHz the network step holds.)
+    clocks = None
+    if clock_sampler is not None:
+        import time
+        cs = clock_sampler
+        cs.start()
+        cs.window(True)
+        t_end = time.perf_counter() + 0.3
+        i = 0
+        while time.perf_counter() < t_end:
+            for _ in range(50):
+                fast.run_device(x[i & 1].data_ptr(), y.data_ptr(), batch, st)
+                i += 1
+            torch.cuda.synchronize()
+        cs.window(False)
+        c = cs.stop()
+        clocks = {"sm_mhz": c.get("sm_mhz"), "sm_max_mhz": c.get("sm_max_mhz"), "reasons": c.get("reasons"), "samples": c.get("samples"),
+                  "what": "NVML samples over 0.3 s of the same back-to-back launches, untimed, right after the timed region"}
     ops = 2.0 * fast.macs * batch
     tops = ops / (ms * 1e-3) / 1e12
     peak = 2.0 * peaks["bf16_tflops"]
@@ -51,7 +70,12 @@ def run(torch, w, c0, c1, in_zp, out_zp, out_scale, H, W, batch, steps, warmup, 
                 "roofline": {"bound": "tensor", "achieved": tops, "peak": peak, "unit": "TOP/s", "frac": tops / peak, "traffic": traffic,
                              "peak_source": "2 x measured cuBLAS bf16 burst TFLOP/s (tcgen05 kind::i8 issues 2x the bf16 MAC rate); nominal dense int8 is 4500; "
                                             "the MMA-only ceiling of this instruction shape measured by tools/ubench/mma_i8.cu is 4423 TOP/s",
-                             "frac_of_nominal_4500": tops / 4500.0, "frac_of_mma_only_ceiling_4423": tops / mma_only},
+                             "frac_of_nominal_4500": tops / 4500.0, "frac_of_mma_only_ceiling_4423": tops / mma_only,
+                             # the same ceiling in CYCLES (66.9 clk per M128 N128 K32 instruction, profiles/r02g_mma_i8_views.txt) at the SM clock
+                             # this kernel sustains: separates what the kernel loses from what the power cap takes
+                             "mma_only_ceiling_at_sampled_clock": (148 * 2.0 * 128 * 128 * 32 / 66.9 * clocks["sm_mhz"] * 1e6 / 1e12) if clocks and clocks.get("sm_mhz") else None,
+                             "frac_of_mma_only_ceiling_at_sampled_clock": (tops / (148 * 2.0 * 128 * 128 * 32 / 66.9 * clocks["sm_mhz"] * 1e6 / 1e12)) if clocks and clocks.get("sm_mhz") else None},
+                "clocks": clocks,
                 "l2": f"input+output per launch {(x[0].numel() + y.numel()) / 1e6:.0f} MB > 126 MB L2; inputs alternate between 2 buffers",
                 "algorithmic_bytes_per_launch": int(x[0].numel() + y.numel() + fast.weight_bytes)})
     fast.close()
@@ -80,7 +104,7 @@ def main():
     c1 = r.uniform(1e-3, 1e-2, Cout).astype(np.float32)
     c0 = r.uniform(-4, 4, Cout).astype(np.float32)
     print(json.dumps(run(torch, w, c0, c1, in_zp=-128, out_zp=-128, out_scale=0.0235294, H=H, W=W, batch=batch, steps=steps, warmup=3, peaks=peaks,
-                         seed=seed)))
+                         seed=seed, clock_sampler=bench.ClockSampler(0))))
 
 
 if __name__ == "__main__":
