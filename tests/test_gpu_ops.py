@@ -277,6 +277,52 @@ def test_requant_saturation_and_large_accumulators():
         np.testing.assert_array_equal(got, want)
 
 
+# kernels whose requantize epilogue converts with the packed F2IP (mf_device.cuh f2i_pack4): accumulators are made EXACTLY 2 * x by a
+# filter that is 2 at one tap and 0 elsewhere, and the per-channel constants walk through exact .5 ties of both signs (c1 = 0.25 ->
+# t = c0 + x / 2), integers, quarter steps, saturation at both ends, huge offsets and vanishing scales.
+TIE_CASES = [
+    # B, H, W, Cin, Cout, KH, KW, stride, depthwise, act, kernel
+    (3, 24, 24, 32, 32, 1, 1, 1, False, "none", "conv_tc"),                      # tcgen05 pointwise, packed pixels, pre-biased accumulators
+    (3, 24, 24, 32, 32, 1, 1, 1, False, "relu6", "conv_tc"),                     # clamp narrower than int8: requant4_clamp
+    (9, 6, 6, 128, 128, 1, 1, 1, False, "none", "conv_tc"),
+    (2, 16, 16, 128, 128, 3, 3, 1, False, "none", "conv3x3_pair|conv_tc"),       # tcgen05 3x3 on CTA pairs (the I2F variant of the epilogue is
+                                                                                 # covered by test_config5_full_size_image_vs_oracle)
+    (300, 12, 12, 16, 16, 3, 3, 1, True, "none", "dwconv3x3_pair"),
+    (300, 12, 12, 16, 16, 3, 3, 2, True, "none", "dwconv3x3_smem"),
+    (300, 12, 12, 16, 16, 3, 3, 1, True, "relu", "dwconv3x3_pair"),              # FULL = false epilogue
+    (300, 32, 32, 1, 8, 3, 3, 2, True, "none", "dwconv_cin1_smem"),
+    (3, 12, 12, 8, 8, 3, 3, 1, True, "none", "dwconv3x3_rows"),
+]
+
+
+@pytest.mark.parametrize("case", TIE_CASES)
+def test_epilogue_ties_and_saturation_on_fast_kernels(case):
+    import re
+    B, H, W, Cin, Cout, KH, KW, st, dw, act, kname = case
+    r = rng(zlib.crc32(repr(case).encode()))
+    x = r.integers(-128, 128, (B, H, W, Cin)).astype(np.int8)
+    x[0, 0, 0, :] = 127
+    x[0, 0, 1 % W, :] = -128
+    if dw:
+        w = np.zeros((1, KH, KW, Cout), np.int8)
+        w[0, KH // 2, KW // 2, :] = 2
+    else:
+        w = np.zeros((Cout, KH, KW, Cin), np.int8)
+        for n in range(Cout):
+            w[n, KH // 2, KW // 2, n % Cin] = 2
+    c1v = [0.25, 0.25, 0.25, 0.125, 0.75, 1.0, 64.0, 1e-3, 0.5, 0.375, 0.25, 3.0e38 / 256, 0.0, 0.24999999, 0.25000003, 0.5]
+    c0v = [0.0, 0.5, -0.5, 0.25, 0.125, 0.0, 0.0, 0.499, -63.5, 64.5, 1e9, 0.0, -0.5, 0.0, 0.0, -1e9]
+    c1 = np.array([c1v[n % 16] for n in range(Cout)], np.float32)
+    c0 = np.array([c0v[n % 16] for n in range(Cout)], np.float32)
+    OH, OW = -(-H // st), -(-W // st)
+    args = (x, 0, w, [0], np.float32(0.0235294), -3 if act == "none" else -128, act, "same", (st, st), c0, c1, (OH, OW))
+    got = mf.ops.conv_2d(*args, depthwise=dw, impl=0)
+    assert re.search(kname, mf.ops.last_kernel), mf.ops.last_kernel
+    want = np.stack([oracle.conv_2d(x[b], *args[1:], depthwise=dw) for b in range(min(B, 4))])
+    np.testing.assert_array_equal(got[:min(B, 4)], want)
+    np.testing.assert_array_equal(mf.ops.conv_2d(*args, depthwise=dw, impl=1), got)       # every sample against the generic kernel
+
+
 @pytest.mark.parametrize("K,N,B,wzp,dtype", [(1, 16, 5, 0, np.int8), (16, 16, 7, 0, np.int8), (16, 1, 3, 0, np.int8), (4000, 4, 9, 0, np.int8),
                                               (37, 5, 4, 22, np.int8), (64, 8, 6, -7, np.int8), (48, 3, 4, 9, np.uint8)])
 def test_fully_connected_vs_oracle(K, N, B, wzp, dtype):
