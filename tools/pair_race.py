@@ -1,3 +1,5 @@
+"""One launch of conv3x3_pair_kernel checked against the generic kernel: the smallest workload for compute-sanitizer runs on the
+CTA-pair path (`compute-sanitizer --tool racecheck python tools/pair_race.py`; see profiles/r02g_conv3x3_experiments.txt, item 4)."""
 import sys, os
 from pathlib import Path
 import numpy as np
