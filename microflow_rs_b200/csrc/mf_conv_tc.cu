@@ -75,6 +75,7 @@ struct ConvTcParams {
     float lo, hi;
     uint32_t idesc, stage_bytes, b_block_bytes, tmem_cols, nkb;
     uint32_t stage_tx;          // bytes one stage's TMA load delivers (== stage_bytes unless the stage is padded to 1024)
+    uint32_t acc_mask, acc_shift;   // TMEM accumulator ring: nacc = acc_mask + 1 = 1 << acc_shift buffers (2, or 4 when 4 N <= 512 and MF_TC_NACC=4)
     int early;                  // release the accumulator right after tcgen05.ld (MF_TC_EARLY, default 1)
     int out_u8;                 // outputs are uint8 (F2IP.U8 in the general epilogue)
     uint32_t patch, patch_w;    // single-patch mode (ConvTcPlan::patch) and its patch width TW + KW - 1 in pixels
@@ -126,7 +127,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == kWarpMma && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(bfull_bar, 1);
-        for (uint32_t a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
+        for (uint32_t a = 0; a < 4; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kWarpAlloc) {
@@ -178,7 +179,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t stage16 = p.stage_bytes >> 4, bblk16 = p.b_block_bytes >> 4, arow16 = (uint32_t)p.TW * 8u;   // TW rows * 128 B / 16
             if (a0 + (uint32_t)p.stages * stage16 >= (1u << 14) || b0 + p.nkb * bblk16 >= (1u << 14)) __trap();     // descriptor start field would overflow
             for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+                const uint32_t acc = it & p.acc_mask, aph = (it >> p.acc_shift) & 1;
                 mbar_wait(tempty_bar(acc), PREBIAS ? aph : (aph ^ 1));     // PREBIAS: phase 0 of each buffer is the epilogue warps' initial fill
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.N;
@@ -260,7 +261,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const size_t lin_bytes = (size_t)lin_step * (size_t)p.N;
             const uint32_t ntiles = (uint32_t)p.num_tiles;
             for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+                const uint32_t acc = it & p.acc_mask, aph = (it >> p.acc_shift) & 1;
                 bool valid;
                 const int32_t *corr = s_corr;
                 uint8_t *orow;
@@ -411,7 +412,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == kWarpMma && lane == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
         mbar_init(bfull_bar, 2);
-        for (uint32_t a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kEpiWarps); }
+        for (uint32_t a = 0; a < 4; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kWarpAlloc) {
@@ -469,7 +470,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t a0 = smem_u32(sA) >> 4, b0 = smem_u32(sB) >> 4;
             const uint32_t stage16 = p.stage_bytes >> 4, bblk16 = bblk >> 4;
             for (uint32_t t = pair; 2u * t < ntiles; t += npairs, ++it) {
-                const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+                const uint32_t acc = it & p.acc_mask, aph = (it >> p.acc_shift) & 1;
                 mbar_wait(tempty_bar(acc), aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.N;
@@ -502,7 +503,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         pdl_wait();
         uint32_t it = 0;
         for (uint32_t t = pair; 2u * t < ntiles; t += npairs, ++it) {
-            const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+            const uint32_t acc = it & p.acc_mask, aph = (it >> p.acc_shift) & 1;
             bool tvalid;
             const uint32_t tile = tile_of(t, tvalid);
             uint32_t b, rem, ty, tx;
@@ -761,9 +762,16 @@ cudaError_t conv_tc_launch(const ConvTcPlan &p, const ConvTcLaunch &l, int num_s
     k.patch_w = (uint32_t)(p.TW + p.KW - 1);
     k.b_block_bytes = (uint32_t)(p.N * 128);
     k.nkb = (uint32_t)(p.KH * p.KW * p.CB);
-    // TMEM accumulator ring: two buffers.  Four (they fit the 512 columns when N <= 128) were measured no faster -- config 5: 0.1010
-    // vs 0.1000 ms; person_detect 1.058 vs 1.057 ms/step (profiles/r01j_conv3x3_experiments.txt) -- and were removed again.
-    const uint32_t need_cols = 2u * (uint32_t)p.N;
+    // TMEM accumulator ring: four buffers where they fit the 512 columns (N <= 128), else two.  Round 1 measured four no faster (config 5:
+    // 0.1010 vs 0.1000 ms, profiles/r01j_conv3x3_experiments.txt) -- the MMA issue loop was the limiter then.  With elect.sync issuers and the
+    // early accumulator release: CTA-pair kernel 0.0794 -> 0.0777 ms at batch 16, 0.1509 -> 0.1492 at batch 32; one-CTA kernel and the
+    // person_detect step unchanged (profiles/r02g_conv3x3_experiments.txt).  MF_TC_NACC=2 restores two.
+    static const int env_nacc = [] { const char *e = std::getenv("MF_TC_NACC"); return e ? std::atoi(e) : 4; }();
+    static const bool env_prebias = [] { const char *e = std::getenv("MF_TC_PREBIAS"); return e && std::atoi(e) != 0; }();      // its initial fill arms two buffers
+    const uint32_t nacc = (env_nacc == 4 && !env_prebias && 4u * (uint32_t)p.N <= 512u) ? 4u : 2u;
+    k.acc_mask = nacc - 1;
+    k.acc_shift = nacc == 4 ? 2 : 1;
+    const uint32_t need_cols = nacc * (uint32_t)p.N;
     k.tmem_cols = need_cols <= 32 ? 32 : (need_cols <= 64 ? 64 : (need_cols <= 128 ? 128 : (need_cols <= 256 ? 256 : 512)));
     if (k.num_tiles <= 0) return cudaSuccess;
 
