@@ -166,6 +166,21 @@ def test_sass_shows_the_blackwell_paths():
     assert dw and all("UBLKCP" in t and "IDP.4A" in t and "FADD2" in t for t in dw)
 
 
+def test_sass_tensor_core_issue_is_not_serialised():
+    """The MMA / TMA issuing thread is picked with elect.sync (tcptx::elect_one).  With `lane == 0` the compiler wraps every UTCIMMA and
+    UTMALDG in an ELECT / BRA.U.ANY loop (~10 extra instructions per MMA, profiles/r02g_conv3x3_experiments.txt): pin their absence."""
+    funcs = _sass_by_function()
+    tc = {n: b for n, b in funcs.items() if re.search(r"conv_tc_kernel|(?<!dw)conv3x3_pair_kernel", n)}
+    assert len(tc) >= 20
+    for n, body in tc.items():
+        assert not [ln for ln in body if "BRA.U.ANY" in ln], n
+    for n, body in funcs.items():
+        if "fused_chain_kernel" in n:          # its two remaining loops belong to the once-per-unit bulk copies, none to the MMAs
+            assert sum("BRA.U.ANY" in ln for ln in body) <= 2, n
+            mma = [i for i, ln in enumerate(body) if "UTCIMMA" in ln]
+            assert mma and not any("BRA.U.ANY" in ln for ln in body[mma[0]:mma[-1]]), n
+
+
 def test_sass_packed_float_to_int8_conversion():
     """f2i_pack4 (mf_device.cuh) relies on ptxas fusing {cvt.rzi.s32.f32 x2, cvt.pack.sat.s8.s32} into ONE F2IP.S8.F32.TRUNC.NTZ (two
     values per instruction, not on the quarter-rate XU pipe).  If a toolchain stops doing that the epilogues silently fall back to
